@@ -1,0 +1,149 @@
+/* b200fe -- C ABI of the B200 (sm_100a) acoustic front end: Kaldi-style 80-dim log-mel fbank
+ * + CMVN + SpecAugment masks + zero-padded batch layout, for gaochangfeng/lighting-asr (LASR).
+ *
+ * Every entry point replaces a piece of the reference's per-utterance CPU path; citations use
+ * R/ = the LASR checkout and TA: = torchaudio/compliance/kaldi.py (torchaudio 2.11.0), the
+ * library R/lasr/data/datatrans.py:75-102 delegates to.
+ *
+ * Conventions: all functions return 0 on success or a negative status (B200FE_E*); the text of
+ * the last failure on the calling thread is returned by b200fe_last_error().  Pointers named
+ * d_* are DEVICE pointers owned by the caller (e.g. the torch allocator); the library never
+ * allocates per call, never synchronises the stream and keeps no global state: a plan holds a
+ * few kB of read-only device tables and may be shared by any number of streams/threads.
+ * `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef B200FE_H
+#define B200FE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FE_OK 0
+#define B200FE_EINVAL (-1)      /* bad argument / unsupported option combination */
+#define B200FE_ECUDA (-2)       /* CUDA runtime error, see b200fe_last_error() */
+#define B200FE_ESHORT (-3)      /* an utterance is shorter than one window (TA:142 asserts) */
+
+#define B200FE_MAX_MEL 128
+#define B200FE_MAX_FREQ_MASKS 4
+#define B200FE_MAX_TIME_MASKS 4
+
+typedef struct b200fe_plan b200fe_plan;
+
+/* Options = the keyword arguments of WavToKaldiFbank (R/lasr/data/datatrans.py:43-71) that
+ * reach torchaudio.compliance.kaldi.fbank (TA:514-541).  Not supported (rejected with EINVAL):
+ * snip_edges=False, use_energy=True, vtln_warp != 1, htk_compat (no effect without energy). */
+typedef struct b200fe_opts {
+    float sample_frequency;        /* 16000 */
+    float frame_length_ms;         /* 25 */
+    float frame_shift_ms;          /* 10 */
+    int num_mel_bins;              /* 80 */
+    float low_freq;                /* 20 */
+    float high_freq;               /* 0 (= Nyquist offset, TA:457-458) */
+    float preemphasis_coefficient; /* 0.97 */
+    int remove_dc_offset;          /* 1 */
+    int use_power;                 /* 1 */
+    int use_log_fbank;             /* 1 */
+    int window_type;               /* 0 povey, 1 hanning, 2 hamming, 3 rectangular, 4 blackman (TA:86-113) */
+    float blackman_coeff;          /* 0.42 */
+    int audio_bit;                 /* 16: waveform is scaled by 2^(audio_bit-1) (datatrans.py:74) */
+    /* Optional host tables that override the built-in (double precision, rounded once)
+     * constants so that they match the caller's torch build bit for bit.  May be NULL. */
+    const float* window;           /* [window_size] */
+    const float* mel_weights;      /* [num_mel_bins][padded_window_size/2] row-major (TA:436-511) */
+} b200fe_opts;
+
+void b200fe_default_opts(b200fe_opts* o);
+int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** plan);
+void b200fe_plan_destroy(b200fe_plan* plan);
+const char* b200fe_last_error(void);
+
+/* Host helpers: TA:125-151 window properties and the snip_edges frame count TA:63-67. */
+int b200fe_window_size(const b200fe_plan* plan);
+int b200fe_window_shift(const b200fe_plan* plan);
+int b200fe_padded_window_size(const b200fe_plan* plan);
+long long b200fe_num_frames(const b200fe_plan* plan, long long num_samples);
+/* Introspection for tests / benchmarks: what = 0 straight-line mel path in use, 1 registers
+ * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count. */
+int b200fe_plan_info(const b200fe_plan* plan, int what);
+
+/* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
+ * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
+ * fused into b200fe_fbank_fused through its `d_peak` argument. */
+int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride,
+                       const long long* d_nsamp, int batch, float* d_peak, void* stream);
+
+/* One fused launch over a zero-padded batch of waveforms.
+ * Replaces WavToKaldiFbank (R/lasr/data/datatrans.py:42-104 -> TA:514-645) for every
+ * utterance of the batch and the padding collate batch_list (R/lasr/data/dataset.py:8-22):
+ * features are written straight into the (batch, max_frames, num_mel_bins) layout, rows past an
+ * utterance's frame count are zero (pad_audio = 0, R/example/asr_en/conf/config_baseline.yaml:70). */
+typedef struct b200fe_fbank_args {
+    const float* d_wav;          /* [batch][wav_stride] float32 */
+    long long wav_stride;        /* elements between utterances */
+    const long long* d_nsamp;    /* [batch] valid samples */
+    int batch;
+    const float* d_peak;         /* NULL, or [batch] from b200fe_peak_absmax: x / (peak + 1e-9) first */
+    float* d_out;                /* [batch][max_frames][num_mel_bins]; NULL = statistics only */
+    long long* d_out_len;        /* optional [batch]: frames per utterance (the wav_len tensor, dataset.py:198,206) */
+    int max_frames;              /* rows per utterance in d_out (>= max_b frames(nsamp[b]) is the caller's job) */
+    /* CMVN applied in the epilogue, (x - mean) * istd in float32.  NULL = none.
+     * cmvn_stride 0 = one global vector pair, num_mel_bins = per utterance. */
+    const float* d_cmvn_mean;
+    const float* d_cmvn_istd;
+    long long cmvn_stride;
+    /* SpecAugment rectangles per utterance: [n_freq_masks + n_time_masks][2] int32 (start, stop),
+     * frequency masks first (R/lasr/utils/specaugment.py:47-106).  mask_zero = 1 zeroes them in this
+     * launch (replace_with_zero=True); mask_zero = 0 leaves them to b200fe_specaug_fill (mean fill). */
+    const int* d_masks;
+    int n_freq_masks, n_time_masks;
+    int mask_zero;
+    /* Column statistics of what is written (after CMVN), accumulated with fp64 atomics:
+     * d_stats[u * stats_stride + c * num_mel_bins + d]: c < n_row_classes = sums over the rows of
+     * class c, c == n_row_classes = sums of squares over all rows.  stats_stride 0 = one
+     * accumulator for the whole batch (global CMVN, Kaldi compute-cmvn-stats).  Row classes are
+     * the elementary intervals of d_row_bounds[u][n_row_classes-1] (sorted); NULL = one class.
+     * The caller zeroes d_stats. */
+    double* d_stats;
+    long long stats_stride;
+    const int* d_row_bounds;
+    int n_row_classes;
+} b200fe_fbank_args;
+
+int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);
+
+/* Turns per-utterance statistics into (a) utterance CMVN vectors and (b) the SpecAugment mean
+ * fills of R/lasr/utils/specaugment.py:71-74,102-105 (each mask is filled with the mean of the
+ * CURRENT array, i.e. after CMVN and after all earlier masks), evaluated in closed form from the
+ * row-class column sums.  cmvn_mode: 0 = statistics are already in the output domain,
+ * 1 = subtract utterance mean, 2 = mean and variance (var floored at 1e-20). */
+typedef struct b200fe_post_args {
+    float* d_feats;              /* [batch][max_frames][num_mel_bins], updated in place */
+    const long long* d_nsamp;    /* [batch] (frame counts are derived exactly as in the fused launch) */
+    int batch;
+    int max_frames;
+    const double* d_stats;       /* as written by b200fe_fbank_fused (stats_stride != 0) */
+    long long stats_stride;
+    const int* d_row_bounds;
+    int n_row_classes;
+    int cmvn_mode;
+    float* d_cmvn_mean;          /* [batch][num_mel_bins] workspace/outputs (required when cmvn_mode != 0) */
+    float* d_cmvn_istd;
+    const int* d_masks;          /* as above; NULL = no SpecAugment */
+    int n_freq_masks, n_time_masks;
+    float* d_fills;              /* [batch][n_freq_masks + n_time_masks] outputs (required with masks) */
+} b200fe_post_args;
+
+int b200fe_postpass(const b200fe_plan* plan, const b200fe_post_args* args, void* stream);
+
+/* Global CMVN: [2][num_mel_bins + 1] Kaldi statistics (row 0 sums + count, row 1 sums of
+ * squares + 0) on the HOST -> mean / inverse std vectors (float32, host). */
+int b200fe_cmvn_from_stats(const double* stats, int num_mel_bins, int norm_vars, float* mean, float* istd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FE_H */

@@ -1,0 +1,104 @@
+"""ctypes binding of include/b200fe.h.  Fails loudly when the CUDA library is absent."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_ll = C.c_longlong
+c_fp = C.POINTER(C.c_float)
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("sample_frequency", C.c_float), ("frame_length_ms", C.c_float), ("frame_shift_ms", C.c_float),
+        ("num_mel_bins", C.c_int), ("low_freq", C.c_float), ("high_freq", C.c_float),
+        ("preemphasis_coefficient", C.c_float), ("remove_dc_offset", C.c_int), ("use_power", C.c_int),
+        ("use_log_fbank", C.c_int), ("window_type", C.c_int), ("blackman_coeff", C.c_float),
+        ("audio_bit", C.c_int), ("window", C.c_void_p), ("mel_weights", C.c_void_p),
+    ]
+
+
+class FbankArgs(C.Structure):
+    _fields_ = [
+        ("d_wav", C.c_void_p), ("wav_stride", c_ll), ("d_nsamp", C.c_void_p), ("batch", C.c_int),
+        ("d_peak", C.c_void_p), ("d_out", C.c_void_p), ("d_out_len", C.c_void_p), ("max_frames", C.c_int),
+        ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p), ("cmvn_stride", c_ll),
+        ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("mask_zero", C.c_int),
+        ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
+    ]
+
+
+class PostArgs(C.Structure):
+    _fields_ = [
+        ("d_feats", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
+        ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
+        ("cmvn_mode", C.c_int), ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p),
+        ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("d_fills", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
+    "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info",
+    "b200fe_peak_absmax", "b200fe_fbank_fused", "b200fe_postpass", "b200fe_cmvn_from_stats",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Returns the loaded CDLL.  Raises RuntimeError if the CUDA library cannot be found or built:
+    the product has no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise RuntimeError("libb200fe.so is missing and could not be built (no CPU fallback exists): %s" % e)
+    if not os.path.exists(path):
+        raise RuntimeError("libb200fe.so is missing (run `python -m __graft_entry__` or lighting-asr_b200/build.py); "
+                           "the front end has no CPU fallback")
+    lib = C.CDLL(path)
+    lib.b200fe_default_opts.argtypes = [C.POINTER(Opts)]
+    lib.b200fe_default_opts.restype = None
+    lib.b200fe_plan_create.argtypes = [C.POINTER(Opts), C.POINTER(C.c_void_p)]
+    lib.b200fe_plan_create.restype = C.c_int
+    lib.b200fe_plan_destroy.argtypes = [C.c_void_p]
+    lib.b200fe_plan_destroy.restype = None
+    lib.b200fe_last_error.argtypes = []
+    lib.b200fe_last_error.restype = C.c_char_p
+    for f in ("b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size"):
+        getattr(lib, f).argtypes = [C.c_void_p]
+        getattr(lib, f).restype = C.c_int
+    lib.b200fe_plan_info.argtypes = [C.c_void_p, C.c_int]
+    lib.b200fe_plan_info.restype = C.c_int
+    lib.b200fe_num_frames.argtypes = [C.c_void_p, c_ll]
+    lib.b200fe_num_frames.restype = c_ll
+    lib.b200fe_peak_absmax.argtypes = [C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.b200fe_peak_absmax.restype = C.c_int
+    lib.b200fe_fbank_fused.argtypes = [C.c_void_p, C.POINTER(FbankArgs), C.c_void_p]
+    lib.b200fe_fbank_fused.restype = C.c_int
+    lib.b200fe_postpass.argtypes = [C.c_void_p, C.POINTER(PostArgs), C.c_void_p]
+    lib.b200fe_postpass.restype = C.c_int
+    lib.b200fe_cmvn_from_stats.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, c_fp, c_fp]
+    lib.b200fe_cmvn_from_stats.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class B200feError(RuntimeError):
+    pass
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().b200fe_last_error().decode("utf-8", "replace")
+        raise B200feError("%s failed (%d): %s" % (what, status, msg))

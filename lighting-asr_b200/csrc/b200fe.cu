@@ -1,0 +1,389 @@
+// C ABI of the B200 acoustic front end (see include/b200fe.h).  Host side: plan construction
+// (window, FFT twiddles, mel tables in the layout the kernels want) and kernel launches.
+#include "../../include/b200fe.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "fbank_kernel.cuh"
+
+#define B200FE_MEL_HOST_TABLES
+#include "mel_static_default.inc"
+#undef B200FE_MEL_HOST_TABLES
+
+using namespace b200fe;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) return fail(B200FE_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+struct b200fe_plan {
+    b200fe_opts o;
+    int win, shift, nfft, nmel;
+    int device;
+    int num_sms;
+    // device tables
+    float* d_window_scaled = nullptr;   // window * 2^(bits-1)
+    float* d_window_plain = nullptr;
+    float2* d_twiddle = nullptr;
+    float2* d_split_tw = nullptr;
+    // host copies of the constant-bank tables
+    short seg_start[kMaxMel + 3];
+    short grp_begin[9];
+    float2 w_updn[256];
+    int tile_floats;
+    int smem_bytes;
+    int nload;          // 13 or 16
+    int static_mel;     // 1: tables equal the baked-in LASR default -> straight-line phase B
+    int ctas_per_sm;
+};
+
+static const void* plan_kernel(const b200fe_plan* p)
+{
+    if (p->nload == 13) return p->static_mel ? (const void*)fbank_fused_kernel<13, true> : (const void*)fbank_fused_kernel<13, false>;
+    return (const void*)fbank_fused_kernel<16, false>;
+}
+
+extern "C" void b200fe_default_opts(b200fe_opts* o)
+{
+    memset(o, 0, sizeof *o);
+    o->sample_frequency = 16000.f;
+    o->frame_length_ms = 25.f;
+    o->frame_shift_ms = 10.f;
+    o->num_mel_bins = 80;
+    o->low_freq = 20.f;
+    o->high_freq = 0.f;
+    o->preemphasis_coefficient = 0.97f;
+    o->remove_dc_offset = 1;
+    o->use_power = 1;
+    o->use_log_fbank = 1;
+    o->window_type = 0;
+    o->blackman_coeff = 0.42f;
+    o->audio_bit = 16;
+}
+
+extern "C" const char* b200fe_last_error(void) { return g_err.c_str(); }
+
+static double mel_scale(double f) { return 1127.0 * std::log(1.0 + f / 700.0); }
+
+extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
+{
+    if (!opts || !out) return fail(B200FE_EINVAL, "null argument");
+    b200fe_plan* p = new b200fe_plan();
+    p->o = *opts;
+    const b200fe_opts& o = p->o;
+    // TA:136-139
+    p->shift = (int)(o.sample_frequency * o.frame_shift_ms * 0.001f);
+    p->win = (int)(o.sample_frequency * o.frame_length_ms * 0.001f);
+    p->nfft = next_pow2(p->win);
+    p->nmel = o.num_mel_bins;
+    auto bad = [&](const char* m) { delete p; return fail(B200FE_EINVAL, "%s", m); };
+    if (p->win < 2 || p->shift <= 0) return bad("window size must be >= 2 and shift > 0 (TA:142-145)");
+    if (p->nfft != 512) return bad("only a padded window of 512 samples is supported by the 16 kHz kernel (use the dual-256 path for 8 kHz)");
+    if (p->nmel <= 3 || p->nmel > kMaxMel) return bad("num_mel_bins must be in (3, 128] (TA:449)");
+    if (o.preemphasis_coefficient < 0.f || o.preemphasis_coefficient > 1.f) return bad("preemphasis_coefficient must be in [0,1] (TA:149)");
+    if (p->shift % 2 != 0) return bad("an odd frame shift (in samples) is not supported (8-byte aligned frame loads)");
+    const int nbins = p->nfft / 2;
+    const double nyq = 0.5 * o.sample_frequency;
+    double high = o.high_freq;
+    if (high <= 0.0) high += nyq;   // TA:457-458
+    if (!(0.0 <= o.low_freq && o.low_freq < nyq && 0.0 < high && high <= nyq && o.low_freq < high))
+        return bad("bad low_freq / high_freq versus Nyquist (TA:460-462)");
+
+    // ---- window (TA:86-113), double precision unless the caller supplied its own table ----
+    std::vector<float> window(512, 0.f), window_s(512, 0.f);
+    const double scale = std::ldexp(1.0, o.audio_bit - 1);
+    for (int n = 0; n < p->win; ++n) {
+        double w;
+        if (o.window) w = o.window[n];
+        else {
+            const double a = 2.0 * M_PI / (p->win - 1);
+            switch (o.window_type) {
+                case 0: w = std::pow(0.5 - 0.5 * std::cos(a * n), 0.85); break;
+                case 1: w = 0.5 - 0.5 * std::cos(a * n); break;
+                case 2: w = 0.54 - 0.46 * std::cos(a * n); break;
+                case 3: w = 1.0; break;
+                case 4: w = o.blackman_coeff - 0.5 * std::cos(a * n) + (0.5 - o.blackman_coeff) * std::cos(2 * a * n); break;
+                default: return bad("unknown window_type");
+            }
+        }
+        window[n] = (float)w;
+        window_s[n] = (float)w * (float)scale;   // exact: power of two
+    }
+    // ---- mel filterbank (TA:436-511, vtln_warp == 1) ----
+    std::vector<float> W((size_t)p->nmel * nbins, 0.f);
+    const double mel_lo = mel_scale(o.low_freq), mel_hi = mel_scale(high);
+    const double delta = (mel_hi - mel_lo) / (p->nmel + 1);
+    const double bin_w = (double)o.sample_frequency / p->nfft;
+    if (o.mel_weights) memcpy(W.data(), o.mel_weights, W.size() * sizeof(float));
+    else
+        for (int j = 0; j < p->nmel; ++j) {
+            const double left = mel_lo + j * delta, center = mel_lo + (j + 1) * delta, right = mel_lo + (j + 2) * delta;
+            for (int k = 0; k < nbins; ++k) {
+                const double m = mel_scale(bin_w * k);
+                const double up = (m - left) / (center - left), down = (right - m) / (right - center);
+                const double w = std::fmax(0.0, std::fmin(up, down));
+                W[(size_t)j * nbins + k] = (float)w;
+            }
+        }
+    // segment structure: seg(k) = number of centers strictly below mel(k); bin seg gets the
+    // up-slope weight, bin seg-1 the down-slope weight; every other entry of column k must be 0.
+    std::vector<int> seg(nbins);
+    for (int k = 0; k < nbins; ++k) {
+        const double m = mel_scale(bin_w * k);
+        int s = 0;
+        if (m <= mel_lo) s = -1;                       // left of the first filter
+        else { while (s <= p->nmel && mel_lo + (s + 1) * delta < m) ++s; }
+        seg[k] = s;
+    }
+    for (int k = 0; k < nbins; ++k) {
+        float up = 0.f, dn = 0.f;
+        int s = seg[k];
+        // tolerate a one-off between this double computation and a float32 table from the caller
+        auto nz = [&](int j) { return j >= 0 && j < p->nmel && W[(size_t)j * nbins + k] != 0.f; };
+        if (s >= 0 && !(nz(s) || nz(s - 1)) ) { if (nz(s + 1) || nz(s)) s = s + 1; else if (nz(s - 2)) s = s - 1; }
+        if (s > p->nmel) s = p->nmel + 1;
+        if (s >= 0 && s <= p->nmel) {
+            if (s < p->nmel) up = W[(size_t)s * nbins + k];
+            if (s >= 1) dn = W[(size_t)(s - 1) * nbins + k];
+        }
+        for (int j = 0; j < p->nmel; ++j)
+            if (j != s && j != s - 1 && W[(size_t)j * nbins + k] != 0.f) return bad("mel weights are not a two-band triangular filterbank");
+        seg[k] = s;
+        p->w_updn[k] = make_float2(up * 0.25f, dn * 0.25f);   // |X|^2 arrives as 4|X|^2 (power) ...
+        if (!o.use_power) p->w_updn[k] = make_float2(up * 0.5f, dn * 0.5f);   // ... or 2|X| (magnitude)
+    }
+    // monotone segments -> seg_start
+    for (int k = 1; k < nbins; ++k) if (seg[k] < seg[k - 1] && seg[k] >= 0) return bad("mel segments are not monotone");
+    {
+        int k = 0;
+        for (int s = 0; s <= p->nmel + 1; ++s) {
+            while (k < nbins && seg[k] < s) ++k;
+            p->seg_start[s] = (short)k;
+        }
+        p->seg_start[p->nmel + 2] = (short)nbins;
+    }
+    // warp groups: 8 consecutive runs of bins with balanced (#k read + per-bin epilogue) cost
+    {
+        std::vector<double> cost(p->nmel);
+        double tot = 0;
+        for (int j = 0; j < p->nmel; ++j) { cost[j] = (p->seg_start[j + 2] - p->seg_start[j]) * 0.5 + 6.0; tot += cost[j]; }
+        int j = 0; double acc = 0;
+        p->grp_begin[0] = 0;
+        for (int w = 1; w < 8; ++w) {
+            const double target = tot * w / 8.0;
+            while (j < p->nmel && acc + cost[j] * 0.5 < target) { acc += cost[j]; ++j; }
+            p->grp_begin[w] = (short)j;
+        }
+        p->grp_begin[8] = (short)p->nmel;
+    }
+    // ---- FFT twiddles (double precision, rounded once) ----
+    std::vector<float2> twd(256), stw(256);
+    for (int n1 = 0; n1 < 16; ++n1)
+        for (int k = 0; k < 16; ++k) {
+            const double ang = -2.0 * M_PI * (double)((n1 * k) % 256) / 256.0;
+            twd[n1 * 16 + k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+    for (int k = 0; k < 256; ++k) {   // -j * exp(-2 pi j k / 512) = -sin(t) - j cos(t), t = 2 pi k / 512
+        const double t = 2.0 * M_PI * k / 512.0;
+        stw[k] = make_float2((float)(-std::sin(t)), (float)(-std::cos(t)));
+    }
+    p->nload = (p->win > 384 && p->win <= 416) ? 13 : 16;
+    p->tile_floats = ((kFT - 1) * p->shift + 512 + 16 + 3) & ~3;
+    p->smem_bytes = make_layout(p->tile_floats, p->nmel).total;
+
+    cudaError_t e = cudaGetDevice(&p->device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, p->device);
+    if (e != cudaSuccess) { delete p; return fail(B200FE_ECUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
+    p->num_sms = prop.multiProcessorCount;
+    if ((size_t)p->smem_bytes > prop.sharedMemPerBlockOptin) { delete p; return fail(B200FE_EINVAL, "tile does not fit in shared memory (%d B)", p->smem_bytes); }
+    auto up = [&](void** d, const void* h, size_t n) -> cudaError_t {
+        cudaError_t r = cudaMalloc(d, n);
+        if (r != cudaSuccess) return r;
+        return cudaMemcpy(*d, h, n, cudaMemcpyHostToDevice);
+    };
+    if ((e = up((void**)&p->d_window_scaled, window_s.data(), 512 * 4)) != cudaSuccess ||
+        (e = up((void**)&p->d_window_plain, window.data(), 512 * 4)) != cudaSuccess ||
+        (e = up((void**)&p->d_twiddle, twd.data(), 256 * 8)) != cudaSuccess ||
+        (e = up((void**)&p->d_split_tw, stw.data(), 256 * 8)) != cudaSuccess) {
+        b200fe_plan_destroy(p);
+        return fail(B200FE_ECUDA, "plan upload: %s", cudaGetErrorString(e));
+    }
+    p->static_mel = 0;
+    if (p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power) {
+        bool same = memcmp(p->seg_start, kStaticSegStart, sizeof(short) * (p->nmel + 3)) == 0 &&
+                    memcmp(p->grp_begin, kStaticGrpBegin, sizeof kStaticGrpBegin) == 0;
+        for (int k = 0; same && k < 256; ++k) same = (p->w_updn[k].x == kStaticUp[k] && p->w_updn[k].y == kStaticDn[k]);
+        p->static_mel = same ? 1 : 0;
+    }
+    const void* kfn = plan_kernel(p);
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
+    if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kThreads, p->smem_bytes);
+    if (e != cudaSuccess || occ < 1) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "fbank kernel cannot be resident (occ=%d): %s", occ, cudaGetErrorString(e)); }
+    p->ctas_per_sm = occ;
+    *out = p;
+    return B200FE_OK;
+}
+
+extern "C" void b200fe_plan_destroy(b200fe_plan* p)
+{
+    if (!p) return;
+    cudaFree(p->d_window_scaled);
+    cudaFree(p->d_window_plain);
+    cudaFree(p->d_twiddle);
+    cudaFree(p->d_split_tw);
+    delete p;
+}
+
+extern "C" int b200fe_window_size(const b200fe_plan* p) { return p->win; }
+extern "C" int b200fe_window_shift(const b200fe_plan* p) { return p->shift; }
+extern "C" int b200fe_padded_window_size(const b200fe_plan* p) { return p->nfft; }
+extern "C" int b200fe_plan_info(const b200fe_plan* p, int what)
+{
+    switch (what) {
+        case 0: return p->static_mel;
+        case 1: return p->nload;
+        case 2: return p->smem_bytes;
+        case 3: return p->ctas_per_sm;
+        case 4: return p->num_sms;
+        default: return -1;
+    }
+}
+extern "C" long long b200fe_num_frames(const b200fe_plan* p, long long n)
+{
+    return n < p->win ? 0 : 1 + (n - p->win) / p->shift;   // TA:63-67
+}
+
+extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride,
+                                  const long long* d_nsamp, int batch, float* d_peak, void* stream)
+{
+    if (!plan || !d_wav || !d_nsamp || !d_peak || batch <= 0 || wav_stride <= 0) return fail(B200FE_EINVAL, "peak_absmax: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(d_peak, 0, sizeof(float) * batch, st));
+    const long long chunk = 256LL * 4 * 8;
+    dim3 grid((unsigned)((wav_stride + chunk - 1) / chunk), (unsigned)batch);
+    absmax_kernel<<<grid, 256, 0, st>>>(d_wav, wav_stride, d_nsamp, d_peak);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args* g, void* stream)
+{
+    if (!p || !g) return fail(B200FE_EINVAL, "fbank_fused: null argument");
+    if (!g->d_wav || !g->d_nsamp || g->batch <= 0 || g->wav_stride <= 0) return fail(B200FE_EINVAL, "fbank_fused: bad waveform arguments");
+    if (!g->d_out && !g->d_stats) return fail(B200FE_EINVAL, "fbank_fused: neither an output nor a statistics buffer");
+    if (g->max_frames <= 0) return fail(B200FE_EINVAL, "fbank_fused: max_frames must be positive");
+    if ((g->d_cmvn_mean == nullptr) != (g->d_cmvn_istd == nullptr)) return fail(B200FE_EINVAL, "fbank_fused: cmvn mean and istd go together");
+    if (g->d_cmvn_mean && g->cmvn_stride != 0 && g->cmvn_stride != p->nmel) return fail(B200FE_EINVAL, "fbank_fused: cmvn_stride must be 0 or num_mel_bins");
+    if (g->n_freq_masks < 0 || g->n_freq_masks > B200FE_MAX_FREQ_MASKS || g->n_time_masks < 0 || g->n_time_masks > B200FE_MAX_TIME_MASKS)
+        return fail(B200FE_EINVAL, "fbank_fused: too many masks");
+    int n_cls = g->d_stats ? (g->n_row_classes > 0 ? g->n_row_classes : 1) : 1;
+    if (n_cls > kMaxRowClasses) return fail(B200FE_EINVAL, "fbank_fused: too many row classes");
+
+    FbankArgs a;
+    memset(&a, 0, sizeof a);
+    a.wav = g->d_wav; a.wav_stride = g->wav_stride; a.nsamp = g->d_nsamp; a.peak = g->d_peak; a.B = g->batch;
+    a.out = g->d_out; a.out_len = g->d_out_len; a.Tmax = g->max_frames; a.nmel = p->nmel;
+    a.win = p->win; a.shift = p->shift;
+    a.remove_dc = p->o.remove_dc_offset; a.use_power = p->o.use_power; a.use_log = p->o.use_log_fbank;
+    a.preemph = p->o.preemphasis_coefficient;
+    a.log_floor = 1.1920928955078125e-07f;   // TA:21-22
+    a.in_scale = (float)std::ldexp(1.0, p->o.audio_bit - 1);
+    a.window = g->d_peak ? p->d_window_plain : p->d_window_scaled;
+    a.twiddle = p->d_twiddle; a.split_tw = p->d_split_tw;
+    a.cm_mean = g->d_cmvn_mean; a.cm_istd = g->d_cmvn_istd; a.cm_stride = g->cmvn_stride;
+    a.masks = (g->n_freq_masks + g->n_time_masks) > 0 ? g->d_masks : nullptr;
+    a.n_fmask = g->n_freq_masks; a.n_tmask = g->n_time_masks; a.mask_zero = g->mask_zero;
+    a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds; a.n_cls = n_cls;
+    a.tiles_per_utt = (g->max_frames + kFT - 1) / kFT;
+    const long long ntiles = (long long)a.tiles_per_utt * g->batch;
+    if (ntiles > 0x7fffffffLL) return fail(B200FE_EINVAL, "fbank_fused: too many tiles");
+    a.ntiles = (int)ntiles;
+    a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 && (g->wav_stride % 4) == 0) ? 1 : 0;
+    a.tile_floats = p->tile_floats;
+    memcpy(a.seg_start, p->seg_start, sizeof a.seg_start);
+    memcpy(a.grp_begin, p->grp_begin, sizeof a.grp_begin);
+    memcpy(a.w_updn, p->w_updn, sizeof a.w_updn);
+
+    const int grid = (int)std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm);
+    cudaStream_t st = (cudaStream_t)stream;
+    void* kargs[] = {(void*)&a};
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, void* stream)
+{
+    if (!p || !g || !g->d_feats || !g->d_nsamp || g->batch <= 0 || g->max_frames <= 0) return fail(B200FE_EINVAL, "postpass: bad argument");
+    const int nm = g->n_freq_masks + g->n_time_masks;
+    const bool masks = g->d_masks != nullptr && nm > 0;
+    if (!masks && g->cmvn_mode == 0) return B200FE_OK;
+    if (!g->d_stats || g->stats_stride <= 0) return fail(B200FE_EINVAL, "postpass: per-utterance statistics are required");
+    if (g->cmvn_mode != 0 && (!g->d_cmvn_mean || !g->d_cmvn_istd)) return fail(B200FE_EINVAL, "postpass: cmvn workspace missing");
+    if (masks && !g->d_fills) return fail(B200FE_EINVAL, "postpass: fill buffer missing");
+    if (g->n_freq_masks > B200FE_MAX_FREQ_MASKS || g->n_time_masks > B200FE_MAX_TIME_MASKS) return fail(B200FE_EINVAL, "postpass: too many masks");
+    PostArgs a;
+    memset(&a, 0, sizeof a);
+    a.feats = g->d_feats; a.nsamp = g->d_nsamp; a.B = g->batch; a.Tmax = g->max_frames; a.nmel = p->nmel;
+    a.win = p->win; a.shift = p->shift;
+    a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds;
+    a.n_cls = g->n_row_classes > 0 ? g->n_row_classes : 1;
+    if (a.n_cls > kMaxRowClasses) return fail(B200FE_EINVAL, "postpass: too many row classes");
+    a.cmvn_mode = g->cmvn_mode; a.cm_mean = g->d_cmvn_mean; a.cm_istd = g->d_cmvn_istd;
+    a.masks = masks ? g->d_masks : nullptr; a.n_fmask = masks ? g->n_freq_masks : 0; a.n_tmask = masks ? g->n_time_masks : 0;
+    a.fills = g->d_fills;
+    a.rows_per_cta = 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    finalize_kernel<<<g->batch, 128, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
+    postpass_kernel<<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_cmvn_from_stats(const double* stats, int nmel, int norm_vars, float* mean, float* istd)
+{
+    if (!stats || !mean || !istd || nmel <= 0) return fail(B200FE_EINVAL, "cmvn_from_stats: bad argument");
+    const double n = stats[nmel];
+    if (!(n > 0)) return fail(B200FE_EINVAL, "cmvn_from_stats: zero frame count");
+    for (int d = 0; d < nmel; ++d) {
+        const double m = stats[d] / n;
+        double var = stats[(nmel + 1) + d] / n - m * m;
+        if (var < 1e-20) var = 1e-20;
+        mean[d] = (float)m;
+        istd[d] = norm_vars ? (float)(1.0 / std::sqrt(var)) : 1.0f;
+    }
+    return B200FE_OK;
+}

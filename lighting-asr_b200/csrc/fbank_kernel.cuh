@@ -1,0 +1,507 @@
+// Fused Kaldi-fbank kernel for sm_100a (B200).
+//
+// Replaces, for a whole padded batch in one launch, the per-utterance CPU chain
+//   lasr/data/datatrans.py:42-104 (WavToKaldiFbank) -> torchaudio/compliance/kaldi.py:514-645
+//   (framing TA:44-83, DC removal / pre-emphasis / window / zero-pad TA:154-217, rfft+power
+//   TA:616-618, mel projection TA:621-630, floored log TA:631-633) and the zero-padded collate
+//   lasr/data/dataset.py:8-22, plus the CMVN / SpecAugment epilogue of SURVEY.md section 8.
+//
+// Work decomposition:
+//   * grid  : persistent CTAs striding over tiles; a tile = FT(32) consecutive frames of one
+//             utterance.  256 threads = 16 half-warps.
+//   * load  : the waveform span of a tile ((FT-1)*shift + win samples, each sample fetched once
+//             per tile) is brought to shared memory with one 1-D TMA bulk copy (UBLKCP) per
+//             tile into a 2-stage ring, completion on an mbarrier.
+//   * phase A (half-warp per frame, 2 frames each): 16 lanes x 16 complex registers hold the
+//             frame packed as a 256-point complex sequence z[n] = y[2n] + j y[2n+1].
+//             DC removal, pre-emphasis and the window are applied while loading; DFT-16 in
+//             registers (packed FADD2/FFMA2), twiddle, one transposition through shared memory,
+//             second DFT-16, conjugate-pair exchange with warp shuffles, real-FFT split and
+//             |X|^2 -> power spectrum written transposed, PT4[k/4][frame][k%4].
+//   * phase B (warp = group of mel bins, lane = frame): sparse triangular mel accumulate.  For the
+//             LASR default option set the projection is straight-line code with the weights as
+//             immediates (mel_static_default.inc); otherwise the (up, down) weights are
+//             warp-uniform loads from the constant bank (kernel parameters).  log / CMVN /
+//             zero-masks are applied and the tile's features land in a staging buffer.
+//   * phase C : coalesced copy-out (+ zero fill of padded rows) and, in statistics mode,
+//             per-column sums / sums of squares per SpecAugment row class, flushed with one
+//             fp64 atomic per column, class and tile.
+#pragma once
+#include "b200fe_common.cuh"
+
+namespace b200fe {
+
+constexpr int kFT = 32;             // frames per tile
+constexpr int kThreads = 256;       // 8 warps, 16 half-warps
+constexpr int kHalfWarps = 16;
+constexpr int kXRow = 17;           // padded row length (float2) of the transposition buffer
+constexpr int kPTStride = 33;       // PT4[k/4][frame] float4 groups; a row of 32 frames is padded to 33 groups
+constexpr int kMaxMel = 128;
+constexpr int kMaxTimeMasks = 4;
+constexpr int kMaxFreqMasks = 4;
+constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
+constexpr int kStages = 2;
+
+struct FbankArgs {
+    // input
+    const float* wav;            // [B][wav_stride] fp32 waveform
+    long long wav_stride;
+    const long long* nsamp;      // [B] valid samples
+    const float* peak;           // [B] per-utterance abs-max (peak normalisation) or nullptr
+    int B;
+    // output
+    float* out;                  // [B][Tmax][nmel] (nullptr in statistics-only mode)
+    long long* out_len;          // [B] frames per utterance (optional)
+    int Tmax;
+    int nmel;
+    // framing / fbank options
+    int win, shift;              // samples
+    int remove_dc, use_power, use_log;
+    float preemph;
+    float log_floor;             // FLT_EPSILON
+    float in_scale;              // 2^(audio_bit-1), applied on load when peak != nullptr (else folded in window)
+    // plan tables
+    const float* window;         // [512] window * (in_scale or 1), zero-extended
+    const float2* twiddle;       // [16][16] W_256^(n1*klo)
+    const float2* split_tw;      // [256]  -j * W_512^k
+    // CMVN applied in the epilogue: (x - mean) * istd ; nullptr = off ; stride 0 = global, nmel = per utterance
+    const float* cm_mean;
+    const float* cm_istd;
+    long long cm_stride;
+    // SpecAugment rectangles, per utterance [n_fmask + n_tmask][2] = (start, stop) ; freq first
+    const int* masks;
+    int n_fmask, n_tmask;
+    int mask_zero;               // 1: zero the masked cells here (replace_with_zero); 0: leave them for the fill kernel
+    // statistics: stats[u*stats_stride + c*nmel + d], c < n_cls row-class sums, c == n_cls sums of squares
+    double* stats;
+    long long stats_stride;      // 0 = one global accumulator
+    const int* row_bounds;       // per utterance [n_cls-1] sorted class boundaries (nullptr -> one class)
+    int n_cls;
+    // scheduling
+    int tiles_per_utt;
+    int ntiles;
+    int use_tma;
+    int tile_floats;             // floats reserved per tile stage
+    // mel tables (warp-uniform, read through the constant bank) -- generic (non-static) phase B
+    short seg_start[kMaxMel + 3];   // k where segment s begins, s = 0..nmel+1  (segment s feeds bin s (up) and s-1 (down))
+    short grp_begin[9];             // mel bins handled by warp w: [grp_begin[w], grp_begin[w+1])
+    float2 w_updn[256];             // (up weight -> bin seg(k), down weight -> bin seg(k)-1) * 0.25
+};
+
+struct SmemLayout {
+    int tile_off[kStages];
+    int xbuf_off, pt_off, outs_off, misc_off, bar_off, total;
+};
+
+// misc area: mean[128] | istd[128] | colmask[4]
+__host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
+{
+    SmemLayout L;
+    int o = 0;
+    for (int s = 0; s < kStages; ++s) { L.tile_off[s] = o; o += tile_floats * 4; }
+    L.xbuf_off = o;
+    int xbytes = kHalfWarps * 16 * kXRow * 8;
+    int obytes = kFT * (nmel + 1) * 4;           // staging aliases the transposition buffers (dead after phase A)
+    o += (xbytes > obytes ? xbytes : obytes);
+    L.outs_off = L.xbuf_off;
+    L.pt_off = o; o += 64 * kPTStride * 16;
+    L.misc_off = o; o += (2 * kMaxMel + 4) * 4;
+    L.bar_off = o; o += 8 * kStages;
+    L.total = o;
+    return L;
+}
+
+// fp32 evaluation of round_fp32(x / (m + 1e-9)): reciprocal estimate plus one exact-residual
+// correction (the 1e-9 is applied to the residual because m + 1e-9 is not an fp32 number).
+__device__ __forceinline__ float peak_div(float x, float m, float rcp)
+{
+    float q = x * rcp;
+    float e = fmaf(-q, m, x);
+    e = fmaf(-q, 1e-9f, e);
+    return fmaf(e, rcp, q);
+}
+
+__device__ __forceinline__ int row_class(const int* __restrict__ bounds, int nb, int t)
+{
+    int c = 0;
+    for (int i = 0; i < nb; ++i) c += (bounds[i] <= t);
+    return c;
+}
+
+struct TileGeom {
+    int utt, f0, nvalid, nrows, T;
+};
+
+// Epilogue of one mel bin for one frame (phase B): floored log, CMVN, zero masks, staging store.
+struct EpiCtx {
+    const float* s_mean;
+    const float* s_istd;
+    float* orow;              // staging row of this lane's frame
+    unsigned cmask[4];        // column bits that are zero-masked
+    float log_floor;
+    bool use_log, row_masked, valid;
+};
+
+template <bool kLog>
+__device__ __forceinline__ void emit_bin(const EpiCtx& c, int j, float e)
+{
+    if (kLog) e = fast_log(fmaxf(e, c.log_floor));
+    e = (e - c.s_mean[j]) * c.s_istd[j];
+    const bool z = c.row_masked || ((c.cmask[j >> 5] >> (j & 31)) & 1u) || !c.valid;
+    c.orow[j] = z ? 0.f : e;
+}
+
+#define B200FE_MEL_DEVICE_CODE
+#define MGROUP_BEGIN(w) template <bool kLog> __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, const EpiCtx& c) { \
+        float au = 0.f, ad = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
+#define MK(k, wu, wd) { if (((k) >> 2) != cur) { cur = (k) >> 2; p4 = pcol[cur * kPTStride]; } \
+        const float p = ((k) & 3) == 0 ? p4.x : ((k) & 3) == 1 ? p4.y : ((k) & 3) == 2 ? p4.z : p4.w; \
+        if ((wu) != 0.f) au = fmaf((wu), p, au); if ((wd) != 0.f) ad = fmaf((wd), p, ad); }
+#define MEND0() { up_prev = au; au = 0.f; ad = 0.f; }
+#define MEND(j) { emit_bin<kLog>(c, (j), up_prev + ad); up_prev = au; au = 0.f; ad = 0.f; }
+#define MGROUP_END(w) }
+#include "mel_static_default.inc"
+#undef MGROUP_BEGIN
+#undef MK
+#undef MEND0
+#undef MEND
+#undef MGROUP_END
+#undef B200FE_MEL_DEVICE_CODE
+
+template <int NLOAD, bool kStaticMel>
+__global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout L = make_layout(a.tile_floats, a.nmel);
+    float2* xbuf_all = reinterpret_cast<float2*>(smem + L.xbuf_off);
+    float* pt = reinterpret_cast<float*>(smem + L.pt_off);
+    float* outs = reinterpret_cast<float*>(smem + L.outs_off);
+    float* s_mean = reinterpret_cast<float*>(smem + L.misc_off);
+    float* s_istd = s_mean + kMaxMel;
+    unsigned* s_cmask = reinterpret_cast<unsigned*>(s_istd + kMaxMel);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int h2 = lane >> 4, l = lane & 15;
+    const int hw = warp * 2 + h2;
+    const unsigned hmask = 0xFFFFu << (16 * h2);
+    float2* xbuf = xbuf_all + hw * 16 * kXRow;
+    const int ostride = a.nmel + 1;
+
+    // ---- per-lane constants (live in registers across all tiles) ----
+    float2 wreg[NLOAD];
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) {
+        int j = 2 * (l + 16 * n2);
+        wreg[n2] = make_float2(__ldg(a.window + j), __ldg(a.window + j + 1));
+    }
+    float2 tw[16];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) tw[k] = __ldg(a.twiddle + l * 16 + k);
+    float2 stw[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) stw[r] = __ldg(a.split_tw + l + 16 * r);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    // global CMVN vectors (or the identity) are staged once; per-utterance vectors per tile
+    const bool cm_per_utt = a.cm_mean != nullptr && a.cm_stride != 0;
+    if (tid < kMaxMel) {
+        const bool on = a.cm_mean != nullptr && !cm_per_utt && tid < a.nmel;
+        s_mean[tid] = on ? __ldg(a.cm_mean + tid) : 0.f;
+        s_istd[tid] = on ? __ldg(a.cm_istd + tid) : 1.f;
+    }
+    if (tid < 4) s_cmask[tid] = 0u;
+    __syncthreads();
+
+    const float c_pre = a.preemph;
+    const float inv_win = 1.0f / (float)a.win;
+    const float dc_coef = a.remove_dc ? (float)(1.0 - (double)a.preemph) : 0.0f;
+    const bool zmask = a.mask_zero && a.masks != nullptr;
+    const int nmask = a.n_fmask + a.n_tmask;
+
+    auto tile_geom = [&](int tile) -> TileGeom {
+        TileGeom g;
+        g.utt = (int)((unsigned)tile / (unsigned)a.tiles_per_utt);
+        g.f0 = (tile - g.utt * a.tiles_per_utt) * kFT;
+        const unsigned n = (unsigned)__ldg(a.nsamp + g.utt);       // < 2^31 samples per utterance
+        g.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
+        g.nvalid = min(max(g.T - g.f0, 0), kFT);
+        g.nrows = min(a.Tmax - g.f0, kFT);
+        return g;
+    };
+    auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
+        if (g.nvalid <= 0) return;
+        const int nsmp = (g.nvalid - 1) * a.shift + a.win;
+        const uint32_t bytes = (uint32_t)((nsmp * 4 + 15) & ~15);
+        const float* src = a.wav + (long long)g.utt * a.wav_stride + (long long)g.f0 * a.shift;
+        mbar_expect_tx(&bars[stage], bytes);
+        tma_load_1d(smem + L.tile_off[stage], src, bytes, &bars[stage]);
+    };
+
+    int it = 0;
+    uint32_t phase_bits = 0;
+    int tile = blockIdx.x;
+    TileGeom g = tile_geom(tile < a.ntiles ? tile : 0);
+    if (a.use_tma && tid == 0 && tile < a.ntiles) issue_load(g, 0);
+
+    for (; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        const int utt = g.utt, f0 = g.f0, nvalid = g.nvalid, nrows = g.nrows;
+        float* xs = reinterpret_cast<float*>(smem + L.tile_off[stage]);
+        const int nxt = tile + gridDim.x;
+        TileGeom gn = g;
+        if (nxt < a.ntiles) gn = tile_geom(nxt);
+
+        if (a.use_tma) {
+            // prefetch the next tile of this CTA into the other stage (its previous contents were
+            // consumed before the phase-A barrier of the previous iteration)
+            if (tid == 0 && nxt < a.ntiles) issue_load(gn, (it + 1) % kStages);
+            // a stage's mbarrier phase advances only for tiles that actually carried a load
+            if (nvalid > 0) { mbar_wait(&bars[stage], (phase_bits >> stage) & 1u); phase_bits ^= (1u << stage); }
+        } else if (nvalid > 0) {
+            // generic path (unaligned base / stride): cooperative coalesced loads
+            const int nsmp = (nvalid - 1) * a.shift + a.win;
+            const float* src = a.wav + (long long)utt * a.wav_stride + (long long)f0 * a.shift;
+            for (int i = tid; i < nsmp; i += kThreads) xs[i] = __ldg(src + i);
+            __syncthreads();
+        }
+
+        if (nvalid > 0) {
+            // per-tile epilogue tables (visible after the phase-A barrier)
+            if (cm_per_utt && tid < a.nmel) {
+                s_mean[tid] = __ldg(a.cm_mean + (long long)utt * a.cm_stride + tid);
+                s_istd[tid] = __ldg(a.cm_istd + (long long)utt * a.cm_stride + tid);
+            }
+            if (zmask && tid < kMaxMel) {
+                const int* mk = a.masks + (long long)utt * nmask * 2;
+                bool m = false;
+                for (int i = 0; i < a.n_fmask; ++i) m |= (tid >= __ldg(mk + 2 * i) && tid < __ldg(mk + 2 * i + 1));
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) s_cmask[warp] = bal;
+            }
+
+            // ================= phase A: half-warp per frame =================
+            float pscale = 1.0f, prcp = 0.0f, pmax = 1.0f;
+            const bool has_peak = (a.peak != nullptr);
+            if (has_peak) {
+                // reference: x / (max + 1e-9) in fp64, rounded to fp32, times 2^(bits-1) (datatrans.py:24-25,73-74)
+                pmax = __ldg(a.peak + utt);
+                prcp = (float)(1.0 / ((double)pmax + 1e-9));
+                pscale = a.in_scale;
+            }
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                // frame slot inside the tile; concurrent half-warps of a warp are 4 frames apart so that
+                // their PT stores fall into disjoint banks
+                const int fl = (warp & 3) + 4 * h2 + 8 * (warp >> 2) + 16 * sub;
+                if (fl < nvalid) {
+                    const float* xf = xs + fl * a.shift + 2 * l;
+                    float2 v[16];
+                    // Load, (peak-normalise,) pre-emphasise; accumulate the frame sum on the fly so that
+                    // only p[] stays live.  y[j] = ((x[j]-m) - c (x[j-1]-m)) w[j]
+                    //                            = (x[j] - c x[j-1] - (1-c) m) w[j]      (TA:183-204)
+                    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int n2 = 0; n2 < NLOAD; ++n2) {
+                        const int j = 2 * (l + 16 * n2);
+                        float2 xr = *reinterpret_cast<const float2*>(xf + 32 * n2);
+                        float xp = (n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1];   // replicate pad at the frame start (TA:195)
+                        if (has_peak) {
+                            xr.x = peak_div(xr.x, pmax, prcp) * pscale;
+                            xr.y = peak_div(xr.y, pmax, prcp) * pscale;
+                            xp = peak_div(xp, pmax, prcp) * pscale;
+                        }
+                        if (NLOAD == 16 || n2 == NLOAD - 1) {
+                            // samples past the window must not enter the mean (their window weight is 0,
+                            // but whatever sits in shared memory there may be NaN)
+                            if (j >= a.win) { xr.x = 0.f; xp = 0.f; }
+                            if (j + 1 >= a.win) xr.y = 0.f;
+                        }
+                        acc2 = add2(acc2, xr);
+                        v[n2].x = fmaf(-c_pre, xp, xr.x);
+                        v[n2].y = fmaf(-c_pre, xr.x, xr.y);
+                    }
+                    float sum = acc2.x + acc2.y;
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+                    const float cdc = sum * inv_win * dc_coef;   // (1 - preemph) * frame mean
+#pragma unroll
+                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(sub2(v[n2], bc(cdc)), wreg[n2]);
+#pragma unroll
+                    for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+
+                    // ---- pass 1: DFT-16 over n2, twiddle W_256^(n1*klo) ----
+                    dft16(v);
+#pragma unroll
+                    for (int k = 1; k < 16; ++k) v[k] = c_mul(v[k], tw[k].x, tw[k].y);
+                    // ---- transpose through shared memory: row n1 = l, column klo ----
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) xbuf[l * kXRow + k] = v[k];
+                    __syncwarp(hmask);
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) v[n1] = xbuf[n1 * kXRow + l];
+                    __syncwarp(hmask);
+                    // ---- pass 2: DFT-16 over n1 -> Z[l + 16 r] in v[r] ----
+                    dft16(v);
+                    // ---- conjugate-pair exchange: own r = 0..7 pairs with lane (16-l)&15, register 15-r ----
+                    const int partner = (16 * h2) + ((16 - l) & 15);
+                    float2 rc[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        rc[r].x = __shfl_sync(hmask, v[15 - r].x, partner);
+                        rc[r].y = __shfl_sync(hmask, v[15 - r].y, partner);
+                    }
+                    if (l == 0) {   // bins 16 r pair with 16 (16 - r): shift by one register, bin 0 pairs with itself
+#pragma unroll
+                        for (int r = 7; r >= 1; --r) rc[r] = rc[r - 1];
+                        rc[0] = v[0];
+                    }
+                    // ---- real-FFT split + power: 2X[k] = S + T, 2 conj X[256-k] = S - T ----
+                    // PT4 layout: float index of (k, fl) = ((k>>2)*kPTStride + fl)*4 + (k&3)
+                    float* pa = pt + ((l >> 2) * kPTStride + fl) * 4 + (l & 3);                                // k = l + 16 r
+                    float* pb = pt + (((256 - l) >> 2) * kPTStride + fl) * 4 + ((256 - l) & 3);                // k = 256 - l - 16 r
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float2 bcj = make_float2(rc[r].x, -rc[r].y);
+                        float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
+                        float2 T = c_mul(D, stw[r].x, stw[r].y);
+                        float2 xa = add2(S, T), xb = sub2(S, T);
+                        xa = mul2(xa, xa); xb = mul2(xb, xb);
+                        float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
+                        if (!a.use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
+                        pa[r * 4 * kPTStride * 4] = pwa;
+                        if (r != 0 || l != 0) pb[-r * 4 * kPTStride * 4] = pwb;
+                    }
+                    if (l == 0) {   // bin 128 is its own partner: X[128] = conj Z[128]
+                        float2 z = v[8];
+                        float p = 4.0f * (z.x * z.x + z.y * z.y);
+                        if (!a.use_power) p = sqrtf(p);
+                        pt[(32 * kPTStride + fl) * 4] = p;
+                    }
+                }
+            }
+            __syncthreads();   // PT complete; tile stage and transposition buffers are free
+
+            // ================= phase B: warp = mel-bin group, lane = frame =================
+            {
+                const int fl = lane;
+                const int t = f0 + fl;
+                EpiCtx c;
+                c.s_mean = s_mean; c.s_istd = s_istd; c.orow = outs + fl * ostride;
+                c.log_floor = a.log_floor; c.use_log = a.use_log != 0; c.valid = fl < nvalid; c.row_masked = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c.cmask[i] = zmask ? s_cmask[i] : 0u;
+                if (zmask) {
+                    const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
+                    for (int i = 0; i < a.n_tmask; ++i) c.row_masked |= (t >= __ldg(mk + 2 * i) && t < __ldg(mk + 2 * i + 1));
+                }
+                const float4* pcol = reinterpret_cast<const float4*>(pt) + fl;
+                if (kStaticMel) {
+                    if (a.use_log) {
+                        switch (warp) {
+                            case 0: mel_static_group0<true>(pcol, c); break;
+                            case 1: mel_static_group1<true>(pcol, c); break;
+                            case 2: mel_static_group2<true>(pcol, c); break;
+                            case 3: mel_static_group3<true>(pcol, c); break;
+                            case 4: mel_static_group4<true>(pcol, c); break;
+                            case 5: mel_static_group5<true>(pcol, c); break;
+                            case 6: mel_static_group6<true>(pcol, c); break;
+                            default: mel_static_group7<true>(pcol, c); break;
+                        }
+                    } else {
+                        switch (warp) {
+                            case 0: mel_static_group0<false>(pcol, c); break;
+                            case 1: mel_static_group1<false>(pcol, c); break;
+                            case 2: mel_static_group2<false>(pcol, c); break;
+                            case 3: mel_static_group3<false>(pcol, c); break;
+                            case 4: mel_static_group4<false>(pcol, c); break;
+                            case 5: mel_static_group5<false>(pcol, c); break;
+                            case 6: mel_static_group6<false>(pcol, c); break;
+                            default: mel_static_group7<false>(pcol, c); break;
+                        }
+                    }
+                } else {
+                    const int jb = a.grp_begin[warp], je = a.grp_begin[warp + 1];
+                    if (jb < je) {
+                        const float* pf = pt + fl * 4;
+                        float up_prev = 0.f;
+#pragma unroll 1
+                        for (int s = jb; s <= je; ++s) {
+                            const int kb = a.seg_start[s], ke = a.seg_start[s + 1];
+                            float au = 0.f, ad = 0.f;
+#pragma unroll 2
+                            for (int k = kb; k < ke; ++k) {
+                                const float p = pf[(k >> 2) * (kPTStride * 4) + (k & 3)];
+                                const float2 w = a.w_updn[k];
+                                au = fmaf(w.x, p, au);
+                                ad = fmaf(w.y, p, ad);
+                            }
+                            if (s > jb) {
+                                if (c.use_log) emit_bin<true>(c, s - 1, up_prev + ad);
+                                else emit_bin<false>(c, s - 1, up_prev + ad);
+                            }
+                            up_prev = au;
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // staging complete
+        }
+
+        // ================= phase C: copy-out, zero padding, statistics =================
+        if (a.out != nullptr && nrows > 0) {
+            float* obase = a.out + ((long long)utt * a.Tmax + f0) * a.nmel;
+            const int nv = nvalid * a.nmel, nt = nrows * a.nmel;     // tile output is contiguous in global memory
+            if (nvalid > 0) {
+                // element e = row * nmel + col  <->  staging row * (nmel + 1) + col
+                int e = tid;
+                int row = e / a.nmel, col = e - row * a.nmel;
+                const int drow = kThreads / a.nmel, dcol = kThreads - drow * a.nmel;
+                for (; e < nv; e += kThreads) {
+                    obase[e] = outs[row * ostride + col];
+                    col += dcol; row += drow;
+                    if (col >= a.nmel) { col -= a.nmel; row += 1; }
+                }
+            }
+            // rows past the utterance end are zero (pad_audio = 0)
+            if (nt > nv) {
+                if ((a.nmel & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+                    float4* z4 = reinterpret_cast<float4*>(obase);
+                    for (int q = (nv >> 2) + tid; q < (nt >> 2); q += kThreads) z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    for (int e = nv + tid; e < nt; e += kThreads) obase[e] = 0.f;
+                }
+            }
+        }
+        if (a.out_len != nullptr && f0 == 0 && tid == 0) a.out_len[utt] = g.T;
+        if (a.stats != nullptr && nvalid > 0) {
+            const int nb = a.n_cls - 1;
+            const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
+            double* sb = a.stats + (long long)utt * a.stats_stride;
+            for (int j = tid; j < a.nmel; j += kThreads) {
+                int cls = bounds ? row_class(bounds, nb, f0) : 0;
+                float s1 = 0.f, s2 = 0.f;
+                for (int fr = 0; fr < nvalid; ++fr) {
+                    if (bounds) {
+                        const int cc = row_class(bounds, nb, f0 + fr);
+                        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, (double)s1); s1 = 0.f; cls = cc; }
+                    }
+                    const float x = outs[fr * ostride + j];
+                    s1 += x;
+                    s2 = fmaf(x, x, s2);
+                }
+                atomicAdd(sb + (long long)cls * a.nmel + j, (double)s1);
+                atomicAdd(sb + (long long)a.n_cls * a.nmel + j, (double)s2);
+            }
+        }
+        // the staging area aliases the transposition buffers that the next phase A overwrites
+        if (nvalid > 0) __syncthreads();
+        g = gn;
+    }
+}
+
+}  // namespace b200fe

@@ -1,0 +1,353 @@
+"""Batched GPU front end: the drop-in for the reference's per-utterance feature extraction.
+
+Mirrors the call signature of ``WavToKaldiFbank`` (lasr/data/datatrans.py:42-71) in its
+constructor and produces the batch layout of ``AudioDataSet.MergeBatch``
+(lasr/data/dataset.py:181-220): ``feats (B, Tmax, num_mel_bins) float32`` zero padded and
+``feat_len (B,) int64`` frame counts.  All arithmetic runs in the C-ABI CUDA library; torch is
+used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, specaug as _specaug
+
+_WINDOWS = {"povey": 0, "hanning": 1, "hamming": 2, "rectangular": 3, "blackman": 4}
+_CMVN_MODES = ("none", "utt_mean", "utt_meanvar", "global")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _torch_window(window_type, size, blackman_coeff):
+    """Same torch expressions as torchaudio (TA:86-113) so the table matches bit for bit."""
+    import math
+    if window_type == "hanning":
+        return torch.hann_window(size, periodic=False)
+    if window_type == "hamming":
+        return torch.hamming_window(size, periodic=False, alpha=0.54, beta=0.46)
+    if window_type == "povey":
+        return torch.hann_window(size, periodic=False).pow(0.85)
+    if window_type == "rectangular":
+        return torch.ones(size)
+    if window_type == "blackman":
+        a = 2 * math.pi / (size - 1)
+        n = torch.arange(size, dtype=torch.float32)
+        return blackman_coeff - 0.5 * torch.cos(a * n) + (0.5 - blackman_coeff) * torch.cos(2 * a * n)
+    raise Exception("Invalid window type " + window_type)
+
+
+def _torch_mel_banks(num_bins, padded, sample_freq, low_freq, high_freq):
+    """torch restatement of get_mel_banks (TA:436-511, vtln_warp == 1) evaluated with the same
+    float32 tensor operations, so the weights equal torchaudio's bit for bit on this torch."""
+    import math
+    num_fft_bins = padded / 2
+    nyquist = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyquist
+    fft_bin_width = sample_freq / padded
+    mel_low = 1127.0 * math.log(1.0 + low_freq / 700.0)
+    mel_high = 1127.0 * math.log(1.0 + high_freq / 700.0)
+    delta = (mel_high - mel_low) / (num_bins + 1)
+    b = torch.arange(num_bins).unsqueeze(1)
+    left = mel_low + b * delta
+    center = mel_low + (b + 1.0) * delta
+    right = mel_low + (b + 2.0) * delta
+    mel = (1127.0 * (1.0 + (fft_bin_width * torch.arange(num_fft_bins)) / 700.0).log()).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    return torch.max(torch.zeros(1), torch.min(up, down)).float().contiguous()
+
+
+class FbankPlan:
+    """Owns a ``b200fe_plan`` (device tables for one option set on the current device)."""
+
+    def __init__(self, num_mel_bins=80, sample_frequency=16000.0, frame_length=25.0, frame_shift=10.0,
+                 low_freq=20.0, high_freq=0.0, preemphasis_coefficient=0.97, remove_dc_offset=True,
+                 use_power=True, use_log_fbank=True, window_type="povey", blackman_coeff=0.42, audio_bit=16,
+                 torch_tables=True):
+        if window_type not in _WINDOWS:
+            raise Exception("Invalid window type " + window_type)
+        self.lib = _lib.load()
+        o = _lib.Opts()
+        self.lib.b200fe_default_opts(C.byref(o))
+        o.sample_frequency = sample_frequency
+        o.frame_length_ms = frame_length
+        o.frame_shift_ms = frame_shift
+        o.num_mel_bins = num_mel_bins
+        o.low_freq = low_freq
+        o.high_freq = high_freq
+        o.preemphasis_coefficient = preemphasis_coefficient
+        o.remove_dc_offset = int(bool(remove_dc_offset))
+        o.use_power = int(bool(use_power))
+        o.use_log_fbank = int(bool(use_log_fbank))
+        o.window_type = _WINDOWS[window_type]
+        o.blackman_coeff = blackman_coeff
+        o.audio_bit = audio_bit
+        keep = []
+        if torch_tables:
+            win = int(sample_frequency * frame_length * 0.001)
+            padded = 1 if win == 0 else 2 ** (win - 1).bit_length()
+            w = _torch_window(window_type, win, blackman_coeff).float().contiguous()
+            m = _torch_mel_banks(num_mel_bins, padded, sample_frequency, low_freq, high_freq)
+            keep = [w, m]
+            o.window = w.data_ptr()
+            o.mel_weights = m.data_ptr()
+        h = C.c_void_p()
+        _lib.check(self.lib.b200fe_plan_create(C.byref(o), C.byref(h)), "b200fe_plan_create")
+        del keep
+        self.handle = h
+        self.num_mel_bins = num_mel_bins
+        self.window_size = self.lib.b200fe_window_size(h)
+        self.window_shift = self.lib.b200fe_window_shift(h)
+        self.sample_frequency = sample_frequency
+
+    def num_frames(self, n):
+        return int(self.lib.b200fe_num_frames(self.handle, int(n)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.b200fe_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class GpuFbankFrontend(torch.nn.Module):
+    """fbank (+ peak norm) (+ CMVN) (+ SpecAugment masks) over a padded batch, on one GPU.
+
+    forward(wav, wav_len) -> (feats, feat_len)
+      wav      float32 CUDA tensor (B, Nmax), zero padded -- what the unmodified reference dataset
+               yields with ``audio_trans: [avgchannel]`` (dataset.py:196-206)
+      wav_len  int64 (B,) sample counts, CPU (preferred, no sync) or CUDA
+      feats    float32 CUDA (B, Tmax, num_mel_bins), rows >= feat_len[b] are 0
+      feat_len int64 CUDA (B,)  -- the ``wav_len`` entry of the reference batch dict
+    """
+
+    def __init__(self, num_mel_bins=80, dither=0.0, energy_floor=1.0, frame_length=25.0, frame_shift=10.0,
+                 high_freq=0.0, low_freq=20.0, preemphasis_coefficient=0.97, remove_dc_offset=True,
+                 round_to_power_of_two=True, sample_frequency=16000.0, snip_edges=True, use_energy=False,
+                 use_log_fbank=True, use_power=True, vtln_warp=1.0, window_type="povey", blackman_coeff=0.42,
+                 audio_bit=16, peak_norm=False, cmvn="none", cmvn_stats=None, specaug=False,
+                 max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2, replace_with_zero=False,
+                 consume_time_warp_draws=False, l2_chunk_bytes=48 << 20):
+        super().__init__()
+        if not snip_edges or use_energy or vtln_warp != 1.0 or not round_to_power_of_two:
+            raise ValueError("snip_edges=False, use_energy=True, vtln_warp != 1 and round_to_power_of_two=False "
+                             "are not reachable from LASR configs and are not implemented")
+        if dither != 0.0:
+            raise ValueError("dither != 0 is not implemented yet (LASR default is 0.0, datatrans.py:47)")
+        if cmvn not in _CMVN_MODES:
+            raise ValueError("cmvn must be one of %s" % (_CMVN_MODES,))
+        self.opts = dict(num_mel_bins=num_mel_bins, sample_frequency=sample_frequency, frame_length=frame_length,
+                         frame_shift=frame_shift, low_freq=low_freq, high_freq=high_freq,
+                         preemphasis_coefficient=preemphasis_coefficient, remove_dc_offset=remove_dc_offset,
+                         use_power=use_power, use_log_fbank=use_log_fbank, window_type=window_type,
+                         blackman_coeff=blackman_coeff, audio_bit=audio_bit)
+        self.num_mel_bins = num_mel_bins
+        self.peak_norm = peak_norm
+        self.cmvn = cmvn
+        self.specaug = specaug
+        self.replace_with_zero = replace_with_zero
+        self.sa = dict(max_freq_width=max_freq_width, n_freq_mask=n_freq_mask, max_time_width=max_time_width,
+                       n_time_mask=n_time_mask, consume_time_warp_draws=consume_time_warp_draws)
+        self.l2_chunk_bytes = l2_chunk_bytes
+        self._plans = {}
+        self.register_buffer("cmvn_mean", None, persistent=False)
+        self.register_buffer("cmvn_istd", None, persistent=False)
+        if cmvn == "global":
+            if cmvn_stats is None:
+                raise ValueError("cmvn='global' needs cmvn_stats ([2, D+1] Kaldi statistics or a (mean, istd) pair)")
+            self.set_global_cmvn(cmvn_stats)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def plan(self, device):
+        key = torch.device(device).index or 0
+        if key not in self._plans:
+            with torch.cuda.device(key):
+                self._plans[key] = FbankPlan(**self.opts)
+        return self._plans[key]
+
+    def set_global_cmvn(self, stats, norm_vars=True):
+        if isinstance(stats, (tuple, list)) and len(stats) == 2:
+            mean, istd = (torch.as_tensor(np.asarray(s), dtype=torch.float32) for s in stats)
+        else:
+            st = np.ascontiguousarray(np.asarray(stats, dtype=np.float64))
+            d = self.num_mel_bins
+            if st.shape != (2, d + 1):
+                raise ValueError("cmvn statistics must have shape (2, %d)" % (d + 1))
+            mean_np = np.zeros(d, dtype=np.float32)
+            istd_np = np.zeros(d, dtype=np.float32)
+            lib = _lib.load()
+            _lib.check(lib.b200fe_cmvn_from_stats(st.ctypes.data_as(C.POINTER(C.c_double)), d, int(norm_vars),
+                                                  mean_np.ctypes.data_as(_lib.c_fp), istd_np.ctypes.data_as(_lib.c_fp)),
+                       "b200fe_cmvn_from_stats")
+            mean, istd = torch.from_numpy(mean_np), torch.from_numpy(istd_np)
+        self.cmvn_mean = mean.contiguous()
+        self.cmvn_istd = istd.contiguous()
+
+    def frame_counts(self, wav_len):
+        p = self.opts
+        win = int(p["sample_frequency"] * p["frame_length"] * 0.001)
+        shift = int(p["sample_frequency"] * p["frame_shift"] * 0.001)
+        n = np.asarray(wav_len, dtype=np.int64)
+        return np.where(n >= win, 1 + (n - win) // shift, 0), win
+
+    # -- the hot path ------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, wav, wav_len, max_frames=None, masks=None):
+        if not wav.is_cuda:
+            raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
+        if wav.dim() != 2 or wav.dtype != torch.float32:
+            raise ValueError("wav must be float32 (B, Nmax)")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        dev = wav.device
+        B = wav.shape[0]
+        plan = self.plan(dev)
+        lib = plan.lib
+        if torch.is_tensor(wav_len) and wav_len.is_cuda:
+            len_host = wav_len.cpu().numpy() if (self.specaug or max_frames is None) else None
+            len_dev = wav_len.to(torch.int64).contiguous()
+        else:
+            len_host = np.asarray(wav_len, dtype=np.int64).reshape(-1)
+            len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+        if len_host is not None:
+            T_host, win = self.frame_counts(len_host)
+            if (len_host < win).any():
+                # torchaudio asserts (TA:142); LASR filters min_duration upstream (dataset.py:243,272)
+                raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
+            if (len_host > wav.shape[1]).any():
+                raise ValueError("wav_len exceeds the padded width")
+            Tmax = int(T_host.max()) if max_frames is None else int(max_frames)
+        else:
+            T_host, Tmax = None, int(max_frames)
+        D = self.num_mel_bins
+        feats = torch.empty((B, Tmax, D), dtype=torch.float32, device=dev)
+        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        peak = None
+        if self.peak_norm:
+            peak = torch.empty((B,), dtype=torch.float32, device=dev)
+            _lib.check(lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), _ptr(len_dev), B, _ptr(peak), stream),
+                       "b200fe_peak_absmax")
+
+        n_f = n_t = 0
+        masks_dev = bounds_dev = None
+        if self.specaug:
+            if masks is None:
+                m_np, b_np = _specaug.plan_batch(T_host, D, **self.sa)
+            else:
+                m_np = np.ascontiguousarray(masks, dtype=np.int32)
+                n_f_, n_t_ = self.sa["n_freq_mask"], self.sa["n_time_mask"]
+                b_np = np.sort(m_np[:, n_f_:].reshape(B, -1), axis=1).astype(np.int32)
+            n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
+            masks_dev = torch.from_numpy(m_np).to(dev, non_blocking=True)
+            bounds_dev = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev, non_blocking=True)
+        mean_fill = self.specaug and not self.replace_with_zero
+        utt_cmvn = self.cmvn in ("utt_mean", "utt_meanvar")
+        need_post = mean_fill or utt_cmvn
+        n_cls = (2 * n_t + 1) if mean_fill else 1
+
+        gm = gi = None
+        if self.cmvn == "global":
+            gm = self.cmvn_mean.to(dev)
+            gi = self.cmvn_istd.to(dev)
+            self.cmvn_mean, self.cmvn_istd = gm, gi
+
+        # Utterance groups sized so that a group's features stay L2-resident between the fused
+        # launch and the in-place post pass.
+        if need_post:
+            per_utt = Tmax * D * 4
+            group = max(1, min(B, self.l2_chunk_bytes // max(per_utt, 1)))
+        else:
+            group = B
+        stats = cm = ci = fills = None
+        if need_post:
+            stats = torch.zeros((B, n_cls + 1, D), dtype=torch.float64, device=dev)
+            if utt_cmvn:
+                cm = torch.empty((B, D), dtype=torch.float32, device=dev)
+                ci = torch.empty((B, D), dtype=torch.float32, device=dev)
+            if mean_fill:
+                fills = torch.empty((B, n_f + n_t), dtype=torch.float32, device=dev)
+
+        def off(t, b0, per):
+            return C.c_void_p(t.data_ptr() + b0 * per) if t is not None else C.c_void_p(0)
+
+        for b0 in range(0, B, group):
+            nb = min(group, B - b0)
+            a = _lib.FbankArgs()
+            a.d_wav = off(wav, b0, wav.stride(0) * 4)
+            a.wav_stride = wav.stride(0)
+            a.d_nsamp = off(len_dev, b0, 8)
+            a.batch = nb
+            a.d_peak = off(peak, b0, 4)
+            a.d_out = off(feats, b0, Tmax * D * 4)
+            a.d_out_len = off(feat_len, b0, 8)
+            a.max_frames = Tmax
+            if gm is not None:
+                a.d_cmvn_mean, a.d_cmvn_istd, a.cmvn_stride = _ptr(gm), _ptr(gi), 0
+            if self.specaug:
+                a.d_masks = off(masks_dev, b0, (n_f + n_t) * 2 * 4)
+                a.n_freq_masks, a.n_time_masks = n_f, n_t
+                a.mask_zero = int(self.replace_with_zero)
+            if need_post:
+                a.d_stats = off(stats, b0, (n_cls + 1) * D * 8)
+                a.stats_stride = (n_cls + 1) * D
+                a.n_row_classes = n_cls
+                if mean_fill:
+                    a.d_row_bounds = off(bounds_dev, b0, 2 * n_t * 4)
+            _lib.check(lib.b200fe_fbank_fused(plan.handle, C.byref(a), stream), "b200fe_fbank_fused")
+            if need_post:
+                q = _lib.PostArgs()
+                q.d_feats = a.d_out
+                q.d_nsamp = a.d_nsamp
+                q.batch = nb
+                q.max_frames = Tmax
+                q.d_stats = a.d_stats
+                q.stats_stride = a.stats_stride
+                q.d_row_bounds = a.d_row_bounds
+                q.n_row_classes = n_cls
+                q.cmvn_mode = {"utt_mean": 1, "utt_meanvar": 2}.get(self.cmvn, 0)
+                q.d_cmvn_mean = off(cm, b0, D * 4)
+                q.d_cmvn_istd = off(ci, b0, D * 4)
+                if mean_fill:
+                    q.d_masks = a.d_masks
+                    q.n_freq_masks, q.n_time_masks = n_f, n_t
+                    q.d_fills = off(fills, b0, (n_f + n_t) * 4)
+                _lib.check(lib.b200fe_postpass(plan.handle, C.byref(q), stream), "b200fe_postpass")
+        self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak)
+        return feats, feat_len
+
+    # -- global CMVN statistics (Kaldi compute-cmvn-stats), one fused pass without feature output --
+    @torch.no_grad()
+    def accumulate_stats(self, wav, wav_len, stats=None):
+        """Adds this batch's [sum | count ; sumsq | 0] to ``stats`` (float64 CUDA [2, D+1])."""
+        dev = wav.device
+        plan = self.plan(dev)
+        B, D = wav.shape[0], self.num_mel_bins
+        len_host = np.asarray(wav_len.cpu() if torch.is_tensor(wav_len) else wav_len, dtype=np.int64).reshape(-1)
+        T_host, win = self.frame_counts(len_host)
+        len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+        if stats is None:
+            stats = torch.zeros((2, D + 1), dtype=torch.float64, device=dev)
+        acc = torch.zeros((2, D), dtype=torch.float64, device=dev)
+        peak = None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if self.peak_norm:
+            peak = torch.empty((B,), dtype=torch.float32, device=dev)
+            _lib.check(plan.lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), _ptr(len_dev), B, _ptr(peak), stream),
+                       "b200fe_peak_absmax")
+        a = _lib.FbankArgs()
+        a.d_wav, a.wav_stride, a.d_nsamp, a.batch = _ptr(wav), wav.stride(0), _ptr(len_dev), B
+        a.d_peak = _ptr(peak)
+        a.max_frames = int(T_host.max())
+        a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 0, 1
+        _lib.check(plan.lib.b200fe_fbank_fused(plan.handle, C.byref(a), stream), "b200fe_fbank_fused")
+        stats[:, :D] += acc
+        stats[0, D] += float(T_host.sum())
+        return stats

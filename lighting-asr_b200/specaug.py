@@ -1,0 +1,75 @@
+"""Host side of SpecAugment: replays the reference's RNG consumption and emits rectangles.
+
+The reference (lasr/utils/specaugment.py:47-106, driven by lasr/data/datatrans.py:106-151) draws
+mask geometry from TWO global generators -- ``numpy.random`` (legacy MT19937 global state) and
+CPython's ``random`` -- in a fixed interleaved order, per utterance, in batch order
+(lasr/data/dataset.py:190-198).  To be bit-exact on mask positions for the same seeds the host
+code here calls the very same global functions in the same order; only the *application* of the
+rectangles (and the running mean fills) happens on the GPU.
+"""
+import random
+
+import numpy as np
+
+MAX_FREQ_MASKS = 4
+MAX_TIME_MASKS = 4
+
+
+def _draw_time_warp(num_frames, window):
+    """Consumes exactly the draws of time_warp (specaugment.py:20-24) without warping."""
+    if num_frames - window <= window:
+        return None
+    center = random.randrange(window, num_frames - window)
+    warped = random.randrange(center - window, center + window) + 1
+    return center, warped
+
+
+def plan_utterance(num_frames, num_mel, max_freq_width=27, n_freq_mask=2, max_time_width=40,
+                   n_time_mask=2, consume_time_warp_draws=False, max_time_warp=5):
+    """Rectangles for ONE utterance, in application order (frequency masks, then time masks).
+
+    Returns (freq, time): int32 arrays [n_freq_mask, 2] / [n_time_mask, 2] of (start, stop),
+    already clipped the way numpy slicing clips; skipped or empty masks are (0, 0).
+    """
+    if consume_time_warp_draws:
+        _draw_time_warp(num_frames, max_time_warp)
+    freq = np.zeros((n_freq_mask, 2), dtype=np.int32)
+    fs = np.random.randint(0, max_freq_width, size=(n_freq_mask, 2))  # specaugment.py:61
+    for i, (f, w) in enumerate(fs):
+        f0 = random.randrange(0, num_mel - int(f))  # :64 -- drawn before the skip test
+        if int(f) == 0:  # :68-69
+            continue
+        lo, hi = min(f0, num_mel), min(f0 + int(w), num_mel)
+        if hi > lo:
+            freq[i] = (lo, hi)
+    time = np.zeros((n_time_mask, 2), dtype=np.int32)
+    ts = np.random.randint(0, max_time_width, size=(n_time_mask, 2))  # :90
+    for i, (t, w) in enumerate(ts):
+        if num_frames - int(t) <= 0:  # :93-94, no draw
+            continue
+        t0 = random.randrange(0, num_frames - int(t))  # :95
+        if int(t) == 0:  # :98-99
+            continue
+        lo, hi = min(t0, num_frames), min(t0 + int(w), num_frames)
+        if hi > lo:
+            time[i] = (lo, hi)
+    return freq, time
+
+
+def plan_batch(frame_lens, num_mel, **kw):
+    """Rectangles for a batch, utterances visited in order (dataset.py:190).
+
+    Returns (masks [B, n_f + n_t, 2] int32, row_bounds [B, 2 n_t] int32 sorted)."""
+    n_f = kw.get("n_freq_mask", 2)
+    n_t = kw.get("n_time_mask", 2)
+    if n_f > MAX_FREQ_MASKS or n_t > MAX_TIME_MASKS:
+        raise ValueError("at most %d frequency and %d time masks are supported" % (MAX_FREQ_MASKS, MAX_TIME_MASKS))
+    B = len(frame_lens)
+    masks = np.zeros((B, n_f + n_t, 2), dtype=np.int32)
+    bounds = np.zeros((B, 2 * n_t), dtype=np.int32)
+    for b, T in enumerate(frame_lens):
+        f, t = plan_utterance(int(T), num_mel, **kw)
+        masks[b, :n_f] = f
+        masks[b, n_f:] = t
+        bounds[b] = np.sort(t.reshape(-1))
+    return masks, bounds

@@ -1,0 +1,132 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): |gpu - oracle| <= 1e-5 + 1e-4 |oracle| in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import fbank_parity, tol_violations
+from oracle import kaldi_fbank, lasr_frontend
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad_batch(wavs, dev, align=4):
+    n = np.array([len(w) for w in wavs], dtype=np.int64)
+    nmax = int((n.max() + align - 1) // align * align)
+    buf = np.zeros((len(wavs), nmax), dtype=np.float32)
+    for i, w in enumerate(wavs):
+        buf[i, : len(w)] = w
+    return torch.from_numpy(buf).to(dev), n
+
+
+def _ta_fbank(w):
+    from torchaudio.compliance import kaldi
+    x = torch.from_numpy(np.asarray(w, dtype=np.float32)).unsqueeze(0) * 32768.0
+    return kaldi.fbank(x, num_mel_bins=80, dither=0.0, energy_floor=1.0, frame_length=25.0, frame_shift=10.0,
+                       low_freq=20.0, high_freq=0.0, preemphasis_coefficient=0.97, remove_dc_offset=True,
+                       sample_frequency=16000.0, window_type="povey").numpy()
+
+
+def test_c1_uniform_batch(lasr_b200):
+    """BASELINE config 1: 16 utt x 10 s, uniform(-0.5, 0.5), dither 0 (seed 0)."""
+    rng = np.random.default_rng(0)
+    wavs = [rng.uniform(-0.5, 0.5, 160000) for _ in range(16)]
+    fe = lasr_b200.GpuFbankFrontend()
+    wav, n = _pad_batch(wavs, "cuda:0")
+    feats, flen = fe(wav, n)
+    torch.cuda.synchronize()
+    assert feats.shape == (16, 998, 80) and feats.dtype == torch.float32
+    assert flen.cpu().tolist() == [998] * 16
+    g = feats.cpu().numpy()
+    worst, n_below, n_direct = 0.0, 0, 0
+    for i, w in enumerate(wavs):
+        ref = lasr_frontend.wav_to_kaldi_fbank(w)                       # numpy restatement (oracle)
+        ta = _ta_fbank(w)                                               # the reference's arithmetic library, live
+        ref64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64)
+        lin64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64, use_log_fbank=False)
+        for r32 in (ta, ref):
+            hard, soft, below = fbank_parity(g[i], r32, ref64, lin64)
+            assert hard == 0 and soft == 0
+        n_below += below
+        n_direct += tol_violations(g[i], ta)
+        worst = max(worst, float(np.abs(g[i] - ta).max()))
+    # the noise-floor carve-out must stay a vanishing fraction of the cells
+    assert n_below <= 1e-4 * g.size
+    assert n_direct <= 1e-5 * g.size
+    print("max |gpu - torchaudio| =", worst, "cells below fp32 noise floor:", n_below, "direct violations:", n_direct)
+
+
+def test_variable_length_padding(lasr_b200):
+    """Ragged batch: frame counts TA:63-67, zero padded rows (dataset.py:18,205)."""
+    rng = np.random.default_rng(1)
+    lens = [400, 401, 559, 560, 561, 719, 720, 16000, 16001, 35 * 16000, 12345, 99999]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    fe = lasr_b200.GpuFbankFrontend()
+    wav, n = _pad_batch(wavs, "cuda:0")
+    feats, flen = fe(wav, n)
+    g = feats.cpu().numpy()
+    T = [kaldi_fbank.num_frames(x) for x in lens]
+    assert flen.cpu().tolist() == T
+    assert g.shape[1] == max(T)
+    for i, w in enumerate(wavs):
+        ref = _ta_fbank(w)
+        assert ref.shape[0] == T[i]
+        ref64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64)
+        lin64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64, use_log_fbank=False)
+        hard, soft, _ = fbank_parity(g[i, : T[i]], ref, ref64, lin64)
+        assert hard == 0 and soft == 0
+        assert np.all(g[i, T[i]:] == 0.0)
+
+
+def test_unaligned_stride_uses_generic_loader(lasr_b200):
+    """A padded width that is not a multiple of 4 floats cannot use the TMA path; results must agree."""
+    rng = np.random.default_rng(2)
+    wavs = [rng.uniform(-0.5, 0.5, n) for n in (16001, 8003, 31999)]
+    fe = lasr_b200.GpuFbankFrontend()
+    wav_a, n = _pad_batch(wavs, "cuda:0", align=4)
+    wav_u, _ = _pad_batch(wavs, "cuda:0", align=1)
+    assert wav_u.shape[1] % 4 != 0
+    fa, _ = fe(wav_a, n)
+    fu, _ = fe(wav_u, n)
+    assert torch.equal(fa, fu)
+
+
+def test_silence_and_dc_known_answers(lasr_b200):
+    """Digital silence / pure DC -> every output is log(eps) = -15.942385."""
+    fe = lasr_b200.GpuFbankFrontend()
+    wav = torch.zeros((2, 16000), device="cuda:0")
+    wav[1] = 0.25
+    feats, _ = fe(wav, np.array([16000, 16000]))
+    g = feats.cpu().numpy()
+    assert np.allclose(g[0], -15.942385, atol=1e-5)
+    assert np.allclose(g[1], -15.942385, atol=1e-5)
+
+
+def test_short_utterance_raises(lasr_b200):
+    """torchaudio asserts window_size <= len(waveform) (TA:142)."""
+    fe = lasr_b200.GpuFbankFrontend()
+    wav = torch.zeros((1, 400), device="cuda:0")
+    with pytest.raises(AssertionError):
+        fe(wav, np.array([399]))
+
+
+def test_other_option_sets(lasr_b200):
+    """Non-default options reachable through WavToKaldiFbank's signature (datatrans.py:43-71)."""
+    from torchaudio.compliance import kaldi
+    rng = np.random.default_rng(3)
+    w = rng.uniform(-0.5, 0.5, 48000)
+    x = torch.from_numpy(w.astype(np.float32)).unsqueeze(0) * 32768.0
+    for kw in (dict(num_mel_bins=40, window_type="hamming"),
+               dict(num_mel_bins=23, window_type="hanning", preemphasis_coefficient=0.0),
+               dict(num_mel_bins=80, remove_dc_offset=False, low_freq=0.0, high_freq=-400.0),
+               dict(num_mel_bins=64, window_type="rectangular", use_log_fbank=False),
+               dict(num_mel_bins=80, frame_length=20.0, frame_shift=12.5, window_type="blackman"),
+               dict(num_mel_bins=80, use_power=False)):
+        fe = lasr_b200.GpuFbankFrontend(**kw)
+        wav, n = _pad_batch([w], "cuda:0")
+        g = fe(wav, n)[0][0].cpu().numpy()
+        ref = kaldi.fbank(x, dither=0.0, energy_floor=1.0, sample_frequency=16000.0, **kw).numpy()
+        assert g.shape == ref.shape, kw
+        assert tol_violations(g, ref) == 0, kw
