@@ -97,7 +97,7 @@ typedef struct b200fe_fbank_args {
     long long cmvn_stride;
     /* SpecAugment rectangles per utterance: [n_freq_masks + n_time_masks][2] int32 (start, stop),
      * frequency masks first (R/lasr/utils/specaugment.py:47-106).  mask_zero = 1 zeroes them in this
-     * launch (replace_with_zero=True); mask_zero = 0 leaves them to b200fe_specaug_fill (mean fill). */
+     * launch (replace_with_zero=True); mask_zero = 0 leaves them to b200fe_postpass, which computes the mean fills. */
     const int* d_masks;
     int n_freq_masks, n_time_masks;
     int mask_zero;

@@ -66,10 +66,13 @@ struct b200fe_plan {
     int ctas_per_sm;
 };
 
-static const void* plan_kernel(const b200fe_plan* p)
+static const void* plan_kernel(const b200fe_plan* p, bool peak)
 {
-    if (p->nload == 13) return p->static_mel ? (const void*)fbank_fused_kernel<13, true> : (const void*)fbank_fused_kernel<13, false>;
-    return (const void*)fbank_fused_kernel<16, false>;
+    if (p->nload == 13) {
+        if (p->static_mel) return peak ? (const void*)fbank_fused_kernel<13, true, true> : (const void*)fbank_fused_kernel<13, true, false>;
+        return peak ? (const void*)fbank_fused_kernel<13, false, true> : (const void*)fbank_fused_kernel<13, false, false>;
+    }
+    return peak ? (const void*)fbank_fused_kernel<16, false, true> : (const void*)fbank_fused_kernel<16, false, false>;
 }
 
 extern "C" void b200fe_default_opts(b200fe_opts* o)
@@ -245,8 +248,9 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         for (int k = 0; same && k < 256; ++k) same = (p->w_updn[k].x == kStaticUp[k] && p->w_updn[k].y == kStaticDn[k]);
         p->static_mel = same ? 1 : 0;
     }
-    const void* kfn = plan_kernel(p);
+    const void* kfn = plan_kernel(p, false);
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
     if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kThreads, p->smem_bytes);
@@ -339,7 +343,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     const int grid = (int)std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm);
     cudaStream_t st = (cudaStream_t)stream;
     void* kargs[] = {(void*)&a};
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
     return B200FE_OK;
 }
 

@@ -105,7 +105,7 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     o += (xbytes > obytes ? xbytes : obytes);
     L.outs_off = L.xbuf_off;
     L.pt_off = o; o += 64 * kPTStride * 16;
-    L.misc_off = o; o += (2 * kMaxMel + 4) * 4;
+    L.misc_off = o; o += (2 * kMaxMel + 8) * 4 + 256 * 8;
     L.bar_off = o; o += 8 * kStages;
     L.total = o;
     return L;
@@ -132,33 +132,18 @@ struct TileGeom {
     int utt, f0, nvalid, nrows, T;
 };
 
-// Epilogue of one mel bin for one frame (phase B): floored log, CMVN, zero masks, staging store.
-struct EpiCtx {
-    const float* s_mean;
-    const float* s_istd;
-    float* orow;              // staging row of this lane's frame
-    unsigned cmask[4];        // column bits that are zero-masked
-    float log_floor;
-    bool use_log, row_masked, valid;
-};
-
-template <bool kLog>
-__device__ __forceinline__ void emit_bin(const EpiCtx& c, int j, float e)
-{
-    if (kLog) e = fast_log(fmaxf(e, c.log_floor));
-    e = (e - c.s_mean[j]) * c.s_istd[j];
-    const bool z = c.row_masked || ((c.cmask[j >> 5] >> (j & 31)) & 1u) || !c.valid;
-    c.orow[j] = z ? 0.f : e;
-}
+// Phase B only stores the raw mel energy of (frame, bin) into the staging tile; log / CMVN / masks are
+// applied by the compact, warp-uniform phase C so that the straight-line mel code stays small.
+__device__ __forceinline__ void emit_bin(float* orow, int j, float e) { orow[j] = e; }
 
 #define B200FE_MEL_DEVICE_CODE
-#define MGROUP_BEGIN(w) template <bool kLog> __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, const EpiCtx& c) { \
+#define MGROUP_BEGIN(w) __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, float* __restrict__ orow) { \
         float au = 0.f, ad = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
 #define MK(k, wu, wd) { if (((k) >> 2) != cur) { cur = (k) >> 2; p4 = pcol[cur * kPTStride]; } \
         const float p = ((k) & 3) == 0 ? p4.x : ((k) & 3) == 1 ? p4.y : ((k) & 3) == 2 ? p4.z : p4.w; \
         if ((wu) != 0.f) au = fmaf((wu), p, au); if ((wd) != 0.f) ad = fmaf((wd), p, ad); }
 #define MEND0() { up_prev = au; au = 0.f; ad = 0.f; }
-#define MEND(j) { emit_bin<kLog>(c, (j), up_prev + ad); up_prev = au; au = 0.f; ad = 0.f; }
+#define MEND(j) { emit_bin(orow, (j), up_prev + ad); up_prev = au; au = 0.f; ad = 0.f; }
 #define MGROUP_END(w) }
 #include "mel_static_default.inc"
 #undef MGROUP_BEGIN
@@ -168,7 +153,7 @@ __device__ __forceinline__ void emit_bin(const EpiCtx& c, int j, float e)
 #undef MGROUP_END
 #undef B200FE_MEL_DEVICE_CODE
 
-template <int NLOAD, bool kStaticMel>
+template <int NLOAD, bool kStaticMel, bool kPeak>
 __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -178,14 +163,14 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     float* outs = reinterpret_cast<float*>(smem + L.outs_off);
     float* s_mean = reinterpret_cast<float*>(smem + L.misc_off);
     float* s_istd = s_mean + kMaxMel;
-    unsigned* s_cmask = reinterpret_cast<unsigned*>(s_istd + kMaxMel);
+    unsigned* s_cmask = reinterpret_cast<unsigned*>(s_istd + kMaxMel);   // [0..3] column bits, [4] row bits
+    float2* s_stw = reinterpret_cast<float2*>(s_cmask + 8);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int h2 = lane >> 4, l = lane & 15;
     const int hw = warp * 2 + h2;
-    const unsigned hmask = 0xFFFFu << (16 * h2);
     float2* xbuf = xbuf_all + hw * 16 * kXRow;
     const int ostride = a.nmel + 1;
 
@@ -199,9 +184,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     float2 tw[16];
 #pragma unroll
     for (int k = 1; k < 16; ++k) tw[k] = __ldg(a.twiddle + l * 16 + k);
-    float2 stw[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) stw[r] = __ldg(a.split_tw + l + 16 * r);
+    // split twiddles -j W_512^k live in shared memory (lane l reads k = l + 16 r: conflict free)
+    for (int k = tid; k < 256; k += kThreads) s_stw[k] = __ldg(a.split_tw + k);
+    const float2* stw = s_stw + l;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -214,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         s_mean[tid] = on ? __ldg(a.cm_mean + tid) : 0.f;
         s_istd[tid] = on ? __ldg(a.cm_istd + tid) : 1.f;
     }
-    if (tid < 4) s_cmask[tid] = 0u;
+    if (tid < 8) s_cmask[tid] = 0u;
     __syncthreads();
 
     const float c_pre = a.preemph;
@@ -283,11 +268,17 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
                 if (lane == 0) s_cmask[warp] = bal;
             }
+            if (zmask && warp == 4) {
+                const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
+                bool m = false;
+                for (int i = 0; i < a.n_tmask; ++i) m |= (f0 + lane >= __ldg(mk + 2 * i) && f0 + lane < __ldg(mk + 2 * i + 1));
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) s_cmask[4] = bal;
+            }
 
             // ================= phase A: half-warp per frame =================
             float pscale = 1.0f, prcp = 0.0f, pmax = 1.0f;
-            const bool has_peak = (a.peak != nullptr);
-            if (has_peak) {
+            if (kPeak) {
                 // reference: x / (max + 1e-9) in fp64, rounded to fp32, times 2^(bits-1) (datatrans.py:24-25,73-74)
                 pmax = __ldg(a.peak + utt);
                 prcp = (float)(1.0 / ((double)pmax + 1e-9));
@@ -297,8 +288,11 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             for (int sub = 0; sub < 2; ++sub) {
                 // frame slot inside the tile; concurrent half-warps of a warp are 4 frames apart so that
                 // their PT stores fall into disjoint banks
+                // Both half-warps run in lock step (full-mask shuffles); a half-warp whose frame is past the
+                // utterance end computes on stale shared memory and simply skips its stores.
                 const int fl = (warp & 3) + 4 * h2 + 8 * (warp >> 2) + 16 * sub;
-                if (fl < nvalid) {
+                const bool fvalid = fl < nvalid;
+                if (fl - 4 * h2 < nvalid) {
                     const float* xf = xs + fl * a.shift + 2 * l;
                     float2 v[16];
                     // Load, (peak-normalise,) pre-emphasise; accumulate the frame sum on the fly so that
@@ -310,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                         const int j = 2 * (l + 16 * n2);
                         float2 xr = *reinterpret_cast<const float2*>(xf + 32 * n2);
                         float xp = (n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1];   // replicate pad at the frame start (TA:195)
-                        if (has_peak) {
+                        if (kPeak) {
                             xr.x = peak_div(xr.x, pmax, prcp) * pscale;
                             xr.y = peak_div(xr.y, pmax, prcp) * pscale;
                             xp = peak_div(xp, pmax, prcp) * pscale;
@@ -327,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     }
                     float sum = acc2.x + acc2.y;
 #pragma unroll
-                    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+                    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                     const float cdc = sum * inv_win * dc_coef;   // (1 - preemph) * frame mean
 #pragma unroll
                     for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(sub2(v[n2], bc(cdc)), wreg[n2]);
@@ -341,10 +335,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     // ---- transpose through shared memory: row n1 = l, column klo ----
 #pragma unroll
                     for (int k = 0; k < 16; ++k) xbuf[l * kXRow + k] = v[k];
-                    __syncwarp(hmask);
+                    __syncwarp();
 #pragma unroll
                     for (int n1 = 0; n1 < 16; ++n1) v[n1] = xbuf[n1 * kXRow + l];
-                    __syncwarp(hmask);
+                    __syncwarp();
                     // ---- pass 2: DFT-16 over n1 -> Z[l + 16 r] in v[r] ----
                     dft16(v);
                     // ---- conjugate-pair exchange: own r = 0..7 pairs with lane (16-l)&15, register 15-r ----
@@ -352,8 +346,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     float2 rc[8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        rc[r].x = __shfl_sync(hmask, v[15 - r].x, partner);
-                        rc[r].y = __shfl_sync(hmask, v[15 - r].y, partner);
+                        rc[r].x = __shfl_sync(0xffffffffu, v[15 - r].x, partner);
+                        rc[r].y = __shfl_sync(0xffffffffu, v[15 - r].y, partner);
                     }
                     if (l == 0) {   // bins 16 r pair with 16 (16 - r): shift by one register, bin 0 pairs with itself
 #pragma unroll
@@ -368,15 +362,16 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     for (int r = 0; r < 8; ++r) {
                         float2 bcj = make_float2(rc[r].x, -rc[r].y);
                         float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
-                        float2 T = c_mul(D, stw[r].x, stw[r].y);
+                        const float2 sw = stw[16 * r];
+                        float2 T = c_mul(D, sw.x, sw.y);
                         float2 xa = add2(S, T), xb = sub2(S, T);
                         xa = mul2(xa, xa); xb = mul2(xb, xb);
                         float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
                         if (!a.use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
-                        pa[r * 4 * kPTStride * 4] = pwa;
-                        if (r != 0 || l != 0) pb[-r * 4 * kPTStride * 4] = pwb;
+                        if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
+                        if (fvalid && (r != 0 || l != 0)) pb[-r * 4 * kPTStride * 4] = pwb;
                     }
-                    if (l == 0) {   // bin 128 is its own partner: X[128] = conj Z[128]
+                    if (l == 0 && fvalid) {   // bin 128 is its own partner: X[128] = conj Z[128]
                         float2 z = v[8];
                         float p = 4.0f * (z.x * z.x + z.y * z.y);
                         if (!a.use_power) p = sqrtf(p);
@@ -389,40 +384,18 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             // ================= phase B: warp = mel-bin group, lane = frame =================
             {
                 const int fl = lane;
-                const int t = f0 + fl;
-                EpiCtx c;
-                c.s_mean = s_mean; c.s_istd = s_istd; c.orow = outs + fl * ostride;
-                c.log_floor = a.log_floor; c.use_log = a.use_log != 0; c.valid = fl < nvalid; c.row_masked = false;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c.cmask[i] = zmask ? s_cmask[i] : 0u;
-                if (zmask) {
-                    const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
-                    for (int i = 0; i < a.n_tmask; ++i) c.row_masked |= (t >= __ldg(mk + 2 * i) && t < __ldg(mk + 2 * i + 1));
-                }
+                float* orow = outs + fl * ostride;
                 const float4* pcol = reinterpret_cast<const float4*>(pt) + fl;
                 if (kStaticMel) {
-                    if (a.use_log) {
-                        switch (warp) {
-                            case 0: mel_static_group0<true>(pcol, c); break;
-                            case 1: mel_static_group1<true>(pcol, c); break;
-                            case 2: mel_static_group2<true>(pcol, c); break;
-                            case 3: mel_static_group3<true>(pcol, c); break;
-                            case 4: mel_static_group4<true>(pcol, c); break;
-                            case 5: mel_static_group5<true>(pcol, c); break;
-                            case 6: mel_static_group6<true>(pcol, c); break;
-                            default: mel_static_group7<true>(pcol, c); break;
-                        }
-                    } else {
-                        switch (warp) {
-                            case 0: mel_static_group0<false>(pcol, c); break;
-                            case 1: mel_static_group1<false>(pcol, c); break;
-                            case 2: mel_static_group2<false>(pcol, c); break;
-                            case 3: mel_static_group3<false>(pcol, c); break;
-                            case 4: mel_static_group4<false>(pcol, c); break;
-                            case 5: mel_static_group5<false>(pcol, c); break;
-                            case 6: mel_static_group6<false>(pcol, c); break;
-                            default: mel_static_group7<false>(pcol, c); break;
-                        }
+                    switch (warp) {
+                        case 0: mel_static_group0(pcol, orow); break;
+                        case 1: mel_static_group1(pcol, orow); break;
+                        case 2: mel_static_group2(pcol, orow); break;
+                        case 3: mel_static_group3(pcol, orow); break;
+                        case 4: mel_static_group4(pcol, orow); break;
+                        case 5: mel_static_group5(pcol, orow); break;
+                        case 6: mel_static_group6(pcol, orow); break;
+                        default: mel_static_group7(pcol, orow); break;
                     }
                 } else {
                     const int jb = a.grp_begin[warp], je = a.grp_begin[warp + 1];
@@ -440,10 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                                 au = fmaf(w.x, p, au);
                                 ad = fmaf(w.y, p, ad);
                             }
-                            if (s > jb) {
-                                if (c.use_log) emit_bin<true>(c, s - 1, up_prev + ad);
-                                else emit_bin<false>(c, s - 1, up_prev + ad);
-                            }
+                            if (s > jb) emit_bin(orow, s - 1, up_prev + ad);
                             up_prev = au;
                         }
                     }
@@ -452,23 +422,31 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             __syncthreads();   // staging complete
         }
 
-        // ================= phase C: copy-out, zero padding, statistics =================
-        if (a.out != nullptr && nrows > 0) {
-            float* obase = a.out + ((long long)utt * a.Tmax + f0) * a.nmel;
-            const int nv = nvalid * a.nmel, nt = nrows * a.nmel;     // tile output is contiguous in global memory
+        // ================= phase C: epilogue + copy-out, zero padding, statistics =================
+        // element e = row * nmel + col of the tile (contiguous in global memory) <-> staging row*(nmel+1)+col
+        {
+            float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * a.nmel : nullptr;
+            const int nv = nvalid * a.nmel, nt = nrows * a.nmel;
             if (nvalid > 0) {
-                // element e = row * nmel + col  <->  staging row * (nmel + 1) + col
+                const unsigned rmask = zmask ? s_cmask[4] : 0u;
+                const bool wb = a.stats != nullptr;       // statistics read the transformed values back
                 int e = tid;
                 int row = e / a.nmel, col = e - row * a.nmel;
                 const int drow = kThreads / a.nmel, dcol = kThreads - drow * a.nmel;
                 for (; e < nv; e += kThreads) {
-                    obase[e] = outs[row * ostride + col];
+                    float* sp = outs + row * ostride + col;
+                    float x = *sp;
+                    if (a.use_log) x = fast_log(fmaxf(x, a.log_floor));
+                    x = (x - s_mean[col]) * s_istd[col];
+                    if (zmask && (((rmask >> row) & 1u) || ((s_cmask[col >> 5] >> (col & 31)) & 1u))) x = 0.f;
+                    if (obase) obase[e] = x;
+                    if (wb) *sp = x;
                     col += dcol; row += drow;
                     if (col >= a.nmel) { col -= a.nmel; row += 1; }
                 }
             }
             // rows past the utterance end are zero (pad_audio = 0)
-            if (nt > nv) {
+            if (obase && nt > nv) {
                 if ((a.nmel & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
                     float4* z4 = reinterpret_cast<float4*>(obase);
                     for (int q = (nv >> 2) + tid; q < (nt >> 2); q += kThreads) z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -479,23 +457,24 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         }
         if (a.out_len != nullptr && f0 == 0 && tid == 0) a.out_len[utt] = g.T;
         if (a.stats != nullptr && nvalid > 0) {
+            __syncthreads();
             const int nb = a.n_cls - 1;
             const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
             double* sb = a.stats + (long long)utt * a.stats_stride;
             for (int j = tid; j < a.nmel; j += kThreads) {
                 int cls = bounds ? row_class(bounds, nb, f0) : 0;
-                float s1 = 0.f, s2 = 0.f;
+                double s1 = 0.0, s2 = 0.0;
                 for (int fr = 0; fr < nvalid; ++fr) {
                     if (bounds) {
                         const int cc = row_class(bounds, nb, f0 + fr);
-                        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, (double)s1); s1 = 0.f; cls = cc; }
+                        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
                     }
-                    const float x = outs[fr * ostride + j];
+                    const double x = (double)outs[fr * ostride + j];
                     s1 += x;
-                    s2 = fmaf(x, x, s2);
+                    s2 = fma(x, x, s2);
                 }
-                atomicAdd(sb + (long long)cls * a.nmel + j, (double)s1);
-                atomicAdd(sb + (long long)a.n_cls * a.nmel + j, (double)s2);
+                atomicAdd(sb + (long long)cls * a.nmel + j, s1);
+                atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
             }
         }
         // the staging area aliases the transposition buffers that the next phase A overwrites

@@ -1,0 +1,101 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
+with empty stub modules for the absent librosa / soundfile) together with the image's
+torchaudio 2.11.0.  TEST INFRASTRUCTURE; run in the build container only:
+
+    python -m oracle.gen_golden
+
+The fixtures pin the CPU oracle (tests/test_oracle_golden.py) and, through it, the CUDA path.
+"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def import_reference():
+    for name in ("librosa", "soundfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import lasr.data.datatrans as dt           # noqa: E402
+    import lasr.utils.specaugment as sa        # noqa: E402
+    from lasr.data.dataset import batch_list   # noqa: E402
+    return dt, sa, batch_list
+
+
+def pattern(T, D=80):
+    t = np.arange(T, dtype=np.float64)[:, None]
+    d = np.arange(D, dtype=np.float64)[None, :]
+    return (10.0 + 3.0 * np.sin(0.37 * t + 0.11 * d) + 0.05 * d - 0.002 * t).astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    dt, sa, batch_list = import_reference()
+    reg = dt.register_trans
+    import torch
+    import torchaudio
+
+    # ---- fbank:80 / norm on short seeded waveforms (what soundfile.read would return: float64) ----
+    rng = np.random.default_rng(1234)
+    fb = {}
+    for i, n in enumerate((400, 559, 560, 4000, 8000, 12345)):
+        kind = i % 3
+        if kind == 0:
+            w = rng.uniform(-0.5, 0.5, n)
+        elif kind == 1:
+            w = np.clip(rng.normal(0, 0.1, n), -1, 1)
+        else:  # speech-like: decaying spectrum + noise, quantised like int16 PCM
+            t = np.arange(n) / 16000.0
+            w = 0.3 * np.sin(2 * np.pi * 180 * t) + 0.1 * np.sin(2 * np.pi * 1230 * t + 1.0) + 0.02 * rng.standard_normal(n)
+            w = np.round(w * 32768.0) / 32768.0
+        fb["wav_%d" % i] = w
+        fb["fbank_%d" % i] = reg["fbank:80"](w)
+        fb["norm_%d" % i] = reg["norm"](w)
+        fb["norm_fbank_%d" % i] = reg["fbank:80"](reg["norm"](w))
+        # subtract_mean is the only CMVN-like option on the reference's call path (datatrans.py:62)
+        fb["fbank_cms_%d" % i] = dt.WavToKaldiFbank(w, subtract_mean=True)
+    fb["batch_list"] = batch_list([fb["fbank_%d" % i] for i in range(6)], pad_value=0)
+    fb["versions"] = np.array([torch.__version__, torchaudio.__version__, np.__version__])
+    np.savez_compressed(os.path.join(OUT, "fbank_reference.npz"), **fb)
+
+    # ---- SpecAugment masks (freq_mask then time_mask exactly as datatrans.py:137-150 calls them) ----
+    sg = {}
+    cases = []
+    for seed in range(6):
+        for T in (5, 12, 39, 98, 300):
+            x = pattern(T)
+            random.seed(seed)
+            np.random.seed(seed)
+            y = x.copy()
+            y = sa.freq_mask(y, 27, 2, inplace=True, replace_with_zero=False)
+            y = sa.time_mask(y, 40, 2, inplace=True, replace_with_zero=False)
+            after = np.array([random.random(), np.random.rand()])
+            key = "s%d_T%d" % (seed, T)
+            sg[key + "_out"] = y
+            sg[key + "_rng_after"] = after
+            # replace_with_zero variant consumes the same draws
+            random.seed(seed)
+            np.random.seed(seed)
+            z = x.copy()
+            z = sa.freq_mask(z, 27, 2, inplace=True, replace_with_zero=True)
+            z = sa.time_mask(z, 40, 2, inplace=True, replace_with_zero=True)
+            sg[key + "_zero_changed"] = np.packbits(z != x)
+            # full registry transform (time warp first): only the RNG position afterwards is recorded
+            random.seed(seed)
+            np.random.seed(seed)
+            reg["specaug"](x.copy())
+            sg[key + "_rng_after_full"] = np.array([random.random(), np.random.rand()])
+            cases.append(key)
+    sg["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(OUT, "specaug_reference.npz"), **sg)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    main()

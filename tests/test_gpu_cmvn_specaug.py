@@ -1,0 +1,156 @@
+"""GPU parity: peak normalisation, CMVN (utterance / global) and SpecAugment masks vs the oracle."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import fbank_parity
+from oracle import kaldi_fbank, lasr_frontend
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pad(wavs, align=4):
+    n = np.array([len(w) for w in wavs], dtype=np.int64)
+    nmax = int((n.max() + align - 1) // align * align)
+    buf = np.zeros((len(wavs), nmax), dtype=np.float32)
+    for i, w in enumerate(wavs):
+        buf[i, : len(w)] = w
+    return torch.from_numpy(buf).to(DEV), n
+
+
+def _close(got, ref, rtol=1e-4, atol=1e-5):
+    return int((np.abs(got.astype(np.float64) - ref) > atol + rtol * np.abs(ref)).sum())
+
+
+def test_peak_norm(lasr_b200):
+    """VoiceNorm (datatrans.py:22-27) folded into the fused launch: abs-max is exact, the features
+    match the oracle chain norm -> fbank:80."""
+    rng = np.random.default_rng(5)
+    wavs = [rng.uniform(-a, a, n).astype(np.float32).astype(np.float64) for a, n in ((0.5, 16000), (0.05, 23457), (0.9, 8000))]
+    fe = lasr_b200.GpuFbankFrontend(peak_norm=True)
+    wav, n = _pad(wavs)
+    feats, flen = fe(wav, n)
+    g = feats.cpu().numpy()
+    peak = fe.last["peak"].cpu().numpy()
+    for i, w in enumerate(wavs):
+        assert peak[i] == np.float32(np.abs(w).max())
+        xn = lasr_frontend.voice_norm(w)
+        ref = lasr_frontend.wav_to_kaldi_fbank(xn, use_torchaudio=True)
+        r64 = lasr_frontend.wav_to_kaldi_fbank(xn, dtype=np.float64)
+        lin = lasr_frontend.wav_to_kaldi_fbank(xn, dtype=np.float64, use_log_fbank=False)
+        T = ref.shape[0]
+        hard, soft, _ = fbank_parity(g[i, :T], ref, r64, lin)
+        assert hard == 0 and soft == 0
+        assert np.all(g[i, T:] == 0)
+
+
+def test_utterance_cmvn(lasr_b200):
+    """BASELINE config 2 semantics on a small ragged batch: fbank + utterance CMVN (mean, var)."""
+    rng = np.random.default_rng(1)
+    lens = [400, 4000, 16000, 16000 * 7 + 13, 16000 * 3, 959, 35 * 16000]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    raw = lasr_b200.GpuFbankFrontend()(wav, n)[0].cpu().numpy()
+    for mode, nv in (("utt_meanvar", True), ("utt_mean", False)):
+        fe = lasr_b200.GpuFbankFrontend(cmvn=mode, l2_chunk_bytes=3 << 20)     # forces several utterance groups
+        feats, flen = fe(wav, n)
+        g = feats.cpu().numpy()
+        for i, w in enumerate(wavs):
+            T = kaldi_fbank.num_frames(len(w))
+            assert int(flen[i]) == T
+            # (a) the CMVN stage itself, given the device's own fbank output
+            ref = lasr_frontend.utterance_cmvn(raw[i, :T], norm_vars=nv)
+            assert _close(g[i, :T], ref.astype(np.float64)) == 0
+            assert np.all(g[i, T:] == 0)
+            # (b) end to end against the reference fbank: fbank tolerance propagated through the affine map
+            ta = lasr_frontend.wav_to_kaldi_fbank(w, use_torchaudio=True)
+            mean, istd = lasr_frontend.cmvn_from_stats(lasr_frontend.cmvn_stats([ta]), nv)
+            e2e = lasr_frontend.apply_cmvn(ta, mean, istd).astype(np.float64)
+            r64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64)
+            lin = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64, use_log_fbank=False)
+            ok = (lin / lin.sum(1, keepdims=True)) >= 1e-8
+            tol = (1e-5 + 1e-4 * np.abs(ta)) * istd[None, :] + 2e-5
+            if T > 1 or not nv:
+                assert int(((np.abs(g[i, :T] - e2e) > tol) & ok).sum()) == 0
+
+
+def _run_specaug(lasr_b200, wavs, seed, replace_with_zero, cmvn_stats):
+    wav, n = _pad(wavs)
+    fe = lasr_b200.GpuFbankFrontend(cmvn="global", cmvn_stats=cmvn_stats, specaug=True, replace_with_zero=replace_with_zero)
+    random.seed(seed)
+    np.random.seed(seed)
+    feats, flen = fe(wav, n)
+    return fe, feats.cpu().numpy()
+
+
+def test_global_cmvn_and_specaug_masks(lasr_b200):
+    """BASELINE config 3 semantics (small batch): fbank + global CMVN + 2 freq / 2 time masks.
+    Mask POSITIONS are bit-exact for the same seeds (specaugment.py:47-106); fills within tolerance."""
+    rng = np.random.default_rng(2)
+    lens = [160000, 160000, 48000, 7 * 16000 + 77, 6000, 1200]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    plain = lasr_b200.GpuFbankFrontend()
+    raw = plain(wav, n)[0].cpu().numpy()
+    T = [kaldi_fbank.num_frames(x) for x in lens]
+    # statistics pass (no feature output) vs the fp64 definition on the device's own features
+    st = plain.accumulate_stats(wav, n).cpu().numpy()
+    ref_st = lasr_frontend.cmvn_stats([raw[i, : T[i]] for i in range(len(lens))])
+    assert st.shape == (2, 81) and st[0, 80] == sum(T)
+    assert np.allclose(st, ref_st, rtol=1e-9, atol=1e-6)
+    mean, istd = lasr_frontend.cmvn_from_stats(ref_st)
+    for zero in (False, True):
+        fe, g = _run_specaug(lasr_b200, wavs, 11, zero, st)
+        random.seed(11)
+        np.random.seed(11)
+        for i in range(len(lens)):
+            x = lasr_frontend.apply_cmvn(raw[i, : T[i]], mean, istd)
+            base = x.copy()
+            y, rects = lasr_frontend.spec_augment_masks(x, replace_with_zero=zero)   # oracle, same RNG streams, same order
+            gi = g[i, : T[i]]
+            masked = np.zeros_like(base, dtype=bool)
+            for kind, lo, hi, _ in rects:
+                if kind == "f":
+                    masked[:, max(lo, 0):max(hi, 0)] = True
+                else:
+                    masked[max(lo, 0):max(hi, 0)] = True
+            # un-masked cells are the CMVN'd features, masked cells carry the oracle's value
+            assert _close(gi[~masked], base[~masked].astype(np.float64)) == 0
+            if zero:
+                assert np.all(gi[masked] == 0)
+            else:
+                assert _close(gi[masked], y[masked].astype(np.float64), rtol=1e-4, atol=2e-5) == 0
+            # positions: exactly the planned rectangles changed
+            assert np.array_equal(masked, lasr_b200_mask(fe, i, T[i]))
+            assert np.all(g[i, T[i]:] == 0)
+
+
+def lasr_b200_mask(fe, i, T):
+    m = fe.last["masks"].cpu().numpy()[i]
+    out = np.zeros((T, 80), dtype=bool)
+    for lo, hi in m[:2]:
+        out[:, lo:hi] = True
+    for lo, hi in m[2:]:
+        out[lo:hi] = True
+    return out
+
+
+def test_specaug_without_cmvn_mean_fill(lasr_b200):
+    """specaug directly on log-mel (LASR's own chain norm -> fbank:80 -> specaug has no CMVN)."""
+    rng = np.random.default_rng(9)
+    wavs = [rng.uniform(-0.5, 0.5, n) for n in (32000, 16000 * 4 + 5, 3000)]
+    wav, n = _pad(wavs)
+    raw = lasr_b200.GpuFbankFrontend()(wav, n)[0].cpu().numpy()
+    fe = lasr_b200.GpuFbankFrontend(specaug=True)
+    random.seed(4)
+    np.random.seed(4)
+    g = fe(wav, n)[0].cpu().numpy()
+    random.seed(4)
+    np.random.seed(4)
+    for i, w in enumerate(wavs):
+        T = kaldi_fbank.num_frames(len(w))
+        y, _ = lasr_frontend.spec_augment_masks(raw[i, :T].copy())
+        assert _close(g[i, :T], y.astype(np.float64), rtol=1e-4, atol=2e-5) == 0

@@ -129,4 +129,11 @@ def test_other_option_sets(lasr_b200):
         g = fe(wav, n)[0][0].cpu().numpy()
         ref = kaldi.fbank(x, dither=0.0, energy_floor=1.0, sample_frequency=16000.0, **kw).numpy()
         assert g.shape == ref.shape, kw
-        assert tol_violations(g, ref) == 0, kw
+        okw = dict(kw)
+        ref64 = kaldi_fbank.fbank(w.astype(np.float32) * np.float32(32768.0), dtype=np.float64, **okw)
+        okw["use_log_fbank"] = False
+        okw["use_power"] = True
+        lin64 = kaldi_fbank.fbank(w.astype(np.float32) * np.float32(32768.0), dtype=np.float64, **okw)
+        hard, soft, below = fbank_parity(g, ref, ref64, lin64)
+        assert hard == 0 and soft == 0, kw
+        assert below <= 1e-3 * g.size, kw

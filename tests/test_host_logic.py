@@ -1,0 +1,130 @@
+"""CPU: host-side logic of the product (no CUDA needed): SpecAugment RNG replay against the
+reference fixtures, CMVN statistics helpers, C-ABI library symbols, plugin boundary."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sg():
+    return np.load(os.path.join(GOLD, "specaug_reference.npz"))
+
+
+def _pattern(T):
+    from oracle.gen_golden import pattern
+    return pattern(T)
+
+
+def _apply(masks_f, masks_t, T, D=80):
+    m = np.zeros((T, D), dtype=bool)
+    for lo, hi in masks_f:
+        m[:, lo:hi] = True
+    for lo, hi in masks_t:
+        m[lo:hi] = True
+    return m
+
+
+def test_planner_positions_bit_exact(lasr_b200, sg):
+    """Mask rectangles planned by the product equal the cells the reference overwrote
+    (specaugment.py:47-106) for the same seeds; both RNG streams end in the same state."""
+    for key in sg["cases"]:
+        seed, T = int(key.split("_")[0][1:]), int(key.split("_T")[1])
+        random.seed(seed)
+        np.random.seed(seed)
+        f, t = lasr_b200.specaug.plan_utterance(T, 80)
+        assert np.array_equal(np.array([random.random(), np.random.rand()]), sg[key + "_rng_after"]), key
+        planned = _apply(f, t, T)
+        assert np.array_equal(np.packbits(planned), sg[key + "_zero_changed"]), key
+        x = _pattern(T)
+        changed = sg[key + "_out"] != x
+        assert not np.any(changed & ~planned), key     # mean fill may coincide with a value, never exceed the plan
+
+
+def test_planner_can_consume_time_warp_draws(lasr_b200, sg):
+    """With consume_time_warp_draws the planner leaves both generators where the reference's full
+    ``specaug`` transform (warp + masks, datatrans.py:136-150) leaves them."""
+    for key in sg["cases"]:
+        seed, T = int(key.split("_")[0][1:]), int(key.split("_T")[1])
+        random.seed(seed)
+        np.random.seed(seed)
+        lasr_b200.specaug.plan_utterance(T, 80, consume_time_warp_draws=True)
+        assert np.array_equal(np.array([random.random(), np.random.rand()]), sg[key + "_rng_after_full"]), key
+
+
+def test_plan_batch_layout(lasr_b200):
+    random.seed(3)
+    np.random.seed(3)
+    masks, bounds = lasr_b200.specaug.plan_batch([98, 300, 12], 80)
+    assert masks.shape == (3, 4, 2) and masks.dtype == np.int32
+    assert bounds.shape == (3, 4) and np.all(np.diff(bounds, axis=1) >= 0)
+    assert np.all(masks[:, :2] <= 80) and np.all(masks[0, 2:] <= 98) and np.all(masks[2, 2:] <= 12)
+    with pytest.raises(ValueError):
+        lasr_b200.specaug.plan_batch([98], 80, n_time_mask=9)
+
+
+def test_header_symbols_exported(lasr_b200):
+    """Every function declared in include/b200fe.h is exported by the built library."""
+    hdr = open(os.path.join(ROOT, "include", "b200fe.h")).read()
+    names = set(re.findall(r"\b(b200fe_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"b200fe_opts", "b200fe_plan", "b200fe_fbank_args", "b200fe_post_args"}
+    assert {"b200fe_plan_create", "b200fe_fbank_fused", "b200fe_postpass", "b200fe_peak_absmax"} <= names
+    lib = lasr_b200._lib.load()
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert names == set(lasr_b200._lib.EXPORTS)
+
+
+def test_cmvn_from_stats_host_function(lasr_b200):
+    from oracle import lasr_frontend
+    rng = np.random.default_rng(1)
+    feats = [rng.normal(2, 3, (T, 80)).astype(np.float32) for T in (20, 33)]
+    st = lasr_frontend.cmvn_stats(feats)
+    lib = lasr_b200._lib.load()
+    mean = np.zeros(80, np.float32)
+    istd = np.zeros(80, np.float32)
+    rc = lib.b200fe_cmvn_from_stats(np.ascontiguousarray(st).ctypes.data_as(C.POINTER(C.c_double)), 80, 1,
+                                    mean.ctypes.data_as(lasr_b200._lib.c_fp), istd.ctypes.data_as(lasr_b200._lib.c_fp))
+    assert rc == 0
+    m, s = lasr_frontend.cmvn_from_stats(st)
+    assert np.allclose(mean, m, rtol=1e-6) and np.allclose(istd, s, rtol=1e-6)
+    m2, s2 = lasr_b200.cmvn.mean_istd(st)
+    assert np.array_equal(m2, mean) and np.array_equal(s2, istd)
+    bad = np.zeros((2, 81))
+    assert lib.b200fe_cmvn_from_stats(bad.ctypes.data_as(C.POINTER(C.c_double)), 80, 1,
+                                      mean.ctypes.data_as(lasr_b200._lib.c_fp), istd.ctypes.data_as(lasr_b200._lib.c_fp)) < 0
+    assert b"zero frame count" in lib.b200fe_last_error()
+
+
+def test_stats_file_roundtrip(lasr_b200, tmp_path):
+    st = np.arange(2 * 81, dtype=np.float64).reshape(2, 81) * 1.5 + 0.1
+    p = str(tmp_path / "cmvn.stats")
+    lasr_b200.cmvn.save_stats(p, st)
+    assert np.array_equal(lasr_b200.cmvn.load_stats(p), st)
+
+
+def test_shard_utterances_balanced(lasr_b200):
+    rng = np.random.default_rng(0)
+    n = (rng.uniform(1, 35, 256) * 16000).astype(np.int64)
+    for ws in (1, 2, 4, 8):
+        parts = lasr_b200.cmvn.shard_utterances(n, ws)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(256))
+        loads = np.array([n[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= n.max()
+
+
+def test_no_cpu_path(lasr_b200):
+    import torch
+    fe = lasr_b200.GpuFbankFrontend()
+    with pytest.raises(RuntimeError):
+        fe(torch.zeros(1, 16000), np.array([16000]))
+    with pytest.raises(ValueError):
+        lasr_b200.GpuFbankFrontend(snip_edges=False)
+    with pytest.raises(ValueError):
+        lasr_b200.GpuFbankFrontend(cmvn="global")

@@ -1,0 +1,116 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(oracle/gen_golden.py: lasr.data.datatrans / lasr.utils.specaugment / batch_list + torchaudio 2.11.0)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import fbank_parity
+from oracle import kaldi_fbank, lasr_frontend
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def fb():
+    return np.load(os.path.join(GOLD, "fbank_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def sg():
+    return np.load(os.path.join(GOLD, "specaug_reference.npz"))
+
+
+def test_frame_counts_known_answers():
+    # N=160000 -> 998, 1 s -> 98, 35 s -> 3498 ; TA:63-67
+    assert kaldi_fbank.num_frames(160000) == 998
+    assert kaldi_fbank.num_frames(16000) == 98
+    assert kaldi_fbank.num_frames(35 * 16000) == 3498
+    assert kaldi_fbank.num_frames(399) == 0 and kaldi_fbank.num_frames(400) == 1
+    assert kaldi_fbank.num_frames(559) == 1 and kaldi_fbank.num_frames(560) == 2
+    assert kaldi_fbank.window_properties(16000) == (160, 400, 512)
+    assert kaldi_fbank.window_properties(8000, sample_frequency=8000.0) == (80, 200, 256)
+    with pytest.raises(AssertionError):
+        kaldi_fbank.window_properties(399)
+
+
+def test_fbank_matches_reference_fixture(fb):
+    for i in range(6):
+        w = fb["wav_%d" % i]
+        ref = fb["fbank_%d" % i]
+        got = lasr_frontend.wav_to_kaldi_fbank(w)
+        r64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64)
+        lin = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64, use_log_fbank=False)
+        assert got.shape == ref.shape and got.dtype == np.float32
+        hard, soft, _ = fbank_parity(got, ref, r64, lin)
+        assert hard == 0 and soft == 0
+        hard, soft, _ = fbank_parity(r64, ref, r64, lin)      # the fp64 oracle agrees with the reference too
+        assert hard == 0 and soft == 0
+
+
+def test_silence_is_log_eps():
+    out = lasr_frontend.wav_to_kaldi_fbank(np.zeros(4000))
+    assert np.all(out == np.float32(np.log(np.float32(kaldi_fbank.EPSILON))))
+    assert abs(float(out[0, 0]) + 15.942385) < 1e-6
+
+
+def test_voice_norm_bit_exact(fb):
+    for i in range(6):
+        assert np.array_equal(lasr_frontend.voice_norm(fb["wav_%d" % i]), fb["norm_%d" % i])
+
+
+def test_norm_then_fbank(fb):
+    for i in range(6):
+        w = fb["wav_%d" % i]
+        got = lasr_frontend.wav_to_kaldi_fbank(lasr_frontend.voice_norm(w))
+        r64 = lasr_frontend.wav_to_kaldi_fbank(lasr_frontend.voice_norm(w), dtype=np.float64)
+        lin = lasr_frontend.wav_to_kaldi_fbank(lasr_frontend.voice_norm(w), dtype=np.float64, use_log_fbank=False)
+        hard, soft, _ = fbank_parity(got, fb["norm_fbank_%d" % i], r64, lin)
+        assert hard == 0 and soft == 0
+
+
+def test_subtract_mean_pins_utterance_mean_normalisation(fb):
+    """fbank(subtract_mean=True) (TA:220-226) is the only CMVN-like op on the reference's path; the
+    oracle's utterance mean normalisation must reproduce it."""
+    for i in range(6):
+        raw = fb["fbank_%d" % i]
+        got = lasr_frontend.utterance_cmvn(raw, norm_vars=False)
+        assert np.allclose(got, fb["fbank_cms_%d" % i], rtol=0, atol=2e-5)
+
+
+def test_batch_list(fb):
+    got = lasr_frontend.batch_list([fb["fbank_%d" % i] for i in range(6)], pad_value=0)
+    assert np.array_equal(got, fb["batch_list"])
+
+
+def _pattern(T):
+    from oracle.gen_golden import pattern
+    return pattern(T)
+
+
+def test_specaug_masks_match_reference(sg):
+    for key in sg["cases"]:
+        seed, T = int(key.split("_")[0][1:]), int(key.split("_T")[1])
+        random.seed(seed)
+        np.random.seed(seed)
+        x = _pattern(T)
+        y, rects = lasr_frontend.spec_augment_masks(x.copy())
+        assert np.array_equal(y, sg[key + "_out"]), key          # positions AND fills, bit for bit
+        assert np.array_equal(np.array([random.random(), np.random.rand()]), sg[key + "_rng_after"]), key
+        random.seed(seed)
+        np.random.seed(seed)
+        z, _ = lasr_frontend.spec_augment_masks(x.copy(), replace_with_zero=True)
+        assert np.array_equal(np.packbits(z != x), sg[key + "_zero_changed"]), key
+
+
+def test_cmvn_definition():
+    rng = np.random.default_rng(0)
+    feats = [rng.normal(3, 2, (T, 80)).astype(np.float32) for T in (10, 57, 300)]
+    st = lasr_frontend.cmvn_stats(feats)
+    assert st.shape == (2, 81) and st[0, 80] == 367 and st[1, 80] == 0
+    mean, istd = lasr_frontend.cmvn_from_stats(st)
+    cat = np.concatenate(feats).astype(np.float64)
+    assert np.allclose(mean, cat.mean(0)) and np.allclose(istd, 1 / cat.std(0))
+    y = lasr_frontend.utterance_cmvn(feats[2])
+    assert np.allclose(y.mean(0), 0, atol=1e-5) and np.allclose(y.std(0), 1, atol=1e-4)

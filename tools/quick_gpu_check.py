@@ -36,3 +36,23 @@ ms = e0.elapsed_time(e1) / K
 hours = B2 * N2 / 16000 / 3600
 frames = B2 * (1 + (N2 - 400) // 160)
 print("ms/step %.3f  audio-h/s %.1f  GB/s(alg) %.1f  ns/frame %.3f" % (ms, hours / (ms * 1e-3), (4 * B2 * N2 + 320 * frames) / (ms * 1e-3) / 1e9, ms * 1e6 / frames))
+
+# raw C-ABI launch timing (no Python allocation in the loop)
+import ctypes as C
+from importlib import import_module
+L = import_module("lighting-asr_b200._lib")
+plan = fe.plan(dev)
+T2 = int(1 + (N2 - 400) // 160)
+out = torch.empty((B2, T2, 80), device=dev)
+nd = torch.from_numpy(n2).to(dev)
+a = L.FbankArgs()
+a.d_wav = wav2.data_ptr(); a.wav_stride = wav2.stride(0); a.d_nsamp = nd.data_ptr(); a.batch = B2
+a.d_out = out.data_ptr(); a.max_frames = T2
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for _ in range(3): L.check(plan.lib.b200fe_fbank_fused(plan.handle, C.byref(a), st), "x")
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20): plan.lib.b200fe_fbank_fused(plan.handle, C.byref(a), st)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 20
+print("RAW kernel: ms %.4f  audio-h/s %.1f  GB/s(alg) %.1f  ns/frame %.3f  static_mel=%d" % (ms, hours / (ms * 1e-3), (4 * B2 * N2 + 320 * frames) / (ms * 1e-3) / 1e9, ms * 1e6 / frames, plan.lib.b200fe_plan_info(plan.handle, 0)))
