@@ -156,6 +156,9 @@ class GpuFbankFrontend(torch.nn.Module):
                        n_time_mask=n_time_mask, consume_time_warp_draws=consume_time_warp_draws)
         self.l2_chunk_bytes = l2_chunk_bytes
         self._plans = {}
+        self._host_cache = {}
+        self.launch_count = 0           # kernels launched by this object (bench.py reports it)
+        self.profile_events = None      # set to [] to collect (start, stop) CUDA events around every fused launch
         self.register_buffer("cmvn_mean", None, persistent=False)
         self.register_buffer("cmvn_istd", None, persistent=False)
         if cmvn == "global":
@@ -198,7 +201,7 @@ class GpuFbankFrontend(torch.nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, wav, wav_len, max_frames=None, masks=None):
+    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None):
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
         if wav.dim() != 2 or wav.dtype != torch.float32:
@@ -226,15 +229,22 @@ class GpuFbankFrontend(torch.nn.Module):
         else:
             T_host, Tmax = None, int(max_frames)
         D = self.num_mel_bins
-        feats = torch.empty((B, Tmax, D), dtype=torch.float32, device=dev)
-        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if out is not None:
+            if out.shape != (B, Tmax, D) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+                raise ValueError("out must be a contiguous float32 (B, Tmax, D) tensor on the input's device")
+            feats = out
+        else:
+            feats = torch.empty((B, Tmax, D), dtype=torch.float32, device=dev)
+        feat_len = out_len if out_len is not None else torch.empty((B,), dtype=torch.int64, device=dev)
+        cur_stream = torch.cuda.current_stream(dev)
+        stream = C.c_void_p(cur_stream.cuda_stream)
 
         peak = None
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
             _lib.check(lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), _ptr(len_dev), B, _ptr(peak), stream),
                        "b200fe_peak_absmax")
+            self.launch_count += 2          # memset + abs-max kernel
 
         n_f = n_t = 0
         masks_dev = bounds_dev = None
@@ -301,7 +311,15 @@ class GpuFbankFrontend(torch.nn.Module):
                 a.n_row_classes = n_cls
                 if mean_fill:
                     a.d_row_bounds = off(bounds_dev, b0, 2 * n_t * 4)
+            if self.profile_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(cur_stream)
             _lib.check(lib.b200fe_fbank_fused(plan.handle, C.byref(a), stream), "b200fe_fbank_fused")
+            self.launch_count += 1
+            if self.profile_events is not None:
+                e1.record(cur_stream)
+                self.profile_events.append((e0, e1))
             if need_post:
                 q = _lib.PostArgs()
                 q.d_feats = a.d_out
@@ -320,8 +338,66 @@ class GpuFbankFrontend(torch.nn.Module):
                     q.n_freq_masks, q.n_time_masks = n_f, n_t
                     q.d_fills = off(fills, b0, (n_f + n_t) * 4)
                 _lib.check(lib.b200fe_postpass(plan.handle, C.byref(q), stream), "b200fe_postpass")
+                self.launch_count += 2      # finalize + in-place post pass
         self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak)
         return feats, feat_len
+
+    # -- host-to-host path: the drop-in for the reference's collate_fn (features back on the host) --
+    @torch.no_grad()
+    def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True):
+        """Pipelined H2D copy -> fused kernels -> D2H copy over utterance groups on three streams.
+
+        wav_host: float32 CPU tensor (B, Nmax), ideally pinned.  Returns (feats, feat_len): pinned
+        CPU tensors when ``return_host`` (what AudioDataSet.collate_fn hands to the trainer,
+        dataset.py:222-232), else CUDA tensors (the case where the encoder consumes them in place)."""
+        dev = torch.device(device)
+        B, Nmax = wav_host.shape
+        len_host = np.asarray(wav_len, dtype=np.int64).reshape(-1)
+        T_host, win = self.frame_counts(len_host)
+        if (len_host < win).any():
+            raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
+        Tmax, D = int(T_host.max()), self.num_mel_bins
+        key = (B, Nmax, Tmax, dev.index or 0)
+        c = self._host_cache.get(key)
+        if c is None:
+            self._host_cache.clear()
+            c = dict(wav=torch.empty((B, Nmax), dtype=torch.float32, device=dev),
+                     feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
+                     flen=torch.empty((B,), dtype=torch.int64, device=dev),
+                     hfeats=torch.empty((B, Tmax, D), dtype=torch.float32, pin_memory=True),
+                     hlen=torch.empty((B,), dtype=torch.int64, pin_memory=True),
+                     s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev))
+            self._host_cache[key] = c
+        main = torch.cuda.current_stream(dev)
+        s_in, s_out = c["s_in"], c["s_out"]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        group = max(1, min(B, group_bytes // max(Nmax * 4, 1)))
+        self.h2d_bytes = self.d2h_bytes = 0
+        for b0 in range(0, B, group):
+            b1 = min(B, b0 + group)
+            with torch.cuda.stream(s_in):
+                c["wav"][b0:b1].copy_(wav_host[b0:b1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            self.h2d_bytes += (b1 - b0) * Nmax * 4
+            main.wait_event(ev_in)
+            self.forward(c["wav"][b0:b1], len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1])
+            self.h2d_bytes += (b1 - b0) * 8
+            if return_host:
+                ev_c = torch.cuda.Event()
+                ev_c.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_c)
+                    c["hfeats"][b0:b1].copy_(c["feats"][b0:b1], non_blocking=True)
+                self.d2h_bytes += (b1 - b0) * Tmax * D * 4
+        if return_host:
+            with torch.cuda.stream(s_out):
+                c["hlen"].copy_(c["flen"], non_blocking=True)
+            self.d2h_bytes += B * 8
+            main.wait_stream(s_out)
+            return c["hfeats"], c["hlen"]
+        return c["feats"], c["flen"]
 
     # -- global CMVN statistics (Kaldi compute-cmvn-stats), one fused pass without feature output --
     @torch.no_grad()

@@ -1,0 +1,127 @@
+"""Plug-in points into the unmodified reference.
+
+1. Transform registry (``lasr.data.datatrans.register_trans``, a ``Register`` whose
+   ``register(name)`` decorator overrides an existing key after a warning,
+   lasr/utils/register.py:6-18).  Transforms are called as ``fn(array)`` with exactly one
+   positional argument and no kwargs (lasr/data/dataset.py:196-197, lasr/process/asrprocess.py:54-55).
+   ``install(register_trans)`` overrides ``fbank:80`` and adds fused keys.
+2. Config-named classes (``{name: "module:Class", kwargs: {...}}`` -> ``BaseConfig`` ->
+   ``Class(**kwargs)``; every YAML key must be a named parameter of ``__init__``,
+   lasr/utils/generater.py:91-99).  ``B200Collate`` / ``make_dataset_class`` provide the batched
+   collate that runs the whole batch through one fused launch in the main process.
+
+CUDA must not be touched inside forked DataLoader workers (bin/train_lighting.py:228): use
+``num_workers=0`` (the GPU front end replaces the 16 CPU workers) or the ASRProcess path.
+"""
+import numpy as np
+import torch
+
+from .frontend import GpuFbankFrontend
+
+
+class GpuTransform:
+    """Registry-compatible callable: 1-D waveform ndarray -> (T, 80) features.
+
+    ``return_tensor=False`` returns a float32 ndarray like ``WavToKaldiFbank`` does
+    (datatrans.py:104) so that ``batch_list`` can stack it; ``True`` returns the CUDA tensor,
+    which ``ASRProcess.model_forward`` accepts through ``torch.as_tensor`` (asrprocess.py:63)."""
+
+    def __init__(self, device="cuda:0", return_tensor=False, **frontend_kwargs):
+        self.device = torch.device(device)
+        self.return_tensor = return_tensor
+        self.frontend = GpuFbankFrontend(**frontend_kwargs)
+
+    def __call__(self, wav):
+        w = np.asarray(wav)
+        if w.ndim != 1:
+            raise ValueError("expected a mono 1-D waveform (run 'avgchannel' first, datatrans.py:10-14)")
+        n = w.shape[0]
+        pad = (-n) % 4
+        buf = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+        if pad:
+            buf = torch.nn.functional.pad(buf, (0, pad))
+        feats, _ = self.frontend(buf.to(self.device, non_blocking=True).unsqueeze(0), np.array([n], dtype=np.int64))
+        feats = feats[0]
+        return feats if self.return_tensor else feats.cpu().numpy()
+
+
+def install(register_trans, device="cuda:0", return_tensor=False, **fbank_kwargs):
+    """Overrides ``fbank:80`` in the reference's registry and adds fused chains:
+
+    ``fbank:80``                 -> GPU fbank (same defaults as WavToKaldiFbank)
+    ``b200:norm+fbank:80``       -> peak norm + fbank in one launch (replaces ["norm", "fbank:80"])
+    ``b200:norm+fbank:80+specaug`` -> + SpecAugment masks (mean fill), masks-only RNG replay
+    """
+    base = dict(fbank_kwargs)
+    table = {
+        "fbank:80": GpuTransform(device, return_tensor, **base),
+        "b200:norm+fbank:80": GpuTransform(device, return_tensor, peak_norm=True, **base),
+        "b200:norm+fbank:80+specaug": GpuTransform(device, return_tensor, peak_norm=True, specaug=True, **base),
+    }
+    for key, fn in table.items():
+        register_trans.register(key)(fn)
+    return table
+
+
+class B200Collate:
+    """Batched replacement of ``AudioDataSet.MergeBatch``'s transform loop (dataset.py:190-206).
+
+    ``__call__(list_of_waveforms)`` -> dict(wav_array=(B,Tmax,80) float32, wav_len=(B,) int64),
+    the two entries ``LightModelFace.pack_data`` reads (bin/train_lighting.py:104-126).  Features
+    stay on the GPU unless ``to_host`` (Lightning's batch transfer is then a no-op)."""
+
+    def __init__(self, device="cuda:0", to_host=False, **frontend_kwargs):
+        self.device = torch.device(device)
+        self.to_host = to_host
+        self.frontend = GpuFbankFrontend(**frontend_kwargs)
+
+    def __call__(self, wavs):
+        n = np.array([len(w) for w in wavs], dtype=np.int64)
+        nmax = int((n.max() + 3) // 4 * 4)
+        host = torch.zeros((len(wavs), nmax), dtype=torch.float32).pin_memory()
+        for i, w in enumerate(wavs):
+            host[i, : n[i]] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+        feats, flen = self.frontend.extract_host(host, n, device=self.device, return_host=self.to_host)
+        if self.to_host:
+            return {"wav_array": feats.clone(), "wav_len": flen.clone()}
+        torch.cuda.current_stream(self.device).synchronize()
+        return {"wav_array": feats.clone(), "wav_len": flen.clone()}
+
+
+def make_dataset_class():
+    """Builds ``B200BatchAudioDataSet`` on top of the reference's ``BatchAudioDataSet`` (only
+    possible where the ``lasr`` package and its audio I/O dependencies are importable).  Use it
+    from config.yaml as ``name: "lasr_b200.lasr_plugin:B200BatchAudioDataSet"`` after calling
+    this once, with ``audio_trans: [avgchannel]`` semantics: waveforms are read by the reference
+    reader, everything after is one fused GPU launch per batch."""
+    import lasr.data.reader as reader
+    from lasr.data.dataset import BatchAudioDataSet, batch_list
+    from lasr.data.datatrans import register_trans
+
+    class B200BatchAudioDataSet(BatchAudioDataSet):
+        def __init__(self, wav_list=None, text_list=None, feats_list=None, tokenizer="char", audio_trans=("avgchannel",),
+                     feats_trans=None, pad_audio=0, pad_feats=0, batch_sort=True, batch_size=32, batch_duration=320,
+                     batch_bin=32 * 500 * 80, batch_type="size", max_duration=30, min_duration=0.3, text_freq=0.08,
+                     min_token=0, max_token=5000, device="cuda:0", peak_norm=True, cmvn="none", specaug=False):
+            super().__init__(wav_list, text_list, feats_list, tokenizer, list(audio_trans), feats_trans, pad_audio, pad_feats,
+                             batch_sort, batch_size, batch_duration, batch_bin, batch_type, max_duration, min_duration,
+                             text_freq, min_token, max_token)
+            self._collate = B200Collate(device, peak_norm=peak_norm, cmvn=cmvn, specaug=specaug)
+
+        def collate_fn(self, batch):
+            items = [x for b in batch for x in b]
+            wavs = []
+            for it in items:
+                w, sr = reader.read_audio(it["wav"])
+                w = register_trans["avgchannel"](w)
+                if sr != 16000:
+                    w = register_trans["resample:16k"](w, sr)
+                wavs.append(w)
+            out = {k: [it[k] for it in items] for k in items[0]}
+            out.update(self._collate(wavs))
+            out["token_id"] = torch.from_numpy(batch_list(out["token_id"], pad_value=self.tokenizer.ID_VALUE_PAD, dtype=np.int64))
+            out["token_len"] = torch.from_numpy(np.array(out["token_len"], dtype=np.int64))
+            return out
+
+    globals()["B200BatchAudioDataSet"] = B200BatchAudioDataSet
+    return B200BatchAudioDataSet
