@@ -70,6 +70,11 @@ long long b200fe_num_frames(const b200fe_plan* plan, long long num_samples);
  * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count. */
 int b200fe_plan_info(const b200fe_plan* plan, int what);
 
+/* Host helper: fills table[2*i] = utterance, table[2*i+1] = first frame for every tile of 32 frames
+ * with at least one valid frame, in utterance order; returns the number of tiles (table may be NULL
+ * to query the size), or a negative status. */
+int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host, int batch, int* table_host, int capacity);
+
 /* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
  * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
  * fused into b200fe_fbank_fused through its `d_peak` argument. */
@@ -111,6 +116,13 @@ typedef struct b200fe_fbank_args {
     long long stats_stride;
     const int* d_row_bounds;
     int n_row_classes;
+    /* Optional compact work list for ragged batches (b200fe_build_tile_table): [n_tiles][2] int32
+     * (utterance, first frame) of every 32-frame tile that holds valid frames, consumed through the
+     * atomic counter d_work_counter (4 bytes, reset by the call).  Padded rows are then zeroed by a
+     * separate streaming kernel of the same call.  NULL = iterate the padded (batch x max_frames) grid. */
+    const int* d_tile_table;
+    int n_tiles;
+    int* d_work_counter;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

@@ -43,6 +43,30 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ w
     }
 }
 
+// Rows past an utterance's frame count are zero (pad_audio = 0, dataset.py:18,205): float4 stores over
+// [T_u * nmel, Tmax * nmel) of every utterance (used with the compact tile list).
+__global__ void __launch_bounds__(256) zero_pad_kernel(float* __restrict__ out, const long long* __restrict__ nsamp, int Tmax, int nmel,
+                                                       int win, int shift)
+{
+    const int utt = blockIdx.y;
+    const long long n = nsamp[utt];
+    const long long T = n >= win ? (1 + (n - win) / shift) : 0;
+    const long long lo = T * nmel, hi = (long long)Tmax * nmel;
+    const long long c0 = (long long)blockIdx.x * (256 * 4 * 8);
+    if (c0 + 256 * 4 * 8 <= lo || lo >= hi) return;
+    float* base = out + (long long)utt * hi;
+    if ((nmel & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const long long e = c0 + ((long long)r * 256 + threadIdx.x) * 4;
+            if (e >= lo && e + 3 < hi) *reinterpret_cast<float4*>(base + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (long long q = e; q < e + 4; ++q) if (q >= lo && q < hi) base[q] = 0.f;
+        }
+    } else {
+        for (long long e = c0 + threadIdx.x; e < c0 + 256 * 4 * 8 && e < hi; e += 256) if (e >= lo) base[e] = 0.f;
+    }
+}
+
 struct PostArgs {
     float* feats;
     const long long* nsamp;
@@ -174,6 +198,68 @@ __global__ void __launch_bounds__(256) postpass_kernel(const PostArgs a)
         float* ptr = base + (long long)r * a.nmel + d;
         if (hit >= 0) *ptr = s_fill[hit];
         else if (a.cmvn_mode != 0) *ptr = (*ptr - s_mean[d]) * s_istd[d];
+    }
+}
+
+// Vectorised in-place post pass for num_mel_bins % 4 == 0: thread = (row slot, 4 columns), float4
+// traffic, per-thread CMVN vectors and frequency-mask winners in registers.
+__global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
+{
+    const int utt = blockIdx.y;
+    const long long n = a.nsamp[utt];
+    const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    if (r0 >= T) return;
+    const int r1 = min(r0 + a.rows_per_cta, T);
+    const int nq = a.nmel >> 2;                    // float4 groups per row
+    const int slots = 256 / nq;                    // rows processed concurrently
+    const int q = threadIdx.x % nq, slot = threadIdx.x / nq;
+    if (slot >= slots) return;
+    const int nm = a.n_fmask + a.n_tmask;
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {1.f, 1.f, 1.f, 1.f};
+    int fhit[4] = {-1, -1, -1, -1};
+    float ffill[4] = {0.f, 0.f, 0.f, 0.f};
+    int tlo[kMaxTimeMasks], thi[kMaxTimeMasks];
+    float tfill[kMaxTimeMasks];
+    if (a.cmvn_mode != 0) {
+        const float4 m4 = *reinterpret_cast<const float4*>(a.cm_mean + (long long)utt * a.nmel + 4 * q);
+        const float4 s4 = *reinterpret_cast<const float4*>(a.cm_istd + (long long)utt * a.nmel + 4 * q);
+        mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+        is[0] = s4.x; is[1] = s4.y; is[2] = s4.z; is[3] = s4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxTimeMasks; ++i) { tlo[i] = 0; thi[i] = 0; tfill[i] = 0.f; }
+    if (a.masks) {
+        const int* mk = a.masks + (long long)utt * nm * 2;
+        const float* fl = a.fills + (long long)utt * nm;
+        for (int i = 0; i < a.n_fmask; ++i) {
+            const int lo = mk[2 * i], hi = mk[2 * i + 1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * q + c >= lo && 4 * q + c < hi) { fhit[c] = i; ffill[c] = fl[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxTimeMasks; ++i)
+            if (i < a.n_tmask) { tlo[i] = mk[2 * (a.n_fmask + i)]; thi[i] = mk[2 * (a.n_fmask + i) + 1]; tfill[i] = fl[a.n_fmask + i]; }
+    }
+    const bool need_read = a.cmvn_mode != 0;
+    float4* base = reinterpret_cast<float4*>(a.feats + (long long)utt * a.Tmax * a.nmel);
+    for (int r = r0 + slot; r < r1; r += slots) {
+        int thit = -1; float tf = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxTimeMasks; ++i) if (r >= tlo[i] && r < thi[i]) { thit = i; tf = tfill[i]; }   // later time masks win
+        float4* ptr = base + (long long)r * nq + q;
+        const bool anyf = (fhit[0] | fhit[1] | fhit[2] | fhit[3]) >= 0 || fhit[0] >= 0 || fhit[1] >= 0 || fhit[2] >= 0 || fhit[3] >= 0;
+        if (!need_read && thit < 0 && !anyf) continue;                    // nothing changes in this float4
+        float4 v = need_read || thit < 0 ? *ptr : make_float4(0.f, 0.f, 0.f, 0.f);
+        float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (need_read) x[c] = (x[c] - mu[c]) * is[c];
+            if (thit >= 0) x[c] = tf;                                    // time masks are applied after frequency masks
+            else if (fhit[c] >= 0) x[c] = ffill[c];
+        }
+        *ptr = make_float4(x[0], x[1], x[2], x[3]);
     }
 }
 

@@ -220,7 +220,8 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         stw[k] = make_float2((float)(-std::sin(t)), (float)(-std::cos(t)));
     }
     p->nload = (p->win > 384 && p->win <= 416) ? 13 : 16;
-    p->tile_floats = ((kFT - 1) * p->shift + 512 + 16 + 3) & ~3;
+    // a frame reads up to 32*nload samples from its start (zero-weighted past the window)
+    p->tile_floats = ((kFT - 1) * p->shift + 32 * p->nload + 3) & ~3;
     p->smem_bytes = make_layout(p->tile_floats, p->nmel).total;
 
     cudaError_t e = cudaGetDevice(&p->device);
@@ -289,6 +290,19 @@ extern "C" long long b200fe_num_frames(const b200fe_plan* p, long long n)
     return n < p->win ? 0 : 1 + (n - p->win) / p->shift;   // TA:63-67
 }
 
+extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* nsamp, int batch, int* table, int capacity)
+{
+    if (!p || !nsamp || batch < 0) return fail(B200FE_EINVAL, "build_tile_table: bad argument");
+    long long n = 0;
+    for (int u = 0; u < batch; ++u) {
+        const long long T = b200fe_num_frames(p, nsamp[u]);
+        for (long long f0 = 0; f0 < T; f0 += kFT, ++n)
+            if (table && n < capacity) { table[2 * n] = u; table[2 * n + 1] = (int)f0; }
+    }
+    if (n > 0x7fffffffLL) return fail(B200FE_EINVAL, "build_tile_table: too many tiles");
+    return (int)n;
+}
+
 extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride,
                                   const long long* d_nsamp, int batch, float* d_peak, void* stream)
 {
@@ -331,7 +345,9 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.n_fmask = g->n_freq_masks; a.n_tmask = g->n_time_masks; a.mask_zero = g->mask_zero;
     a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds; a.n_cls = n_cls;
     a.tiles_per_utt = (g->max_frames + kFT - 1) / kFT;
-    const long long ntiles = (long long)a.tiles_per_utt * g->batch;
+    const bool compact = g->d_tile_table != nullptr;
+    if (compact && (!g->d_work_counter || g->n_tiles < 0)) return fail(B200FE_EINVAL, "fbank_fused: a tile table needs n_tiles and d_work_counter");
+    const long long ntiles = compact ? (long long)g->n_tiles : (long long)a.tiles_per_utt * g->batch;
     if (ntiles > 0x7fffffffLL) return fail(B200FE_EINVAL, "fbank_fused: too many tiles");
     a.ntiles = (int)ntiles;
     a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 && (g->wav_stride % 4) == 0) ? 1 : 0;
@@ -340,8 +356,20 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     memcpy(a.grp_begin, p->grp_begin, sizeof a.grp_begin);
     memcpy(a.w_updn, p->w_updn, sizeof a.w_updn);
 
-    const int grid = (int)std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm);
+    a.tile_table = reinterpret_cast<const int2*>(g->d_tile_table);
+    a.work_counter = g->d_work_counter;
     cudaStream_t st = (cudaStream_t)stream;
+    if (compact) {
+        CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
+        if (g->d_out) {
+            const long long per_utt = (long long)g->max_frames * p->nmel;
+            dim3 zg((unsigned)((per_utt + 8191) / 8192), (unsigned)g->batch);
+            zero_pad_kernel<<<zg, 256, 0, st>>>(g->d_out, g->d_nsamp, g->max_frames, p->nmel, p->win, p->shift);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (ntiles == 0) return B200FE_OK;
+    }
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm));
     void* kargs[] = {(void*)&a};
     CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
     return B200FE_OK;
@@ -371,8 +399,12 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     cudaStream_t st = (cudaStream_t)stream;
     finalize_kernel<<<g->batch, 128, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
+    const bool vec = (p->nmel % 4 == 0) && p->nmel <= 256 * 4 && ((reinterpret_cast<uintptr_t>(g->d_feats) & 15) == 0) &&
+                     (a.cmvn_mode == 0 || (((reinterpret_cast<uintptr_t>(g->d_cmvn_mean) | reinterpret_cast<uintptr_t>(g->d_cmvn_istd)) & 15) == 0));
+    a.rows_per_cta = vec ? 96 : 64;
     dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
-    postpass_kernel<<<grid, 256, 0, st>>>(a);
+    if (vec) postpass_vec_kernel<<<grid, 256, 0, st>>>(a);
+    else postpass_kernel<<<grid, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }

@@ -80,6 +80,10 @@ struct FbankArgs {
     // scheduling
     int tiles_per_utt;
     int ntiles;
+    // optional compact work list of valid tiles (utt, first frame) consumed through an atomic counter
+    // (dynamic scheduling; padded rows are then zeroed by zero_pad_kernel)
+    const int2* tile_table;
+    int* work_counter;
     int use_tma;
     int tile_floats;             // floats reserved per tile stage
     // mel tables (warp-uniform, read through the constant bank) -- generic (non-static) phase B
@@ -105,8 +109,8 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     o += (xbytes > obytes ? xbytes : obytes);
     L.outs_off = L.xbuf_off;
     L.pt_off = o; o += 64 * kPTStride * 16;
-    L.misc_off = o; o += (2 * kMaxMel + 8) * 4 + 256 * 8;
-    L.bar_off = o; o += 8 * kStages;
+    L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
+    L.bar_off = o; o += 8 * kStages + 16;   // mbarriers + 2 scheduler slots
     L.total = o;
     return L;
 }
@@ -162,9 +166,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     float* pt = reinterpret_cast<float*>(smem + L.pt_off);
     float* outs = reinterpret_cast<float*>(smem + L.outs_off);
     float* s_mean = reinterpret_cast<float*>(smem + L.misc_off);
-    float* s_istd = s_mean + kMaxMel;
-    unsigned* s_cmask = reinterpret_cast<unsigned*>(s_istd + kMaxMel);   // [0..3] column bits, [4] row bits
+    float* s_istd = s_mean + ((a.nmel + 3) & ~3);
+    unsigned* s_cmask = reinterpret_cast<unsigned*>(s_istd + ((a.nmel + 3) & ~3));   // [0..3] column bits, [4] row bits
     float2* s_stw = reinterpret_cast<float2*>(s_cmask + 8);
+    float2* s_win = s_stw + 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
 
     const int tid = threadIdx.x;
@@ -172,20 +177,20 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     const int h2 = lane >> 4, l = lane & 15;
     const int hw = warp * 2 + h2;
     float2* xbuf = xbuf_all + hw * 16 * kXRow;
-    const int ostride = a.nmel + 1;
+    // the straight-line mel path fixes num_mel_bins and the power spectrum at compile time
+    const int nmel = kStaticMel ? B200FE_STATIC_NMEL : a.nmel;
+    const bool use_power = kStaticMel ? true : (a.use_power != 0);
+    const int ostride = nmel + 1;
 
     // ---- per-lane constants (live in registers across all tiles) ----
-    float2 wreg[NLOAD];
-#pragma unroll
-    for (int n2 = 0; n2 < NLOAD; ++n2) {
-        int j = 2 * (l + 16 * n2);
-        wreg[n2] = make_float2(__ldg(a.window + j), __ldg(a.window + j + 1));
-    }
+    // window (x 2^15) as float2 pairs in shared memory: lane l reads pair l + 16 n2 (conflict free)
+    for (int k = tid; k < 256; k += kThreads) s_win[k] = make_float2(__ldg(a.window + 2 * k), __ldg(a.window + 2 * k + 1));
+    const float2* wl = s_win + l;
     float2 tw[16];
 #pragma unroll
     for (int k = 1; k < 16; ++k) tw[k] = __ldg(a.twiddle + l * 16 + k);
     // split twiddles -j W_512^k live in shared memory (lane l reads k = l + 16 r: conflict free)
-    for (int k = tid; k < 256; k += kThreads) s_stw[k] = __ldg(a.split_tw + k);
+    for (int k = tid; k < 128; k += kThreads) s_stw[k] = __ldg(a.split_tw + k);   // k = l + 16 r, r < 8
     const float2* stw = s_stw + l;
 
     if (tid == 0) {
@@ -194,8 +199,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     }
     // global CMVN vectors (or the identity) are staged once; per-utterance vectors per tile
     const bool cm_per_utt = a.cm_mean != nullptr && a.cm_stride != 0;
-    if (tid < kMaxMel) {
-        const bool on = a.cm_mean != nullptr && !cm_per_utt && tid < a.nmel;
+    if (tid < nmel) {
+        const bool on = a.cm_mean != nullptr && !cm_per_utt;
         s_mean[tid] = on ? __ldg(a.cm_mean + tid) : 0.f;
         s_istd[tid] = on ? __ldg(a.cm_istd + tid) : 1.f;
     }
@@ -208,14 +213,14 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     const bool zmask = a.mask_zero && a.masks != nullptr;
     const int nmask = a.n_fmask + a.n_tmask;
 
-    auto tile_geom = [&](int tile) -> TileGeom {
+    auto tile_geom = [&](int utt_, int j_) -> TileGeom {
         TileGeom g;
-        g.utt = (int)((unsigned)tile / (unsigned)a.tiles_per_utt);
-        g.f0 = (tile - g.utt * a.tiles_per_utt) * kFT;
+        g.utt = utt_;
+        g.f0 = j_ * kFT;
         const unsigned n = (unsigned)__ldg(a.nsamp + g.utt);       // < 2^31 samples per utterance
         g.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
         g.nvalid = min(max(g.T - g.f0, 0), kFT);
-        g.nrows = min(a.Tmax - g.f0, kFT);
+        g.nrows = a.tile_table != nullptr ? g.nvalid : min(a.Tmax - g.f0, kFT);
         return g;
     };
     auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
@@ -229,17 +234,35 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
 
     int it = 0;
     uint32_t phase_bits = 0;
-    int tile = blockIdx.x;
-    TileGeom g = tile_geom(tile < a.ntiles ? tile : 0);
+    const bool dyn = a.tile_table != nullptr;
+    int* s_sched = reinterpret_cast<int*>(bars + kStages);
+    int tile = blockIdx.x, nxt = blockIdx.x + gridDim.x;
+    if (dyn) {
+        // dynamic scheduling: tile ids come from an atomic counter, one tile of look-ahead
+        if (tid == 0) { s_sched[0] = atomicAdd(a.work_counter, 1); s_sched[1] = atomicAdd(a.work_counter, 1); }
+        __syncthreads();
+        tile = s_sched[0]; nxt = s_sched[1];
+    }
+    // static mode: tile -> (utterance, tile-in-utterance) is advanced incrementally (no division per tile)
+    const int step_q = (int)(gridDim.x / (unsigned)a.tiles_per_utt), step_r = (int)(gridDim.x % (unsigned)a.tiles_per_utt);
+    int cur_utt = (int)((unsigned)blockIdx.x / (unsigned)a.tiles_per_utt), cur_j = blockIdx.x - cur_utt * a.tiles_per_utt;
+    auto geom_of = [&](int t) -> TileGeom {
+        if (dyn) { const int2 e = __ldg(a.tile_table + t); return tile_geom(e.x, e.y / kFT); }
+        return tile_geom(cur_utt, cur_j);
+    };
+    TileGeom g = tile < a.ntiles ? geom_of(tile) : tile_geom(0, 0);
     if (a.use_tma && tid == 0 && tile < a.ntiles) issue_load(g, 0);
 
-    for (; tile < a.ntiles; tile += gridDim.x, ++it) {
+    for (; tile < a.ntiles; ++it) {
         const int stage = it % kStages;
         const int utt = g.utt, f0 = g.f0, nvalid = g.nvalid, nrows = g.nrows;
         float* xs = reinterpret_cast<float*>(smem + L.tile_off[stage]);
-        const int nxt = tile + gridDim.x;
         TileGeom gn = g;
-        if (nxt < a.ntiles) gn = tile_geom(nxt);
+        cur_utt += step_q; cur_j += step_r;
+        if (cur_j >= a.tiles_per_utt) { cur_j -= a.tiles_per_utt; cur_utt += 1; }
+        if (nxt < a.ntiles) gn = geom_of(nxt);
+        int fetched = 0;
+        if (dyn && tid == 0) fetched = atomicAdd(a.work_counter, 1);      // the tile after next; consumed at the end of this iteration
 
         if (a.use_tma) {
             // prefetch the next tile of this CTA into the other stage (its previous contents were
@@ -257,13 +280,14 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
 
         if (nvalid > 0) {
             // per-tile epilogue tables (visible after the phase-A barrier)
-            if (cm_per_utt && tid < a.nmel) {
+            if (cm_per_utt && tid < nmel) {
                 s_mean[tid] = __ldg(a.cm_mean + (long long)utt * a.cm_stride + tid);
                 s_istd[tid] = __ldg(a.cm_istd + (long long)utt * a.cm_stride + tid);
             }
             if (zmask && tid < kMaxMel) {
                 const int* mk = a.masks + (long long)utt * nmask * 2;
                 bool m = false;
+#pragma unroll 1
                 for (int i = 0; i < a.n_fmask; ++i) m |= (tid >= __ldg(mk + 2 * i) && tid < __ldg(mk + 2 * i + 1));
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
                 if (lane == 0) s_cmask[warp] = bal;
@@ -271,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             if (zmask && warp == 4) {
                 const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
                 bool m = false;
+#pragma unroll 1
                 for (int i = 0; i < a.n_tmask; ++i) m |= (f0 + lane >= __ldg(mk + 2 * i) && f0 + lane < __ldg(mk + 2 * i + 1));
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
                 if (lane == 0) s_cmask[4] = bal;
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                     const float cdc = sum * inv_win * dc_coef;   // (1 - preemph) * frame mean
 #pragma unroll
-                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(sub2(v[n2], bc(cdc)), wreg[n2]);
+                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(sub2(v[n2], bc(cdc)), wl[16 * n2]);
 #pragma unroll
                     for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
 
@@ -367,19 +392,20 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                         float2 xa = add2(S, T), xb = sub2(S, T);
                         xa = mul2(xa, xa); xb = mul2(xb, xb);
                         float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
-                        if (!a.use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
+                        if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
                         if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
                         if (fvalid && (r != 0 || l != 0)) pb[-r * 4 * kPTStride * 4] = pwb;
                     }
                     if (l == 0 && fvalid) {   // bin 128 is its own partner: X[128] = conj Z[128]
                         float2 z = v[8];
                         float p = 4.0f * (z.x * z.x + z.y * z.y);
-                        if (!a.use_power) p = sqrtf(p);
+                        if (!use_power) p = sqrtf(p);
                         pt[(32 * kPTStride + fl) * 4] = p;
                     }
                 }
             }
             __syncthreads();   // PT complete; tile stage and transposition buffers are free
+            if (dyn && tid == 0) s_sched[it & 1] = fetched;   // every thread consumed this slot before the barrier
 
             // ================= phase B: warp = mel-bin group, lane = frame =================
             {
@@ -425,29 +451,53 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         // ================= phase C: epilogue + copy-out, zero padding, statistics =================
         // element e = row * nmel + col of the tile (contiguous in global memory) <-> staging row*(nmel+1)+col
         {
-            float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * a.nmel : nullptr;
-            const int nv = nvalid * a.nmel, nt = nrows * a.nmel;
+            float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * nmel : nullptr;
+            const int nv = nvalid * nmel, nt = nrows * nmel;
             if (nvalid > 0) {
-                const unsigned rmask = zmask ? s_cmask[4] : 0u;
                 const bool wb = a.stats != nullptr;       // statistics read the transformed values back
-                int e = tid;
-                int row = e / a.nmel, col = e - row * a.nmel;
-                const int drow = kThreads / a.nmel, dcol = kThreads - drow * a.nmel;
-                for (; e < nv; e += kThreads) {
-                    float* sp = outs + row * ostride + col;
-                    float x = *sp;
-                    if (a.use_log) x = fast_log(fmaxf(x, a.log_floor));
-                    x = (x - s_mean[col]) * s_istd[col];
-                    if (zmask && (((rmask >> row) & 1u) || ((s_cmask[col >> 5] >> (col & 31)) & 1u))) x = 0.f;
-                    if (obase) obase[e] = x;
-                    if (wb) *sp = x;
-                    col += dcol; row += drow;
-                    if (col >= a.nmel) { col -= a.nmel; row += 1; }
+                const bool affine = a.cm_mean != nullptr;
+                const float lf = a.log_floor;
+                if (a.use_log != 0 && !zmask) {
+                    // fast path: element e = row * nmel + col <-> staging e + row
+                    if (affine) {
+#pragma unroll 2
+                        for (int e = tid; e < nv; e += kThreads) {
+                            const int row = e / nmel, col = e - row * nmel;
+                            float* sp = outs + e + row;
+                            float x = fast_log(fmaxf(*sp, lf));
+                            x = (x - s_mean[col]) * s_istd[col];
+                            if (obase) obase[e] = x;
+                            if (wb) *sp = x;
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int e = tid; e < nv; e += kThreads) {
+                            const int row = e / nmel;
+                            float* sp = outs + e + row;
+                            const float x = fast_log(fmaxf(*sp, lf));
+                            if (obase) obase[e] = x;
+                            if (wb) *sp = x;
+                        }
+                    }
+                } else {
+                    const unsigned rmask = zmask ? s_cmask[4] : 0u;
+                    const bool lg = a.use_log != 0;
+#pragma unroll 1
+                    for (int e = tid; e < nv; e += kThreads) {
+                        const int row = e / nmel, col = e - row * nmel;
+                        float* sp = outs + e + row;
+                        float x = *sp;
+                        if (lg) x = fast_log(fmaxf(x, lf));
+                        if (affine) x = (x - s_mean[col]) * s_istd[col];
+                        if (zmask && (((rmask >> row) & 1u) || ((s_cmask[col >> 5] >> (col & 31)) & 1u))) x = 0.f;
+                        if (obase) obase[e] = x;
+                        if (wb) *sp = x;
+                    }
                 }
             }
             // rows past the utterance end are zero (pad_audio = 0)
             if (obase && nt > nv) {
-                if ((a.nmel & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+                if ((nmel & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
                     float4* z4 = reinterpret_cast<float4*>(obase);
                     for (int q = (nv >> 2) + tid; q < (nt >> 2); q += kThreads) z4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
@@ -461,25 +511,34 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             const int nb = a.n_cls - 1;
             const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
             double* sb = a.stats + (long long)utt * a.stats_stride;
-            for (int j = tid; j < a.nmel; j += kThreads) {
-                int cls = bounds ? row_class(bounds, nb, f0) : 0;
-                double s1 = 0.0, s2 = 0.0;
-                for (int fr = 0; fr < nvalid; ++fr) {
-                    if (bounds) {
-                        const int cc = row_class(bounds, nb, f0 + fr);
-                        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
+            // thread = (column j, row part): the rows of the tile are split over kThreads / nmel parts so that
+            // the reduction's critical path is short; every part flushes with fp64 atomics
+            const int parts = max(1, min(kThreads / nmel, 4));
+            const int part = tid / nmel, j = tid - part * nmel;
+            if (part < parts) {
+                const int rb = (nvalid * part) / parts, re = (nvalid * (part + 1)) / parts;
+                if (re > rb) {
+                    int cls = bounds ? row_class(bounds, nb, f0 + rb) : 0;
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int fr = rb; fr < re; ++fr) {
+                        if (bounds) {
+                            const int cc = row_class(bounds, nb, f0 + fr);
+                            if (cc != cls) { atomicAdd(sb + (long long)cls * nmel + j, s1); s1 = 0.0; cls = cc; }
+                        }
+                        const double x = (double)outs[fr * ostride + j];
+                        s1 += x;
+                        s2 = fma(x, x, s2);
                     }
-                    const double x = (double)outs[fr * ostride + j];
-                    s1 += x;
-                    s2 = fma(x, x, s2);
+                    atomicAdd(sb + (long long)cls * nmel + j, s1);
+                    atomicAdd(sb + (long long)a.n_cls * nmel + j, s2);
                 }
-                atomicAdd(sb + (long long)cls * a.nmel + j, s1);
-                atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
             }
         }
         // the staging area aliases the transposition buffers that the next phase A overwrites
         if (nvalid > 0) __syncthreads();
         g = gn;
+        tile = nxt;
+        nxt = dyn ? s_sched[it & 1] : nxt + (int)gridDim.x;
     }
 }
 
