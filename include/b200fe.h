@@ -78,7 +78,7 @@ int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host
 /* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
  * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
  * fused into b200fe_fbank_fused through its `d_peak` argument. */
-int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride,
+int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride, const long long* d_wav_offsets,
                        const long long* d_nsamp, int batch, float* d_peak, void* stream);
 
 /* One fused launch over a zero-padded batch of waveforms.
@@ -123,9 +123,20 @@ typedef struct b200fe_fbank_args {
     const int* d_tile_table;
     int n_tiles;
     int* d_work_counter;
+    /* Optional packed (ragged) input: utterance u starts at d_wav + d_wav_offsets[u] (elements) instead of
+     * d_wav + u * wav_stride; wav_stride must still bound the longest utterance.  offsets_aligned != 0
+     * promises that every offset is a multiple of 4 samples (enables the TMA loader). */
+    const long long* d_wav_offsets;
+    int offsets_aligned;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);
+
+/* Host -> device staging of a zero-padded HOST batch (what batch_list builds, dataset.py:8-22) into the
+ * packed device layout: only the valid samples of every utterance cross PCIe (one cudaMemcpyAsync per
+ * utterance on `stream`; h_wav should be pinned).  h_offsets[u] = destination offset (elements). */
+int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
+                      int batch, float* d_packed, void* stream);
 
 /* Turns per-utterance statistics into (a) utterance CMVN vectors and (b) the SpecAugment mean
  * fills of R/lasr/utils/specaugment.py:71-74,102-105 (each mask is filled with the mean of the

@@ -8,12 +8,12 @@ namespace b200fe {
 
 // ---- VoiceNorm abs-max (R/lasr/data/datatrans.py:24): one float per utterance -----------------
 // |x| >= 0, so the IEEE bit pattern orders like an unsigned integer and atomicMax is exact.
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ wav, long long stride,
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ wav, long long stride, const long long* __restrict__ offsets,
                                                      const long long* __restrict__ nsamp, float* __restrict__ peak)
 {
     const int utt = blockIdx.y;
     const long long n = nsamp[utt];
-    const float* x = wav + (long long)utt * stride;
+    const float* x = wav + (offsets ? offsets[utt] : (long long)utt * stride);
     const long long chunk = 256LL * 4 * 8;
     long long i0 = (long long)blockIdx.x * chunk;
     if (i0 >= n) return;

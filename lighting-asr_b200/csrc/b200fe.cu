@@ -303,7 +303,7 @@ extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* ns
     return (int)n;
 }
 
-extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride,
+extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride, const long long* d_wav_offsets,
                                   const long long* d_nsamp, int batch, float* d_peak, void* stream)
 {
     if (!plan || !d_wav || !d_nsamp || !d_peak || batch <= 0 || wav_stride <= 0) return fail(B200FE_EINVAL, "peak_absmax: bad argument");
@@ -311,8 +311,22 @@ extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, l
     CUDA_TRY(cudaMemsetAsync(d_peak, 0, sizeof(float) * batch, st));
     const long long chunk = 256LL * 4 * 8;
     dim3 grid((unsigned)((wav_stride + chunk - 1) / chunk), (unsigned)batch);
-    absmax_kernel<<<grid, 256, 0, st>>>(d_wav, wav_stride, d_nsamp, d_peak);
+    absmax_kernel<<<grid, 256, 0, st>>>(d_wav, wav_stride, d_wav_offsets, d_nsamp, d_peak);
     CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
+                                 int batch, float* d_packed, void* stream)
+{
+    if (!h_wav || !h_nsamp || !h_offsets || !d_packed || batch < 0) return fail(B200FE_EINVAL, "h2d_ragged: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // merge utterances whose source and destination ranges are both contiguous into one copy
+    for (int u = 0; u < batch; ++u) {
+        if (h_nsamp[u] <= 0) continue;
+        CUDA_TRY(cudaMemcpyAsync(d_packed + h_offsets[u], h_wav + (long long)u * h_stride, sizeof(float) * (size_t)h_nsamp[u],
+                                 cudaMemcpyHostToDevice, st));
+    }
     return B200FE_OK;
 }
 
@@ -331,7 +345,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
 
     FbankArgs a;
     memset(&a, 0, sizeof a);
-    a.wav = g->d_wav; a.wav_stride = g->wav_stride; a.nsamp = g->d_nsamp; a.peak = g->d_peak; a.B = g->batch;
+    a.wav = g->d_wav; a.wav_stride = g->wav_stride; a.wav_offsets = g->d_wav_offsets; a.nsamp = g->d_nsamp; a.peak = g->d_peak; a.B = g->batch;
     a.out = g->d_out; a.out_len = g->d_out_len; a.Tmax = g->max_frames; a.nmel = p->nmel;
     a.win = p->win; a.shift = p->shift;
     a.remove_dc = p->o.remove_dc_offset; a.use_power = p->o.use_power; a.use_log = p->o.use_log_fbank;
@@ -350,7 +364,8 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     const long long ntiles = compact ? (long long)g->n_tiles : (long long)a.tiles_per_utt * g->batch;
     if (ntiles > 0x7fffffffLL) return fail(B200FE_EINVAL, "fbank_fused: too many tiles");
     a.ntiles = (int)ntiles;
-    a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 && (g->wav_stride % 4) == 0) ? 1 : 0;
+    // packed input: the caller promises 4-sample aligned offsets through offsets_aligned
+    a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 && (g->d_wav_offsets ? g->offsets_aligned != 0 : (g->wav_stride % 4) == 0)) ? 1 : 0;
     a.tile_floats = p->tile_floats;
     memcpy(a.seg_start, p->seg_start, sizeof a.seg_start);
     memcpy(a.grp_begin, p->grp_begin, sizeof a.grp_begin);

@@ -46,6 +46,7 @@ struct FbankArgs {
     // input
     const float* wav;            // [B][wav_stride] fp32 waveform
     long long wav_stride;
+    const long long* wav_offsets; // optional [B]: utterance u starts at wav + wav_offsets[u] (packed / ragged input)
     const long long* nsamp;      // [B] valid samples
     const float* peak;           // [B] per-utterance abs-max (peak normalisation) or nullptr
     int B;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         if (g.nvalid <= 0) return;
         const int nsmp = (g.nvalid - 1) * a.shift + a.win;
         const uint32_t bytes = (uint32_t)((nsmp * 4 + 15) & ~15);
-        const float* src = a.wav + (long long)g.utt * a.wav_stride + (long long)g.f0 * a.shift;
+        const float* src = a.wav + (a.wav_offsets ? __ldg(a.wav_offsets + g.utt) : (long long)g.utt * a.wav_stride) + (long long)g.f0 * a.shift;
         mbar_expect_tx(&bars[stage], bytes);
         tma_load_1d(smem + L.tile_off[stage], src, bytes, &bars[stage]);
     };
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         } else if (nvalid > 0) {
             // generic path (unaligned base / stride): cooperative coalesced loads
             const int nsmp = (nvalid - 1) * a.shift + a.win;
-            const float* src = a.wav + (long long)utt * a.wav_stride + (long long)f0 * a.shift;
+            const float* src = a.wav + (a.wav_offsets ? __ldg(a.wav_offsets + utt) : (long long)utt * a.wav_stride) + (long long)f0 * a.shift;
             for (int i = tid; i < nsmp; i += kThreads) xs[i] = __ldg(src + i);
             __syncthreads();
         }

@@ -202,15 +202,29 @@ class GpuFbankFrontend(torch.nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None):
+    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None):
+        """``wav_offsets`` (int64 host array, multiples of 4) switches to the packed layout: ``wav`` is then
+        a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
-        if wav.dim() != 2 or wav.dtype != torch.float32:
-            raise ValueError("wav must be float32 (B, Nmax)")
-        if wav.stride(1) != 1:
+        packed = wav_offsets is not None
+        if wav.dtype != torch.float32 or wav.dim() != (1 if packed else 2):
+            raise ValueError("wav must be float32 (B, Nmax), or 1-D with wav_offsets")
+        if not packed and wav.stride(1) != 1:
             wav = wav.contiguous()
         dev = wav.device
-        B = wav.shape[0]
+        B = len(wav_len) if packed else wav.shape[0]
+        if packed:
+            off_host = np.ascontiguousarray(wav_offsets, dtype=np.int64)
+            if (off_host % 4 != 0).any():
+                raise ValueError("wav_offsets must be multiples of 4 samples")
+            off_dev = torch.from_numpy(off_host).to(dev, non_blocking=True)
+            row_stride = int(wav.numel())
+            row_elems = int(wav.numel())
+        else:
+            off_dev = None
+            row_stride = wav.stride(0)
+            row_elems = wav.shape[1]
         plan = self.plan(dev)
         lib = plan.lib
         if torch.is_tensor(wav_len) and wav_len.is_cuda:
@@ -224,7 +238,7 @@ class GpuFbankFrontend(torch.nn.Module):
             if (len_host < win).any():
                 # torchaudio asserts (TA:142); LASR filters min_duration upstream (dataset.py:243,272)
                 raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
-            if (len_host > wav.shape[1]).any():
+            if (len_host > row_elems).any():
                 raise ValueError("wav_len exceeds the padded width")
             Tmax = int(T_host.max()) if max_frames is None else int(max_frames)
         else:
@@ -243,8 +257,8 @@ class GpuFbankFrontend(torch.nn.Module):
         peak = None
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
-            _lib.check(lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), _ptr(len_dev), B, _ptr(peak), stream),
-                       "b200fe_peak_absmax")
+            _lib.check(lib.b200fe_peak_absmax(plan.handle, _ptr(wav), row_stride if not packed else int(len_host.max()) if len_host is not None else row_stride,
+                                              _ptr(off_dev), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
             self.launch_count += 2          # memset + abs-max kernel
 
         n_f = n_t = 0
@@ -292,8 +306,14 @@ class GpuFbankFrontend(torch.nn.Module):
         for b0 in range(0, B, group):
             nb = min(group, B - b0)
             a = _lib.FbankArgs()
-            a.d_wav = off(wav, b0, wav.stride(0) * 4)
-            a.wav_stride = wav.stride(0)
+            if packed:
+                a.d_wav = _ptr(wav)
+                a.wav_stride = row_stride
+                a.d_wav_offsets = off(off_dev, b0, 8)
+                a.offsets_aligned = 1
+            else:
+                a.d_wav = off(wav, b0, wav.stride(0) * 4)
+                a.wav_stride = wav.stride(0)
             a.d_nsamp = off(len_dev, b0, 8)
             a.batch = nb
             a.d_peak = off(peak, b0, 4)
@@ -361,43 +381,61 @@ class GpuFbankFrontend(torch.nn.Module):
     def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True):
         """Pipelined H2D copy -> fused kernels -> D2H copy over utterance groups on three streams.
 
-        wav_host: float32 CPU tensor (B, Nmax), ideally pinned.  Returns (feats, feat_len): pinned
-        CPU tensors when ``return_host`` (what AudioDataSet.collate_fn hands to the trainer,
-        dataset.py:222-232), else CUDA tensors (the case where the encoder consumes them in place)."""
+        wav_host: zero-padded float32 CPU tensor (B, Nmax), ideally pinned (what batch_list builds).
+        Only the VALID samples of each utterance cross PCIe: they are staged into a packed device
+        buffer (b200fe_h2d_ragged) that the fused kernel reads through per-utterance offsets.
+        Returns (feats, feat_len): pinned CPU tensors when ``return_host`` (what
+        AudioDataSet.collate_fn hands to the trainer, dataset.py:222-232), else CUDA tensors (the
+        case where the encoder consumes them in place)."""
         dev = torch.device(device)
         B, Nmax = wav_host.shape
-        len_host = np.asarray(wav_len, dtype=np.int64).reshape(-1)
+        if wav_host.dtype != torch.float32 or wav_host.stride(1) != 1:
+            raise ValueError("wav_host must be a float32 tensor with contiguous rows")
+        len_host = np.ascontiguousarray(np.asarray(wav_len, dtype=np.int64).reshape(-1))
         T_host, win = self.frame_counts(len_host)
         if (len_host < win).any():
             raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
         Tmax, D = int(T_host.max()), self.num_mel_bins
-        key = (B, Nmax, Tmax, dev.index or 0)
+        offs = np.zeros(B, dtype=np.int64)
+        np.cumsum((len_host[:-1] + 3) // 4 * 4, out=offs[1:])
+        total = int(offs[-1] + (len_host[-1] + 3) // 4 * 4)
+        key = (B, Nmax, Tmax, total, dev.index or 0)
         c = self._host_cache.get(key)
         if c is None:
             self._host_cache.clear()
-            c = dict(wav=torch.empty((B, Nmax), dtype=torch.float32, device=dev),
+            c = dict(wav=torch.zeros((total + 64,), dtype=torch.float32, device=dev),
                      feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
                      flen=torch.empty((B,), dtype=torch.int64, device=dev),
                      hfeats=torch.empty((B, Tmax, D), dtype=torch.float32, pin_memory=True),
                      hlen=torch.empty((B,), dtype=torch.int64, pin_memory=True),
                      s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev))
             self._host_cache[key] = c
+        lib = _lib.load()
         main = torch.cuda.current_stream(dev)
         s_in, s_out = c["s_in"], c["s_out"]
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        group = max(1, min(B, group_bytes // max(Nmax * 4, 1)))
+        # utterance groups of ~group_bytes of valid audio
+        bounds = [0]
+        acc = 0
+        for b in range(B):
+            acc += int(len_host[b]) * 4
+            if acc >= group_bytes:
+                bounds.append(b + 1)
+                acc = 0
+        if bounds[-1] != B:
+            bounds.append(B)
         self.h2d_bytes = self.d2h_bytes = 0
-        for b0 in range(0, B, group):
-            b1 = min(B, b0 + group)
-            with torch.cuda.stream(s_in):
-                c["wav"][b0:b1].copy_(wav_host[b0:b1], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            self.h2d_bytes += (b1 - b0) * Nmax * 4
+        for b0, b1 in zip(bounds[:-1], bounds[1:]):
+            _lib.check(lib.b200fe_h2d_ragged(C.c_void_p(wav_host.data_ptr() + b0 * wav_host.stride(0) * 4), wav_host.stride(0),
+                                             C.c_void_p(len_host.ctypes.data + b0 * 8), C.c_void_p(offs.ctypes.data + b0 * 8), b1 - b0,
+                                             _ptr(c["wav"]), C.c_void_p(s_in.cuda_stream)), "b200fe_h2d_ragged")
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+            self.h2d_bytes += int(len_host[b0:b1].sum()) * 4 + (b1 - b0) * 16
             main.wait_event(ev_in)
-            self.forward(c["wav"][b0:b1], len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1])
-            self.h2d_bytes += (b1 - b0) * 8
+            self.forward(c["wav"], len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1],
+                         wav_offsets=offs[b0:b1])
             if return_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
@@ -430,7 +468,7 @@ class GpuFbankFrontend(torch.nn.Module):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
-            _lib.check(plan.lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), _ptr(len_dev), B, _ptr(peak), stream),
+            _lib.check(plan.lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), C.c_void_p(0), _ptr(len_dev), B, _ptr(peak), stream),
                        "b200fe_peak_absmax")
         a = _lib.FbankArgs()
         a.d_wav, a.wav_stride, a.d_nsamp, a.batch = _ptr(wav), wav.stride(0), _ptr(len_dev), B

@@ -56,20 +56,51 @@ def plan_utterance(num_frames, num_mel, max_freq_width=27, n_freq_mask=2, max_ti
     return freq, time
 
 
-def plan_batch(frame_lens, num_mel, **kw):
+def plan_batch(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2,
+               consume_time_warp_draws=False, max_time_warp=5):
     """Rectangles for a batch, utterances visited in order (dataset.py:190).
 
+    Same draws, in the same order, as calling ``plan_utterance`` per utterance (tested), written as a
+    tight loop because the RNG replay is the only per-utterance host work left on the path.
     Returns (masks [B, n_f + n_t, 2] int32, row_bounds [B, 2 n_t] int32 sorted)."""
-    n_f = kw.get("n_freq_mask", 2)
-    n_t = kw.get("n_time_mask", 2)
+    n_f, n_t = n_freq_mask, n_time_mask
     if n_f > MAX_FREQ_MASKS or n_t > MAX_TIME_MASKS:
         raise ValueError("at most %d frequency and %d time masks are supported" % (MAX_FREQ_MASKS, MAX_TIME_MASKS))
     B = len(frame_lens)
-    masks = np.zeros((B, n_f + n_t, 2), dtype=np.int32)
-    bounds = np.zeros((B, 2 * n_t), dtype=np.int32)
-    for b, T in enumerate(frame_lens):
-        f, t = plan_utterance(int(T), num_mel, **kw)
-        masks[b, :n_f] = f
-        masks[b, n_f:] = t
-        bounds[b] = np.sort(t.reshape(-1))
-    return masks, bounds
+    rr = random.randrange
+    # The two generators are independent objects, so only the order WITHIN each stream matters.  The
+    # numpy draws are unconditional (specaugment.py:61,90): per utterance 2*n_f values below
+    # max_freq_width then 2*n_t values below max_time_width -> one vectorised call with per-element
+    # bounds consumes the legacy MT19937 stream exactly like the per-utterance calls (tested).
+    high = np.tile(np.array([max_freq_width] * (2 * n_f) + [max_time_width] * (2 * n_t), dtype=np.int64), B)
+    draws = np.random.randint(0, high).reshape(B, n_f + n_t, 2).tolist() if B > 0 else []
+    rows = []
+    for T, dr in zip(frame_lens, draws):
+        T = int(T)
+        if consume_time_warp_draws and T - max_time_warp > max_time_warp:
+            center = rr(max_time_warp, T - max_time_warp)
+            rr(center - max_time_warp, center + max_time_warp)
+        row = []
+        for f, w in dr[:n_f]:
+            f0 = rr(0, num_mel - f)
+            if f == 0:
+                row += (0, 0)
+                continue
+            lo = f0 if f0 < num_mel else num_mel
+            hi = f0 + w if f0 + w < num_mel else num_mel
+            row += (lo, hi) if hi > lo else (0, 0)
+        for t, w in dr[n_f:]:
+            if T - t <= 0:
+                row += (0, 0)
+                continue
+            t0 = rr(0, T - t)
+            if t == 0:
+                row += (0, 0)
+                continue
+            lo = t0 if t0 < T else T
+            hi = t0 + w if t0 + w < T else T
+            row += (lo, hi) if hi > lo else (0, 0)
+        rows.append(row)
+    masks = np.asarray(rows, dtype=np.int32).reshape(B, n_f + n_t, 2)
+    bounds = np.sort(masks[:, n_f:].reshape(B, 2 * n_t), axis=1)
+    return masks, np.ascontiguousarray(bounds)

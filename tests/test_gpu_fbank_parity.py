@@ -137,3 +137,45 @@ def test_other_option_sets(lasr_b200):
         hard, soft, below = fbank_parity(g, ref, ref64, lin64)
         assert hard == 0 and soft == 0, kw
         assert below <= 1e-3 * g.size, kw
+
+
+def test_packed_input_and_host_pipeline_match_padded(lasr_b200):
+    """The packed (ragged) device layout and the pipelined host API give bit-identical features."""
+    rng = np.random.default_rng(7)
+    lens = [16000, 401, 70001, 33333, 160000, 999]
+    wavs = [rng.uniform(-0.5, 0.5, n) for n in lens]
+    wav, n = _pad_batch(wavs, "cuda:0")
+    for kw in ({}, {"cmvn": "utt_meanvar"}, {"peak_norm": True}):
+        fe = lasr_b200.GpuFbankFrontend(**kw)
+        ref, rlen = fe(wav, n)
+        offs = np.zeros(len(lens), dtype=np.int64)
+        offs[1:] = np.cumsum((n[:-1] + 3) // 4 * 4)
+        packed = torch.zeros(int(offs[-1] + n[-1] + 64), device="cuda:0")
+        for i, w in enumerate(wavs):
+            packed[offs[i]: offs[i] + n[i]] = torch.from_numpy(w.astype(np.float32)).cuda()
+        got, glen = fe(packed, n, wav_offsets=offs)
+        assert torch.equal(got, ref) and torch.equal(glen, rlen)
+        host = wav.cpu().pin_memory()
+        hf, hl = fe.extract_host(host, n, group_bytes=200000)
+        torch.cuda.synchronize()
+        assert torch.equal(hf, ref.cpu()) and torch.equal(hl, rlen.cpu())
+        df, dl = fe.extract_host(host, n, return_host=False)
+        torch.cuda.synchronize()
+        assert torch.equal(df, ref) and torch.equal(dl, rlen)
+        assert fe.h2d_bytes < host.numel() * 4
+
+
+def test_batch_composition_invariance(lasr_b200):
+    """A frame's features depend only on its 400 samples: shifting an utterance by k*160 samples shifts
+    the rows by k bit for bit, and an utterance alone equals the same utterance inside a batch."""
+    rng = np.random.default_rng(8)
+    w = rng.uniform(-0.5, 0.5, 16000 * 6)
+    others = [rng.uniform(-0.5, 0.5, m) for m in (12345, 16000 * 9)]
+    fe = lasr_b200.GpuFbankFrontend()
+    a, _ = fe(*_pad_batch([w], "cuda:0"))
+    b, _ = fe(*_pad_batch([others[0], w, others[1]], "cuda:0"))
+    T = a.shape[1]
+    assert torch.equal(a[0], b[1, :T])
+    k = 37
+    c, _ = fe(*_pad_batch([w[160 * k:]], "cuda:0"))
+    assert torch.equal(c[0], a[0, k:])

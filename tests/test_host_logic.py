@@ -58,6 +58,25 @@ def test_planner_can_consume_time_warp_draws(lasr_b200, sg):
         assert np.array_equal(np.array([random.random(), np.random.rand()]), sg[key + "_rng_after_full"]), key
 
 
+def test_plan_batch_equals_sequential_planning(lasr_b200):
+    """plan_batch vectorises the numpy draws; masks and both generator states must equal the
+    per-utterance replay (which test_planner_positions_bit_exact pins to the reference)."""
+    lens = [998] * 40 + [5, 12, 39, 98, 300, 7, 11, 1, 2, 40, 41, 3498]
+    for kw in ({}, {"consume_time_warp_draws": True}, {"n_freq_mask": 3, "n_time_mask": 1, "max_freq_width": 15}):
+        random.seed(21)
+        np.random.seed(21)
+        m, b = lasr_b200.specaug.plan_batch(lens, 80, **kw)
+        after = (random.random(), np.random.rand(), int(np.random.randint(0, 1000)))
+        random.seed(21)
+        np.random.seed(21)
+        ref = [lasr_b200.specaug.plan_utterance(t, 80, **kw) for t in lens]
+        assert after == (random.random(), np.random.rand(), int(np.random.randint(0, 1000)))
+        nf = kw.get("n_freq_mask", 2)
+        for i, (f, t) in enumerate(ref):
+            assert np.array_equal(m[i, :nf], f) and np.array_equal(m[i, nf:], t)
+            assert np.array_equal(b[i], np.sort(t.reshape(-1)))
+
+
 def test_plan_batch_layout(lasr_b200):
     random.seed(3)
     np.random.seed(3)
