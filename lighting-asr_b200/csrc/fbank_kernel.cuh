@@ -348,9 +348,13 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     float sum = acc2.x + acc2.y;
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    const float cdc = sum * inv_win * dc_coef;   // (1 - preemph) * frame mean
+                    const float ncdc = -(sum * inv_win * dc_coef);   // -(1 - preemph) * frame mean
+                    // (p - c) w = p w - c w: the products p w do not wait for the shuffle reduction above
+                    float2 wv[NLOAD];
 #pragma unroll
-                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(sub2(v[n2], bc(cdc)), wl[16 * n2]);
+                    for (int n2 = 0; n2 < NLOAD; ++n2) { wv[n2] = wl[16 * n2]; v[n2] = mul2(v[n2], wv[n2]); }
+#pragma unroll
+                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = fma2(bc(ncdc), wv[n2], v[n2]);
 #pragma unroll
                     for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
 
@@ -508,30 +512,43 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         }
         if (a.out_len != nullptr && f0 == 0 && tid == 0) a.out_len[utt] = g.T;
         if (a.stats != nullptr && nvalid > 0) {
+            // Column statistics of what phase C wrote back into the staging tile.  thread = (column j, row
+            // part); fp32 partial sums over <= 11 rows, flushed with fp64 atomics.
             __syncthreads();
             const int nb = a.n_cls - 1;
             const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
             double* sb = a.stats + (long long)utt * a.stats_stride;
-            // thread = (column j, row part): the rows of the tile are split over kThreads / nmel parts so that
-            // the reduction's critical path is short; every part flushes with fp64 atomics
             const int parts = max(1, min(kThreads / nmel, 4));
             const int part = tid / nmel, j = tid - part * nmel;
             if (part < parts) {
                 const int rb = (nvalid * part) / parts, re = (nvalid * (part + 1)) / parts;
                 if (re > rb) {
                     int cls = bounds ? row_class(bounds, nb, f0 + rb) : 0;
-                    double s1 = 0.0, s2 = 0.0;
+                    // sums are taken about a pivot (the part's first value) so that fp32 keeps ~7 digits of the
+                    // spread, not of the offset; converted back in fp64: sum = s1 + n p, sumsq = s2 + 2 p s1 + n p^2
+                    float s1 = 0.f, s2 = 0.f, pivot = 0.f;
+                    int cnt = 0;
+                    double q2 = 0.0;
                     for (int fr = rb; fr < re; ++fr) {
                         if (bounds) {
                             const int cc = row_class(bounds, nb, f0 + fr);
-                            if (cc != cls) { atomicAdd(sb + (long long)cls * nmel + j, s1); s1 = 0.0; cls = cc; }
+                            if (cc != cls) {
+                                const double dp = (double)pivot, d1 = (double)s1;
+                                atomicAdd(sb + (long long)cls * nmel + j, d1 + cnt * dp);
+                                q2 += (double)s2 + 2.0 * dp * d1 + cnt * dp * dp;
+                                s1 = 0.f; s2 = 0.f; cnt = 0; cls = cc;
+                            }
                         }
-                        const double x = (double)outs[fr * ostride + j];
-                        s1 += x;
-                        s2 = fma(x, x, s2);
+                        const float x = outs[fr * ostride + j];
+                        if (fr == rb) pivot = x;
+                        const float d = x - pivot;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                        ++cnt;
                     }
-                    atomicAdd(sb + (long long)cls * nmel + j, s1);
-                    atomicAdd(sb + (long long)a.n_cls * nmel + j, s2);
+                    const double dp = (double)pivot, d1 = (double)s1;
+                    atomicAdd(sb + (long long)cls * nmel + j, d1 + cnt * dp);
+                    atomicAdd(sb + (long long)a.n_cls * nmel + j, q2 + (double)s2 + 2.0 * dp * d1 + cnt * dp * dp);
                 }
             }
         }

@@ -100,7 +100,7 @@ def test_global_cmvn_and_specaug_masks(lasr_b200):
     st = plain.accumulate_stats(wav, n).cpu().numpy()
     ref_st = lasr_frontend.cmvn_stats([raw[i, : T[i]] for i in range(len(lens))])
     assert st.shape == (2, 81) and st[0, 80] == sum(T)
-    assert np.allclose(st, ref_st, rtol=1e-9, atol=1e-6)
+    assert np.allclose(st, ref_st, rtol=2e-7, atol=1e-4)      # fp32 pivoted partial sums per tile part, fp64 across
     mean, istd = lasr_frontend.cmvn_from_stats(ref_st)
     for zero in (False, True):
         fe, g = _run_specaug(lasr_b200, wavs, 11, zero, st)
