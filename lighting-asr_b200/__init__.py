@@ -7,5 +7,6 @@ the repository root.  The hot path lives in ``csrc/`` (hand-written CUDA behind 
 """
 from . import _lib, build, cmvn, lasr_plugin, specaug  # noqa: F401
 from .frontend import FbankPlan, GpuFbankFrontend  # noqa: F401
+from .streaming import StreamingFbank  # noqa: F401
 
-__all__ = ["GpuFbankFrontend", "FbankPlan", "specaug", "cmvn", "build"]
+__all__ = ["GpuFbankFrontend", "FbankPlan", "StreamingFbank", "specaug", "cmvn", "build"]

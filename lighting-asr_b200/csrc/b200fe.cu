@@ -68,11 +68,15 @@ struct b200fe_plan {
 
 static const void* plan_kernel(const b200fe_plan* p, bool peak)
 {
-    if (p->nload == 13) {
-        if (p->static_mel) return peak ? (const void*)fbank_fused_kernel<13, true, true> : (const void*)fbank_fused_kernel<13, true, false>;
-        return peak ? (const void*)fbank_fused_kernel<13, false, true> : (const void*)fbank_fused_kernel<13, false, false>;
+    if (p->nfft == 256) {   // 8 kHz family: two real frames per complex FFT
+        if (p->nload == 13) return peak ? (const void*)fbank_fused_kernel<13, false, true, true> : (const void*)fbank_fused_kernel<13, false, false, true>;
+        return peak ? (const void*)fbank_fused_kernel<16, false, true, true> : (const void*)fbank_fused_kernel<16, false, false, true>;
     }
-    return peak ? (const void*)fbank_fused_kernel<16, false, true> : (const void*)fbank_fused_kernel<16, false, false>;
+    if (p->nload == 13) {
+        if (p->static_mel) return peak ? (const void*)fbank_fused_kernel<13, true, true, false> : (const void*)fbank_fused_kernel<13, true, false, false>;
+        return peak ? (const void*)fbank_fused_kernel<13, false, true, false> : (const void*)fbank_fused_kernel<13, false, false, false>;
+    }
+    return peak ? (const void*)fbank_fused_kernel<16, false, true, false> : (const void*)fbank_fused_kernel<16, false, false, false>;
 }
 
 extern "C" void b200fe_default_opts(b200fe_opts* o)
@@ -110,10 +114,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     p->nmel = o.num_mel_bins;
     auto bad = [&](const char* m) { delete p; return fail(B200FE_EINVAL, "%s", m); };
     if (p->win < 2 || p->shift <= 0) return bad("window size must be >= 2 and shift > 0 (TA:142-145)");
-    if (p->nfft != 512) return bad("only a padded window of 512 samples is supported by the 16 kHz kernel (use the dual-256 path for 8 kHz)");
+    if (p->nfft != 512 && p->nfft != 256) return bad("the padded window must be 512 samples (16 kHz family) or 256 samples (8 kHz family)");
     if (p->nmel <= 3 || p->nmel > kMaxMel) return bad("num_mel_bins must be in (3, 128] (TA:449)");
     if (o.preemphasis_coefficient < 0.f || o.preemphasis_coefficient > 1.f) return bad("preemphasis_coefficient must be in [0,1] (TA:149)");
-    if (p->shift % 2 != 0) return bad("an odd frame shift (in samples) is not supported (8-byte aligned frame loads)");
+    if (p->nfft == 512 && p->shift % 2 != 0) return bad("an odd frame shift (in samples) is not supported (8-byte aligned frame loads)");
     const int nbins = p->nfft / 2;
     const double nyq = 0.5 * o.sample_frequency;
     double high = o.high_freq;
@@ -122,7 +126,7 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         return bad("bad low_freq / high_freq versus Nyquist (TA:460-462)");
 
     // ---- window (TA:86-113), double precision unless the caller supplied its own table ----
-    std::vector<float> window(512, 0.f), window_s(512, 0.f);
+    std::vector<float> window(512, 0.f), window_s(512, 0.f);   // zero-extended (the 256-point family uses the first 256)
     const double scale = std::ldexp(1.0, o.audio_bit - 1);
     for (int n = 0; n < p->win; ++n) {
         double w;
@@ -159,6 +163,7 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         }
     // segment structure: seg(k) = number of centers strictly below mel(k); bin seg gets the
     // up-slope weight, bin seg-1 the down-slope weight; every other entry of column k must be 0.
+    for (int k = 0; k < 256; ++k) p->w_updn[k] = make_float2(0.f, 0.f);
     std::vector<int> seg(nbins);
     for (int k = 0; k < nbins; ++k) {
         const double m = mel_scale(bin_w * k);
@@ -219,9 +224,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         const double t = 2.0 * M_PI * k / 512.0;
         stw[k] = make_float2((float)(-std::sin(t)), (float)(-std::cos(t)));
     }
-    p->nload = (p->win > 384 && p->win <= 416) ? 13 : 16;
-    // a frame reads up to 32*nload samples from its start (zero-weighted past the window)
-    p->tile_floats = ((kFT - 1) * p->shift + 32 * p->nload + 3) & ~3;
+    const int per_reg = p->nfft == 512 ? 32 : 16;     // samples covered by one register slot of the 16 lanes
+    p->nload = (p->win > 12 * per_reg && p->win <= 13 * per_reg) ? 13 : 16;
+    // a frame reads up to per_reg*nload samples from its start (zero-weighted past the window)
+    p->tile_floats = ((kFT - 1) * p->shift + per_reg * p->nload + 3) & ~3;
     p->smem_bytes = make_layout(p->tile_floats, p->nmel).total;
 
     cudaError_t e = cudaGetDevice(&p->device);
@@ -243,15 +249,17 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         return fail(B200FE_ECUDA, "plan upload: %s", cudaGetErrorString(e));
     }
     p->static_mel = 0;
-    if (p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power) {
+    if (p->nfft == 512 && p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power) {
         bool same = memcmp(p->seg_start, kStaticSegStart, sizeof(short) * (p->nmel + 3)) == 0 &&
                     memcmp(p->grp_begin, kStaticGrpBegin, sizeof kStaticGrpBegin) == 0;
         for (int k = 0; same && k < 256; ++k) same = (p->w_updn[k].x == kStaticUp[k] && p->w_updn[k].y == kStaticDn[k]);
         p->static_mel = same ? 1 : 0;
     }
+    // Several plans (option sets) can share one kernel instantiation with different shared-memory sizes:
+    // raise the limit to the device maximum once instead of to this plan's size.
     const void* kfn = plan_kernel(p, false);
-    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes);
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kThreads, p->smem_bytes);

@@ -141,6 +141,125 @@ struct TileGeom {
 // applied by the compact, warp-uniform phase C so that the straight-line mel code stays small.
 __device__ __forceinline__ void emit_bin(float* orow, int j, float e) { orow[j] = e; }
 
+
+// ---------------------------------------------------------------------------------------------
+// Phase A building blocks (all inlined; 16 lanes cooperate on one 256-point complex FFT)
+// ---------------------------------------------------------------------------------------------
+struct FrameCtx {
+    float c_pre, inv_win, dc_coef;   // pre-emphasis, 1 / window size, (1 - preemph) or 0
+    float pmax, prcp, pscale;        // peak normalisation
+    int win;
+};
+
+// 512-point family: the frame's 400 (<= 32*NLOAD) samples are packed as z[n] = y[2n] + j y[2n+1].
+// Load, (peak-normalise,) pre-emphasise, remove DC, window:  y[j] = ((x[j]-m) - c (x[j-1]-m)) w[j]
+//                                                                 = (x[j] - c x[j-1] - (1-c) m) w[j]   (TA:183-204)
+template <int NLOAD, bool kPeak>
+__device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* __restrict__ xf, const float2* __restrict__ wl,
+                                                  const FrameCtx& c, int l)
+{
+    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) {
+        const int j = 2 * (l + 16 * n2);
+        float2 xr = *reinterpret_cast<const float2*>(xf + 32 * n2);
+        float xp = (n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1];   // replicate pad at the frame start (TA:195)
+        if (kPeak) {
+            xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale;
+            xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
+            xp = peak_div(xp, c.pmax, c.prcp) * c.pscale;
+        }
+        if (NLOAD == 16 || n2 == NLOAD - 1) {
+            // samples past the window must not enter the mean (their window weight is 0, but whatever
+            // sits in shared memory there may be NaN)
+            if (j >= c.win) { xr.x = 0.f; xp = 0.f; }
+            if (j + 1 >= c.win) xr.y = 0.f;
+        }
+        acc2 = add2(acc2, xr);
+        v[n2].x = fmaf(-c.c_pre, xp, xr.x);
+        v[n2].y = fmaf(-c.c_pre, xr.x, xr.y);
+    }
+    float sum = acc2.x + acc2.y;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float ncdc = -(sum * c.inv_win * c.dc_coef);   // -(1 - preemph) * frame mean
+    // (p - c) w = p w - c w: the products p w do not wait for the shuffle reduction above
+    float2 wv[NLOAD];
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) { wv[n2] = wl[16 * n2]; v[n2] = mul2(v[n2], wv[n2]); }
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = fma2(bc(ncdc), wv[n2], v[n2]);
+#pragma unroll
+    for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+}
+
+// 256-point family: two consecutive real frames a (at xa) and b (at xb) -> z[n] = ya[n] + j yb[n].
+template <int NLOAD, bool kPeak>
+__device__ __forceinline__ void load_frame_dual(float2 (&v)[16], const float* __restrict__ xa, const float* __restrict__ xb,
+                                                const float* __restrict__ wls, const FrameCtx& c, int l)
+{
+    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) {
+        const int j = l + 16 * n2;
+        const int po = (n2 == 0 && l == 0) ? 0 : 16 * n2 - 1;            // replicate pad at the frame start
+        float2 xr = make_float2(xa[16 * n2], xb[16 * n2]);
+        float2 xp = make_float2(xa[po], xb[po]);
+        if (kPeak) {
+            xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale; xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
+            xp.x = peak_div(xp.x, c.pmax, c.prcp) * c.pscale; xp.y = peak_div(xp.y, c.pmax, c.prcp) * c.pscale;
+        }
+        if (NLOAD == 16 || n2 == NLOAD - 1) {
+            if (j >= c.win) { xr = make_float2(0.f, 0.f); xp = make_float2(0.f, 0.f); }
+        }
+        acc2 = add2(acc2, xr);
+        v[n2] = fma2(bc(-c.c_pre), xp, xr);
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        acc2.x += __shfl_xor_sync(0xffffffffu, acc2.x, o);
+        acc2.y += __shfl_xor_sync(0xffffffffu, acc2.y, o);
+    }
+    const float2 ncdc2 = make_float2(-(acc2.x * c.inv_win * c.dc_coef), -(acc2.y * c.inv_win * c.dc_coef));
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = mul2(add2(v[n2], ncdc2), bc(wls[16 * n2]));
+#pragma unroll
+    for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+}
+
+// 256-point complex FFT across the half-warp: DFT-16 over n2, twiddle W_256^(n1*klo), transposition
+// through shared memory (row n1 = l, column klo), DFT-16 over n1 -> Z[l + 16 r] in v[r].
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], const float2 (&tw)[16], float2* __restrict__ xbuf, int l)
+{
+    dft16(v);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) v[k] = c_mul(v[k], tw[k].x, tw[k].y);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xbuf[l * kXRow + k] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = xbuf[n1 * kXRow + l];
+    __syncwarp();
+    dft16(v);
+}
+
+// Conjugate-pair exchange: the lane's own r = 0..7 (bins l + 16 r) pair with lane (16-l)&15, register
+// 15-r (bins 256 - l - 16 r).  Lane 0 pairs 16 r with 16 (16 - r): shift by one register, bin 0 with itself.
+__device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc)[8], int l, int h2)
+{
+    const int partner = (16 * h2) + ((16 - l) & 15);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        rc[r].x = __shfl_sync(0xffffffffu, v[15 - r].x, partner);
+        rc[r].y = __shfl_sync(0xffffffffu, v[15 - r].y, partner);
+    }
+    if (l == 0) {
+#pragma unroll
+        for (int r = 7; r >= 1; --r) rc[r] = rc[r - 1];
+        rc[0] = v[0];
+    }
+}
+
 #define B200FE_MEL_DEVICE_CODE
 #define MGROUP_BEGIN(w) __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, float* __restrict__ orow) { \
         float au = 0.f, ad = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
@@ -158,7 +277,11 @@ __device__ __forceinline__ void emit_bin(float* orow, int j, float e) { orow[j] 
 #undef MGROUP_END
 #undef B200FE_MEL_DEVICE_CODE
 
-template <int NLOAD, bool kStaticMel, bool kPeak>
+// kDual: padded window of 256 samples (8 kHz family).  Two consecutive real frames a, b are packed as
+// z[n] = ya[n] + j yb[n]; after the same 256-point complex FFT, 2 Xa[k] = Z[k] + conj Z[256-k] and
+// 2j Xb[k] = Z[k] - conj Z[256-k], so the conjugate-pair exchange yields both power spectra without any
+// split twiddle (k = 0..127; the Nyquist bin has zero mel weight, TA:627).
+template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual>
 __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -187,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     // window (x 2^15) as float2 pairs in shared memory: lane l reads pair l + 16 n2 (conflict free)
     for (int k = tid; k < 256; k += kThreads) s_win[k] = make_float2(__ldg(a.window + 2 * k), __ldg(a.window + 2 * k + 1));
     const float2* wl = s_win + l;
+    const float* wls = reinterpret_cast<const float*>(s_win) + l;     // dual-256 mode: scalars w[l + 16 n2]
     float2 tw[16];
 #pragma unroll
     for (int k = 1; k < 16; ++k) tw[k] = __ldg(a.twiddle + l * 16 + k);
@@ -302,110 +426,68 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 if (lane == 0) s_cmask[4] = bal;
             }
 
-            // ================= phase A: half-warp per frame =================
-            float pscale = 1.0f, prcp = 0.0f, pmax = 1.0f;
+            // ================= phase A: half-warp per frame (pair of frames in dual-256 mode) =================
+            FrameCtx fc;
+            fc.c_pre = c_pre; fc.inv_win = inv_win; fc.dc_coef = dc_coef; fc.win = a.win;
+            fc.pmax = 1.0f; fc.prcp = 0.0f; fc.pscale = 1.0f;
             if (kPeak) {
                 // reference: x / (max + 1e-9) in fp64, rounded to fp32, times 2^(bits-1) (datatrans.py:24-25,73-74)
-                pmax = __ldg(a.peak + utt);
-                prcp = (float)(1.0 / ((double)pmax + 1e-9));
-                pscale = a.in_scale;
+                fc.pmax = __ldg(a.peak + utt);
+                fc.prcp = (float)(1.0 / ((double)fc.pmax + 1e-9));
+                fc.pscale = a.in_scale;
             }
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                // frame slot inside the tile; concurrent half-warps of a warp are 4 frames apart so that
-                // their PT stores fall into disjoint banks
-                // Both half-warps run in lock step (full-mask shuffles); a half-warp whose frame is past the
-                // utterance end computes on stale shared memory and simply skips its stores.
-                const int fl = (warp & 3) + 4 * h2 + 8 * (warp >> 2) + 16 * sub;
+            for (int sub = 0; sub < (kDual ? 1 : 2); ++sub) {
+                // Frame slot inside the tile: the two half-warps of a warp store PT columns 4 frames apart
+                // (disjoint banks).  Both half-warps run in lock step (full-mask shuffles); a half-warp whose
+                // frame is past the utterance end computes on stale shared memory and skips its stores.
+                const int fl = kDual ? (8 * (warp >> 1) + 2 * (warp & 1) + 4 * h2)            // frames fl (a), fl + 1 (b)
+                                     : ((warp & 3) + 4 * h2 + 8 * (warp >> 2) + 16 * sub);
                 const bool fvalid = fl < nvalid;
                 if (fl - 4 * h2 < nvalid) {
-                    const float* xf = xs + fl * a.shift + 2 * l;
                     float2 v[16];
-                    // Load, (peak-normalise,) pre-emphasise; accumulate the frame sum on the fly so that
-                    // only p[] stays live.  y[j] = ((x[j]-m) - c (x[j-1]-m)) w[j]
-                    //                            = (x[j] - c x[j-1] - (1-c) m) w[j]      (TA:183-204)
-                    float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int n2 = 0; n2 < NLOAD; ++n2) {
-                        const int j = 2 * (l + 16 * n2);
-                        float2 xr = *reinterpret_cast<const float2*>(xf + 32 * n2);
-                        float xp = (n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1];   // replicate pad at the frame start (TA:195)
-                        if (kPeak) {
-                            xr.x = peak_div(xr.x, pmax, prcp) * pscale;
-                            xr.y = peak_div(xr.y, pmax, prcp) * pscale;
-                            xp = peak_div(xp, pmax, prcp) * pscale;
-                        }
-                        if (NLOAD == 16 || n2 == NLOAD - 1) {
-                            // samples past the window must not enter the mean (their window weight is 0,
-                            // but whatever sits in shared memory there may be NaN)
-                            if (j >= a.win) { xr.x = 0.f; xp = 0.f; }
-                            if (j + 1 >= a.win) xr.y = 0.f;
-                        }
-                        acc2 = add2(acc2, xr);
-                        v[n2].x = fmaf(-c_pre, xp, xr.x);
-                        v[n2].y = fmaf(-c_pre, xr.x, xr.y);
-                    }
-                    float sum = acc2.x + acc2.y;
-#pragma unroll
-                    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    const float ncdc = -(sum * inv_win * dc_coef);   // -(1 - preemph) * frame mean
-                    // (p - c) w = p w - c w: the products p w do not wait for the shuffle reduction above
-                    float2 wv[NLOAD];
-#pragma unroll
-                    for (int n2 = 0; n2 < NLOAD; ++n2) { wv[n2] = wl[16 * n2]; v[n2] = mul2(v[n2], wv[n2]); }
-#pragma unroll
-                    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = fma2(bc(ncdc), wv[n2], v[n2]);
-#pragma unroll
-                    for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
-
-                    // ---- pass 1: DFT-16 over n2, twiddle W_256^(n1*klo) ----
-                    dft16(v);
-#pragma unroll
-                    for (int k = 1; k < 16; ++k) v[k] = c_mul(v[k], tw[k].x, tw[k].y);
-                    // ---- transpose through shared memory: row n1 = l, column klo ----
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) xbuf[l * kXRow + k] = v[k];
-                    __syncwarp();
-#pragma unroll
-                    for (int n1 = 0; n1 < 16; ++n1) v[n1] = xbuf[n1 * kXRow + l];
-                    __syncwarp();
-                    // ---- pass 2: DFT-16 over n1 -> Z[l + 16 r] in v[r] ----
-                    dft16(v);
-                    // ---- conjugate-pair exchange: own r = 0..7 pairs with lane (16-l)&15, register 15-r ----
-                    const int partner = (16 * h2) + ((16 - l) & 15);
+                    if (kDual) load_frame_dual<NLOAD, kPeak>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
+                    else load_frame_single<NLOAD, kPeak>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
+                    fft256_halfwarp(v, tw, xbuf, l);
                     float2 rc[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        rc[r].x = __shfl_sync(0xffffffffu, v[15 - r].x, partner);
-                        rc[r].y = __shfl_sync(0xffffffffu, v[15 - r].y, partner);
-                    }
-                    if (l == 0) {   // bins 16 r pair with 16 (16 - r): shift by one register, bin 0 pairs with itself
-#pragma unroll
-                        for (int r = 7; r >= 1; --r) rc[r] = rc[r - 1];
-                        rc[0] = v[0];
-                    }
-                    // ---- real-FFT split + power: 2X[k] = S + T, 2 conj X[256-k] = S - T ----
+                    pair_exchange(v, rc, l, h2);
                     // PT4 layout: float index of (k, fl) = ((k>>2)*kPTStride + fl)*4 + (k&3)
-                    float* pa = pt + ((l >> 2) * kPTStride + fl) * 4 + (l & 3);                                // k = l + 16 r
-                    float* pb = pt + (((256 - l) >> 2) * kPTStride + fl) * 4 + ((256 - l) & 3);                // k = 256 - l - 16 r
+                    float* pa = pt + ((l >> 2) * kPTStride + fl) * 4 + (l & 3);                        // k = l + 16 r
+                    if (kDual) {
+                        // ---- separate the two real spectra; |2 Xa|^2 and |2 Xb|^2 (0.25 folded in the mel weights)
+                        const bool bvalid = fl + 1 < nvalid;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        float2 bcj = make_float2(rc[r].x, -rc[r].y);
-                        float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
-                        const float2 sw = stw[16 * r];
-                        float2 T = c_mul(D, sw.x, sw.y);
-                        float2 xa = add2(S, T), xb = sub2(S, T);
-                        xa = mul2(xa, xa); xb = mul2(xb, xb);
-                        float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
-                        if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
-                        if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
-                        if (fvalid && (r != 0 || l != 0)) pb[-r * 4 * kPTStride * 4] = pwb;
-                    }
-                    if (l == 0 && fvalid) {   // bin 128 is its own partner: X[128] = conj Z[128]
-                        float2 z = v[8];
-                        float p = 4.0f * (z.x * z.x + z.y * z.y);
-                        if (!use_power) p = sqrtf(p);
-                        pt[(32 * kPTStride + fl) * 4] = p;
+                        for (int r = 0; r < 8; ++r) {
+                            const float2 bcj = make_float2(rc[r].x, -rc[r].y);
+                            float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
+                            S = mul2(S, S); D = mul2(D, D);
+                            float pwa = S.x + S.y, pwb = D.x + D.y;
+                            if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }
+                            if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
+                            if (bvalid) pa[r * 4 * kPTStride * 4 + 4] = pwb;
+                        }
+                    } else {
+                        // ---- real-FFT split + power: 2X[k] = S + T, 2 conj X[256-k] = S - T ----
+                        float* pb = pt + (((256 - l) >> 2) * kPTStride + fl) * 4 + ((256 - l) & 3);    // k = 256 - l - 16 r
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float2 bcj = make_float2(rc[r].x, -rc[r].y);
+                            const float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
+                            const float2 sw = stw[16 * r];
+                            const float2 T = c_mul(D, sw.x, sw.y);
+                            float2 xa = add2(S, T), xb = sub2(S, T);
+                            xa = mul2(xa, xa); xb = mul2(xb, xb);
+                            float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
+                            if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
+                            if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
+                            if (fvalid && (r != 0 || l != 0)) pb[-r * 4 * kPTStride * 4] = pwb;
+                        }
+                        if (l == 0 && fvalid) {   // bin 128 is its own partner: X[128] = conj Z[128]
+                            const float2 z = v[8];
+                            float p = 4.0f * (z.x * z.x + z.y * z.y);
+                            if (!use_power) p = sqrtf(p);
+                            pt[(32 * kPTStride + fl) * 4] = p;
+                        }
                     }
                 }
             }
