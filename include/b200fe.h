@@ -50,6 +50,7 @@ typedef struct b200fe_opts {
     int window_type;               /* 0 povey, 1 hanning, 2 hamming, 3 rectangular, 4 blackman (TA:86-113) */
     float blackman_coeff;          /* 0.42 */
     int audio_bit;                 /* 16: waveform is scaled by 2^(audio_bit-1) (datatrans.py:74) */
+    float dither;                  /* 0 (LASR default, datatrans.py:47); else x[f][j] += dither * N(0,1) per (frame, sample), TA:179-181 */
     /* Optional host tables that override the built-in (double precision, rounded once)
      * constants so that they match the caller's torch build bit for bit.  May be NULL. */
     const float* window;           /* [window_size] */
@@ -128,6 +129,12 @@ typedef struct b200fe_fbank_args {
      * promises that every offset is a multiple of 4 samples (enables the TMA loader). */
     const long long* d_wav_offsets;
     int offsets_aligned;
+    /* Dither (plan option dither != 0): standard-normal noise per (utterance, frame, sample).  By default it
+     * comes from a counter-based Philox4x32-10 generator keyed by dither_seed (use a fresh seed per call);
+     * d_dither_noise [batch][max_frames][window_size] replaces it, e.g. with torch.randn drawn under the same
+     * torch.manual_seed as the reference ("seeded identically"). */
+    unsigned long long dither_seed;
+    const float* d_dither_noise;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

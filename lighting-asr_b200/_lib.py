@@ -14,7 +14,7 @@ class Opts(C.Structure):
         ("num_mel_bins", C.c_int), ("low_freq", C.c_float), ("high_freq", C.c_float),
         ("preemphasis_coefficient", C.c_float), ("remove_dc_offset", C.c_int), ("use_power", C.c_int),
         ("use_log_fbank", C.c_int), ("window_type", C.c_int), ("blackman_coeff", C.c_float),
-        ("audio_bit", C.c_int), ("window", C.c_void_p), ("mel_weights", C.c_void_p),
+        ("audio_bit", C.c_int), ("dither", C.c_float), ("window", C.c_void_p), ("mel_weights", C.c_void_p),
     ]
 
 
@@ -27,6 +27,7 @@ class FbankArgs(C.Structure):
         ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
         ("d_tile_table", C.c_void_p), ("n_tiles", C.c_int), ("d_work_counter", C.c_void_p),
         ("d_wav_offsets", C.c_void_p), ("offsets_aligned", C.c_int),
+        ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p),
     ]
 
 

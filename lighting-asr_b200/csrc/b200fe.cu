@@ -95,6 +95,7 @@ extern "C" void b200fe_default_opts(b200fe_opts* o)
     o->window_type = 0;
     o->blackman_coeff = 0.42f;
     o->audio_bit = 16;
+    o->dither = 0.f;
 }
 
 extern "C" const char* b200fe_last_error(void) { return g_err.c_str(); }
@@ -249,7 +250,7 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         return fail(B200FE_ECUDA, "plan upload: %s", cudaGetErrorString(e));
     }
     p->static_mel = 0;
-    if (p->nfft == 512 && p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power) {
+    if (p->nfft == 512 && p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power && o.dither == 0.f) {
         bool same = memcmp(p->seg_start, kStaticSegStart, sizeof(short) * (p->nmel + 3)) == 0 &&
                     memcmp(p->grp_begin, kStaticGrpBegin, sizeof kStaticGrpBegin) == 0;
         for (int k = 0; same && k < 256; ++k) same = (p->w_updn[k].x == kStaticUp[k] && p->w_updn[k].y == kStaticDn[k]);
@@ -360,6 +361,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.preemph = p->o.preemphasis_coefficient;
     a.log_floor = 1.1920928955078125e-07f;   // TA:21-22
     a.in_scale = (float)std::ldexp(1.0, p->o.audio_bit - 1);
+    a.dither = p->o.dither; a.dither_seed = g->dither_seed; a.dither_noise = g->d_dither_noise;
     a.window = g->d_peak ? p->d_window_plain : p->d_window_scaled;
     a.twiddle = p->d_twiddle; a.split_tw = p->d_split_tw;
     a.cm_mean = g->d_cmvn_mean; a.cm_istd = g->d_cmvn_istd; a.cm_stride = g->cmvn_stride;

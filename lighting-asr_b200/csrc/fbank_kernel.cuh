@@ -61,6 +61,11 @@ struct FbankArgs {
     float preemph;
     float log_floor;             // FLT_EPSILON
     float in_scale;              // 2^(audio_bit-1), applied on load when peak != nullptr (else folded in window)
+    // dither (TA:179-181): x[f][j] += dither * n[f][j], independent noise per (frame, sample).  n comes from
+    // dither_noise [B][Tmax][win] when given (parity with a host generator), else from Philox4x32-10.
+    float dither;
+    unsigned long long dither_seed;
+    const float* dither_noise;
     // plan tables
     const float* window;         // [512] window * (in_scale or 1), zero-extended
     const float2* twiddle;       // [16][16] W_256^(n1*klo)
@@ -149,12 +154,49 @@ struct FrameCtx {
     float c_pre, inv_win, dc_coef;   // pre-emphasis, 1 / window size, (1 - preemph) or 0
     float pmax, prcp, pscale;        // peak normalisation
     int win;
+    // dither (generic kernels only)
+    float dither;                    // in input units (already divided by the folded 2^15 scale)
+    unsigned long long seed;
+    const float* noise_a;            // external noise row of frame a (nullptr -> Philox)
+    const float* noise_b;            // ... of frame b (dual mode)
+    unsigned utt, ta, tb;            // counters for the generator
 };
+
+// Philox4x32-10 counter-based generator -> two standard normals (Box-Muller) for the sample pair
+// (2*pair, 2*pair+1) of frame t of utterance utt.
+__device__ __forceinline__ float2 philox_normal_pair(unsigned long long seed, unsigned utt, unsigned t, unsigned pair)
+{
+    unsigned c0 = pair, c1 = t, c2 = utt, c3 = 0x5eed5eedu;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;   // (0, 1)
+    const float u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+// noise for sample j of one frame
+__device__ __forceinline__ float dither_at(const FrameCtx& c, const float* __restrict__ ext, unsigned t, int j)
+{
+    j = min(j, c.win - 1);                       // registers past the window are masked afterwards
+    if (ext != nullptr) return __ldg(ext + j);
+    const float2 p = philox_normal_pair(c.seed, c.utt, t, (unsigned)(j >> 1));
+    return (j & 1) ? p.y : p.x;
+}
 
 // 512-point family: the frame's 400 (<= 32*NLOAD) samples are packed as z[n] = y[2n] + j y[2n+1].
 // Load, (peak-normalise,) pre-emphasise, remove DC, window:  y[j] = ((x[j]-m) - c (x[j-1]-m)) w[j]
 //                                                                 = (x[j] - c x[j-1] - (1-c) m) w[j]   (TA:183-204)
-template <int NLOAD, bool kPeak>
+template <int NLOAD, bool kPeak, bool kDither>
 __device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* __restrict__ xf, const float2* __restrict__ wl,
                                                   const FrameCtx& c, int l)
 {
@@ -168,6 +210,12 @@ __device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* 
             xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale;
             xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
             xp = peak_div(xp, c.pmax, c.prcp) * c.pscale;
+        }
+        if (kDither && c.dither != 0.f) {
+            // noise is drawn per (frame, sample) AFTER framing (TA:174-181): x[j-1] carries this frame's n[j-1]
+            xr.x = fmaf(c.dither, dither_at(c, c.noise_a, c.ta, j), xr.x);
+            xr.y = fmaf(c.dither, dither_at(c, c.noise_a, c.ta, j + 1), xr.y);
+            xp = fmaf(c.dither, dither_at(c, c.noise_a, c.ta, j > 0 ? j - 1 : 0), xp);
         }
         if (NLOAD == 16 || n2 == NLOAD - 1) {
             // samples past the window must not enter the mean (their window weight is 0, but whatever
@@ -194,7 +242,7 @@ __device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* 
 }
 
 // 256-point family: two consecutive real frames a (at xa) and b (at xb) -> z[n] = ya[n] + j yb[n].
-template <int NLOAD, bool kPeak>
+template <int NLOAD, bool kPeak, bool kDither>
 __device__ __forceinline__ void load_frame_dual(float2 (&v)[16], const float* __restrict__ xa, const float* __restrict__ xb,
                                                 const float* __restrict__ wls, const FrameCtx& c, int l)
 {
@@ -208,6 +256,13 @@ __device__ __forceinline__ void load_frame_dual(float2 (&v)[16], const float* __
         if (kPeak) {
             xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale; xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
             xp.x = peak_div(xp.x, c.pmax, c.prcp) * c.pscale; xp.y = peak_div(xp.y, c.pmax, c.prcp) * c.pscale;
+        }
+        if (kDither && c.dither != 0.f) {
+            const int jp = j > 0 ? j - 1 : 0;
+            xr.x = fmaf(c.dither, dither_at(c, c.noise_a, c.ta, j), xr.x);
+            xr.y = fmaf(c.dither, dither_at(c, c.noise_b, c.tb, j), xr.y);
+            xp.x = fmaf(c.dither, dither_at(c, c.noise_a, c.ta, jp), xp.x);
+            xp.y = fmaf(c.dither, dither_at(c, c.noise_b, c.tb, jp), xp.y);
         }
         if (NLOAD == 16 || n2 == NLOAD - 1) {
             if (j >= c.win) { xr = make_float2(0.f, 0.f); xp = make_float2(0.f, 0.f); }
@@ -430,6 +485,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             FrameCtx fc;
             fc.c_pre = c_pre; fc.inv_win = inv_win; fc.dc_coef = dc_coef; fc.win = a.win;
             fc.pmax = 1.0f; fc.prcp = 0.0f; fc.pscale = 1.0f;
+            // the window table carries the 2^15 input scale unless peak normalisation applies it on load
+            fc.dither = kPeak ? a.dither : a.dither / a.in_scale;
+            fc.seed = a.dither_seed; fc.utt = (unsigned)utt; fc.ta = fc.tb = 0; fc.noise_a = fc.noise_b = nullptr;
             if (kPeak) {
                 // reference: x / (max + 1e-9) in fp64, rounded to fp32, times 2^(bits-1) (datatrans.py:24-25,73-74)
                 fc.pmax = __ldg(a.peak + utt);
@@ -446,8 +504,14 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 const bool fvalid = fl < nvalid;
                 if (fl - 4 * h2 < nvalid) {
                     float2 v[16];
-                    if (kDual) load_frame_dual<NLOAD, kPeak>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
-                    else load_frame_single<NLOAD, kPeak>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
+                    if (!kStaticMel && a.dither != 0.f) {      // generic kernels only; the static (LASR default) path has dither 0
+                        const long long row = ((long long)utt * a.Tmax + f0 + fl) * a.win;
+                        fc.ta = (unsigned)(f0 + fl); fc.tb = fc.ta + 1;
+                        fc.noise_a = a.dither_noise ? a.dither_noise + row : nullptr;
+                        fc.noise_b = a.dither_noise ? a.dither_noise + row + a.win : nullptr;
+                    }
+                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
+                    else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
                     fft256_halfwarp(v, tw, xbuf, l);
                     float2 rc[8];
                     pair_exchange(v, rc, l, h2);

@@ -67,7 +67,7 @@ class FbankPlan:
     def __init__(self, num_mel_bins=80, sample_frequency=16000.0, frame_length=25.0, frame_shift=10.0,
                  low_freq=20.0, high_freq=0.0, preemphasis_coefficient=0.97, remove_dc_offset=True,
                  use_power=True, use_log_fbank=True, window_type="povey", blackman_coeff=0.42, audio_bit=16,
-                 torch_tables=True):
+                 dither=0.0, torch_tables=True):
         if window_type not in _WINDOWS:
             raise Exception("Invalid window type " + window_type)
         self.lib = _lib.load()
@@ -86,6 +86,7 @@ class FbankPlan:
         o.window_type = _WINDOWS[window_type]
         o.blackman_coeff = blackman_coeff
         o.audio_bit = audio_bit
+        o.dither = dither
         keep = []
         if torch_tables:
             win = int(sample_frequency * frame_length * 0.001)
@@ -138,15 +139,15 @@ class GpuFbankFrontend(torch.nn.Module):
         if not snip_edges or use_energy or vtln_warp != 1.0 or not round_to_power_of_two:
             raise ValueError("snip_edges=False, use_energy=True, vtln_warp != 1 and round_to_power_of_two=False "
                              "are not reachable from LASR configs and are not implemented")
-        if dither != 0.0:
-            raise ValueError("dither != 0 is not implemented yet (LASR default is 0.0, datatrans.py:47)")
         if cmvn not in _CMVN_MODES:
             raise ValueError("cmvn must be one of %s" % (_CMVN_MODES,))
         self.opts = dict(num_mel_bins=num_mel_bins, sample_frequency=sample_frequency, frame_length=frame_length,
                          frame_shift=frame_shift, low_freq=low_freq, high_freq=high_freq,
                          preemphasis_coefficient=preemphasis_coefficient, remove_dc_offset=remove_dc_offset,
                          use_power=use_power, use_log_fbank=use_log_fbank, window_type=window_type,
-                         blackman_coeff=blackman_coeff, audio_bit=audio_bit)
+                         blackman_coeff=blackman_coeff, audio_bit=audio_bit, dither=dither)
+        self.dither = dither
+        self.dither_seed = 0            # advanced on every call; set it (or torch.manual_seed-derived) for reproducibility
         self.num_mel_bins = num_mel_bins
         self.peak_norm = peak_norm
         self.cmvn = cmvn
@@ -202,7 +203,7 @@ class GpuFbankFrontend(torch.nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None):
+    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None, dither_noise=None):
         """``wav_offsets`` (int64 host array, multiples of 4) switches to the packed layout: ``wav`` is then
         a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
         if not wav.is_cuda:
@@ -320,6 +321,14 @@ class GpuFbankFrontend(torch.nn.Module):
             a.d_out = off(feats, b0, Tmax * D * 4)
             a.d_out_len = off(feat_len, b0, 8)
             a.max_frames = Tmax
+            if self.dither != 0.0:
+                if dither_noise is not None:
+                    # (B, Tmax, window) standard-normal noise, e.g. torch.randn under the reference's seed
+                    if dither_noise.shape != (B, Tmax, plan.window_size) or dither_noise.dtype != torch.float32 or not dither_noise.is_contiguous():
+                        raise ValueError("dither_noise must be contiguous float32 (B, Tmax, window_size)")
+                    a.d_dither_noise = off(dither_noise, b0, Tmax * plan.window_size * 4)
+                self.dither_seed += 1
+                a.dither_seed = self.dither_seed
             if gm is not None:
                 a.d_cmvn_mean, a.d_cmvn_istd, a.cmvn_stride = _ptr(gm), _ptr(gi), 0
             if self.specaug:
