@@ -88,7 +88,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, out):
     """The reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
         return
@@ -117,16 +117,27 @@ def reference_arm(args, rank, world):
                              "sample": "the full 256-utterance C2 batch per step (%.3f audio-h): torchaudio.compliance.kaldi.fbank via the oracle's "
                                        "restatement of WavToKaldiFbank + fp64 utterance CMVN + batch_list, %d single-threaded worker processes" % (hours, cores)},
             "e2e": {"value": val, "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Everything that libraries print to stdout (e.g. NCCL's version banner) is sent to stderr; the
+    returned file object is the real stdout, used for the single JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="device-resident loop only (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -134,7 +145,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, rank, world, real_stdout)
         return
 
     import torch
@@ -185,6 +196,10 @@ def main():
     fused_ms = [a.elapsed_time(b) for a, b in fe.profile_events]
     fe.profile_events = None
 
+    if args.profile_only:
+        print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "fused_ms_per_step": sum(fused_ms) / args.steps,
+                          "gpu_launches": launches}), file=real_stdout, flush=True)
+        return
     # ---- end to end through the public host API: pinned host waveforms in, host features out ----
     for _ in range(2):
         fe.extract_host(wav_pin, n, device=dev)
@@ -279,7 +294,7 @@ def main():
                                     "sample": "%d x the full C2 batch (%.3f audio-h each) in %.1f s: torchaudio.compliance.kaldi.fbank via the oracle's "
                                               "restatement of WavToKaldiFbank + fp64 utterance CMVN + batch_list, %d single-threaded worker processes"
                                               % (r["reps"], r["audio_hours_per_rep"], r["seconds"], cores)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
