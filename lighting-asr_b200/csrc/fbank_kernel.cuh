@@ -116,7 +116,7 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     L.outs_off = L.xbuf_off;
     L.pt_off = o; o += 64 * kPTStride * 16;
     L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
-    L.bar_off = o; o += 8 * kStages + 16;   // mbarriers + 2 scheduler slots
+    L.bar_off = o; o += 8 * kStages + 32;   // mbarriers + 2 tile descriptors (int4)
     L.total = o;
     return L;
 }
@@ -393,14 +393,28 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     const bool zmask = a.mask_zero && a.masks != nullptr;
     const int nmask = a.n_fmask + a.n_tmask;
 
-    auto tile_geom = [&](int utt_, int j_) -> TileGeom {
+    // ---- tile scheduler ------------------------------------------------------------------------
+    // Thread 0 resolves tile descriptors (id, utterance, first frame, frame count of the utterance) TWO tiles
+    // ahead and publishes them through shared memory, so the dependent global loads (atomic counter ->
+    // tile table -> sample count) never sit on any warp's critical path.
+    struct Desc { int id, utt, f0, T; };
+    const bool dyn = a.tile_table != nullptr;
+    int4* s_desc = reinterpret_cast<int4*>(bars + kStages);
+    auto resolve = [&](int id) -> Desc {               // thread 0 only
+        Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
+        if (id < a.ntiles) {
+            if (dyn) { const int2 e = __ldg(a.tile_table + id); d.utt = e.x; d.f0 = e.y; }
+            else { d.utt = (int)((unsigned)id / (unsigned)a.tiles_per_utt); d.f0 = (id - d.utt * a.tiles_per_utt) * kFT; }
+            const unsigned n = (unsigned)__ldg(a.nsamp + d.utt);       // < 2^31 samples per utterance
+            d.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
+        }
+        return d;
+    };
+    auto geom = [&](const Desc& d) -> TileGeom {
         TileGeom g;
-        g.utt = utt_;
-        g.f0 = j_ * kFT;
-        const unsigned n = (unsigned)__ldg(a.nsamp + g.utt);       // < 2^31 samples per utterance
-        g.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
-        g.nvalid = min(max(g.T - g.f0, 0), kFT);
-        g.nrows = a.tile_table != nullptr ? g.nvalid : min(a.Tmax - g.f0, kFT);
+        g.utt = d.utt; g.f0 = d.f0; g.T = d.T;
+        g.nvalid = min(max(d.T - d.f0, 0), kFT);
+        g.nrows = dyn ? g.nvalid : min(a.Tmax - d.f0, kFT);
         return g;
     };
     auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
@@ -414,40 +428,35 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
 
     int it = 0;
     uint32_t phase_bits = 0;
-    const bool dyn = a.tile_table != nullptr;
-    int* s_sched = reinterpret_cast<int*>(bars + kStages);
-    int tile = blockIdx.x, nxt = blockIdx.x + gridDim.x;
-    if (dyn) {
-        // dynamic scheduling: tile ids come from an atomic counter, one tile of look-ahead
-        if (tid == 0) { s_sched[0] = atomicAdd(a.work_counter, 1); s_sched[1] = atomicAdd(a.work_counter, 1); }
-        __syncthreads();
-        tile = s_sched[0]; nxt = s_sched[1];
+    if (tid == 0) {
+        const int id0 = dyn ? atomicAdd(a.work_counter, 1) : (int)blockIdx.x;
+        const int id1 = dyn ? atomicAdd(a.work_counter, 1) : (int)(blockIdx.x + gridDim.x);
+        const Desc d0 = resolve(id0), d1 = resolve(id1);
+        s_desc[0] = make_int4(d0.id, d0.utt, d0.f0, d0.T);
+        s_desc[1] = make_int4(d1.id, d1.utt, d1.f0, d1.T);
     }
-    // static mode: tile -> (utterance, tile-in-utterance) is advanced incrementally (no division per tile)
-    const int step_q = (int)(gridDim.x / (unsigned)a.tiles_per_utt), step_r = (int)(gridDim.x % (unsigned)a.tiles_per_utt);
-    int cur_utt = (int)((unsigned)blockIdx.x / (unsigned)a.tiles_per_utt), cur_j = blockIdx.x - cur_utt * a.tiles_per_utt;
-    auto geom_of = [&](int t) -> TileGeom {
-        if (dyn) { const int2 e = __ldg(a.tile_table + t); return tile_geom(e.x, e.y / kFT); }
-        return tile_geom(cur_utt, cur_j);
-    };
-    TileGeom g = tile < a.ntiles ? geom_of(tile) : tile_geom(0, 0);
-    if (a.use_tma && tid == 0 && tile < a.ntiles) issue_load(g, 0);
+    __syncthreads();
+    Desc cur, nxt;
+    { const int4 v0 = s_desc[0], v1 = s_desc[1]; cur = Desc{v0.x, v0.y, v0.z, v0.w}; nxt = Desc{v1.x, v1.y, v1.z, v1.w}; }
+    TileGeom g = geom(cur);
+    if (a.use_tma && tid == 0 && cur.id < a.ntiles) issue_load(g, 0);
 
-    for (; tile < a.ntiles; ++it) {
+    for (; cur.id < a.ntiles; ++it) {
         const int stage = it % kStages;
         const int utt = g.utt, f0 = g.f0, nvalid = g.nvalid, nrows = g.nrows;
         float* xs = reinterpret_cast<float*>(smem + L.tile_off[stage]);
-        TileGeom gn = g;
-        cur_utt += step_q; cur_j += step_r;
-        if (cur_j >= a.tiles_per_utt) { cur_j -= a.tiles_per_utt; cur_utt += 1; }
-        if (nxt < a.ntiles) gn = geom_of(nxt);
-        int fetched = 0;
-        if (dyn && tid == 0) fetched = atomicAdd(a.work_counter, 1);      // the tile after next; consumed at the end of this iteration
+        const TileGeom gn = geom(nxt);
+        Desc fut; fut.id = a.ntiles; fut.utt = 0; fut.f0 = 0; fut.T = 0;
+        if (tid == 0) {
+            // descriptor of the tile after next: its loads complete while this tile is being computed
+            const int id2 = dyn ? atomicAdd(a.work_counter, 1) : nxt.id + (int)gridDim.x;
+            fut = resolve(nxt.id < a.ntiles ? id2 : a.ntiles);
+        }
 
         if (a.use_tma) {
             // prefetch the next tile of this CTA into the other stage (its previous contents were
             // consumed before the phase-A barrier of the previous iteration)
-            if (tid == 0 && nxt < a.ntiles) issue_load(gn, (it + 1) % kStages);
+            if (tid == 0 && nxt.id < a.ntiles) issue_load(gn, (it + 1) % kStages);
             // a stage's mbarrier phase advances only for tiles that actually carried a load
             if (nvalid > 0) { mbar_wait(&bars[stage], (phase_bits >> stage) & 1u); phase_bits ^= (1u << stage); }
         } else if (nvalid > 0) {
@@ -556,7 +565,6 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 }
             }
             __syncthreads();   // PT complete; tile stage and transposition buffers are free
-            if (dyn && tid == 0) s_sched[it & 1] = fetched;   // every thread consumed this slot before the barrier
 
             // ================= phase B: warp = mel-bin group, lane = frame =================
             {
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 }
             }
         }
-        if (a.out_len != nullptr && f0 == 0 && tid == 0) a.out_len[utt] = g.T;
+        if (a.out_len != nullptr && f0 == 0 && nrows > 0 && tid == 0) a.out_len[utt] = g.T;
         if (a.stats != nullptr && nvalid > 0) {
             // Column statistics of what phase C wrote back into the staging tile.  thread = (column j, row
             // part); fp32 partial sums over <= 11 rows, flushed with fp64 atomics.
@@ -699,10 +707,13 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             }
         }
         // the staging area aliases the transposition buffers that the next phase A overwrites
-        if (nvalid > 0) __syncthreads();
+        // Publish the descriptor resolved above into the slot of the tile that just finished (all threads copied
+        // it before the previous closing barrier); the closing barrier also protects the staging area.
+        if (tid == 0) s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
+        __syncthreads();
+        cur = nxt;
         g = gn;
-        tile = nxt;
-        nxt = dyn ? s_sched[it & 1] : nxt + (int)gridDim.x;
+        { const int4 v = s_desc[it & 1]; nxt = Desc{v.x, v.y, v.z, v.w}; }
     }
 }
 
