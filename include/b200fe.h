@@ -145,6 +145,13 @@ int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, v
 int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
                       int batch, float* d_packed, void* stream);
 
+/* Device -> host copy of the first h_rows[u] rows of every utterance of a padded [batch][utt_rows][row_elems]
+ * feature tensor into a host tensor of the same layout (one cudaMemcpyAsync per utterance).  The caller
+ * passes, per utterance, the number of rows that can differ from what the host buffer already holds
+ * (frames now valid, or valid in the previous batch and zero now), so zero padding is not re-sent. */
+int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
+                      float* h_feats, void* stream);
+
 /* Turns per-utterance statistics into (a) utterance CMVN vectors and (b) the SpecAugment mean
  * fills of R/lasr/utils/specaugment.py:71-74,102-105 (each mask is filled with the mean of the
  * CURRENT array, i.e. after CMVN and after all earlier masks), evaluated in closed form from the

@@ -43,7 +43,7 @@ class PostArgs(C.Structure):
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table",
-    "b200fe_peak_absmax", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_postpass", "b200fe_cmvn_from_stats",
+    "b200fe_peak_absmax", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_postpass", "b200fe_cmvn_from_stats",
 ]
 
 _lib = None
@@ -93,6 +93,8 @@ def load(build_if_missing=True):
     lib.b200fe_fbank_fused.restype = C.c_int
     lib.b200fe_h2d_ragged.argtypes = [C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.b200fe_h2d_ragged.restype = C.c_int
+    lib.b200fe_d2h_ragged.argtypes = [C.c_void_p, c_ll, c_ll, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.b200fe_d2h_ragged.restype = C.c_int
     lib.b200fe_postpass.argtypes = [C.c_void_p, C.POINTER(PostArgs), C.c_void_p]
     lib.b200fe_postpass.restype = C.c_int
     lib.b200fe_cmvn_from_stats.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, c_fp, c_fp]

@@ -339,6 +339,20 @@ extern "C" int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const l
     return B200FE_OK;
 }
 
+extern "C" int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
+                                 float* h_feats, void* stream)
+{
+    if (!d_feats || !h_rows || !h_feats || batch < 0 || row_elems <= 0 || utt_rows <= 0) return fail(B200FE_EINVAL, "d2h_ragged: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int u = 0; u < batch; ++u) {
+        const long long r = h_rows[u] < utt_rows ? h_rows[u] : utt_rows;
+        if (r <= 0) continue;
+        const long long off = (long long)u * utt_rows * row_elems;
+        CUDA_TRY(cudaMemcpyAsync(h_feats + off, d_feats + off, sizeof(float) * (size_t)(r * row_elems), cudaMemcpyDeviceToHost, st));
+    }
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args* g, void* stream)
 {
     if (!p || !g) return fail(B200FE_EINVAL, "fbank_fused: null argument");

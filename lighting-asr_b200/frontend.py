@@ -415,11 +415,14 @@ class GpuFbankFrontend(torch.nn.Module):
             c = dict(wav=torch.zeros((total + 64,), dtype=torch.float32, device=dev),
                      feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
                      flen=torch.empty((B,), dtype=torch.int64, device=dev),
-                     hfeats=torch.empty((B, Tmax, D), dtype=torch.float32, pin_memory=True),
+                     hfeats=torch.zeros((B, Tmax, D), dtype=torch.float32).pin_memory(),
                      hlen=torch.empty((B,), dtype=torch.int64, pin_memory=True),
+                     hrows=np.zeros(B, dtype=np.int64),      # rows of the host buffer that are not known to be zero
                      s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev))
             self._host_cache[key] = c
         lib = _lib.load()
+        # rows to bring back per utterance: valid now, or valid in the previous batch held by the host buffer
+        d2h_rows = np.ascontiguousarray(np.maximum(T_host, c["hrows"]).astype(np.int64))
         main = torch.cuda.current_stream(dev)
         s_in, s_out = c["s_in"], c["s_out"]
         s_in.wait_stream(main)
@@ -448,15 +451,18 @@ class GpuFbankFrontend(torch.nn.Module):
             if return_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_c)
-                    c["hfeats"][b0:b1].copy_(c["feats"][b0:b1], non_blocking=True)
-                self.d2h_bytes += (b1 - b0) * Tmax * D * 4
+                s_out.wait_event(ev_c)
+                _lib.check(lib.b200fe_d2h_ragged(C.c_void_p(c["feats"].data_ptr() + b0 * Tmax * D * 4), D, Tmax,
+                                                 C.c_void_p(d2h_rows.ctypes.data + b0 * 8), b1 - b0,
+                                                 C.c_void_p(c["hfeats"].data_ptr() + b0 * Tmax * D * 4), C.c_void_p(s_out.cuda_stream)),
+                           "b200fe_d2h_ragged")
+                self.d2h_bytes += int(d2h_rows[b0:b1].sum()) * D * 4
         if return_host:
             with torch.cuda.stream(s_out):
                 c["hlen"].copy_(c["flen"], non_blocking=True)
             self.d2h_bytes += B * 8
             main.wait_stream(s_out)
+            c["hrows"] = T_host.astype(np.int64).copy()
             return c["hfeats"], c["hlen"]
         return c["feats"], c["flen"]
 

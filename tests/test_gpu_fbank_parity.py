@@ -163,6 +163,13 @@ def test_packed_input_and_host_pipeline_match_padded(lasr_b200):
         torch.cuda.synchronize()
         assert torch.equal(df, ref) and torch.equal(dl, rlen)
         assert fe.h2d_bytes < host.numel() * 4
+        # same shapes, utterances permuted: the host buffer is reused and only rows that can differ are re-sent
+        perm = np.array([4, 1, 0, 3, 2, 5])
+        host2 = host[torch.from_numpy(perm)].contiguous().pin_memory()
+        hf2, hl2 = fe.extract_host(host2, n[perm], group_bytes=200000)
+        torch.cuda.synchronize()
+        assert torch.equal(hf2, ref.cpu()[torch.from_numpy(perm)]) and torch.equal(hl2, rlen.cpu()[torch.from_numpy(perm)])
+        assert fe.d2h_bytes < ref.numel() * 4 + 64
 
 
 def test_batch_composition_invariance(lasr_b200):
