@@ -81,6 +81,10 @@ int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host
  * fused into b200fe_fbank_fused through its `d_peak` argument. */
 int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride, const long long* d_wav_offsets,
                        const long long* d_nsamp, int batch, float* d_peak, void* stream);
+/* Same for int16 PCM input: d_peak[b] = max |s16| / 2^15, the value max |x| takes after the reader's
+ * int16 -> float conversion (R/lasr/data/reader.py:24, soundfile). */
+int b200fe_peak_absmax_i16(const b200fe_plan* plan, const short* d_wav, long long wav_stride, const long long* d_wav_offsets,
+                           const long long* d_nsamp, int batch, float* d_peak, void* stream);
 
 /* One fused launch over a zero-padded batch of waveforms.
  * Replaces WavToKaldiFbank (R/lasr/data/datatrans.py:42-104 -> TA:514-645) for every
@@ -135,6 +139,10 @@ typedef struct b200fe_fbank_args {
      * torch.manual_seed as the reference ("seeded identically"). */
     unsigned long long dither_seed;
     const float* d_dither_noise;
+    /* Waveform element type: 0 = float32 in [-1, 1) (what the reader returns), 1 = int16 PCM (what the file
+     * holds; d_wav then points to int16 and strides / offsets count int16 samples, offsets multiples of 8
+     * for the TMA loader).  (float)s16 == float32 sample * 2^15 exactly, so both give identical features. */
+    int wav_dtype;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);
@@ -142,8 +150,8 @@ int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, v
 /* Host -> device staging of a zero-padded HOST batch (what batch_list builds, dataset.py:8-22) into the
  * packed device layout: only the valid samples of every utterance cross PCIe (one cudaMemcpyAsync per
  * utterance on `stream`; h_wav should be pinned).  h_offsets[u] = destination offset (elements). */
-int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
-                      int batch, float* d_packed, void* stream);
+int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
+                      int batch, void* d_packed, int elem_bytes /* 4 float32, 2 int16 */, void* stream);
 
 /* Device -> host copy of the first h_rows[u] rows of every utterance of a padded [batch][utt_rows][row_elems]
  * feature tensor into a host tensor of the same layout (one cudaMemcpyAsync per utterance).  The caller

@@ -27,7 +27,7 @@ class FbankArgs(C.Structure):
         ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
         ("d_tile_table", C.c_void_p), ("n_tiles", C.c_int), ("d_work_counter", C.c_void_p),
         ("d_wav_offsets", C.c_void_p), ("offsets_aligned", C.c_int),
-        ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p),
+        ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p), ("wav_dtype", C.c_int),
     ]
 
 
@@ -43,7 +43,7 @@ class PostArgs(C.Structure):
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table",
-    "b200fe_peak_absmax", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_postpass", "b200fe_cmvn_from_stats",
+    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_postpass", "b200fe_cmvn_from_stats",
 ]
 
 _lib = None
@@ -89,9 +89,11 @@ def load(build_if_missing=True):
     lib.b200fe_build_tile_table.restype = C.c_int
     lib.b200fe_peak_absmax.argtypes = [C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.b200fe_peak_absmax.restype = C.c_int
+    lib.b200fe_peak_absmax_i16.argtypes = lib.b200fe_peak_absmax.argtypes
+    lib.b200fe_peak_absmax_i16.restype = C.c_int
     lib.b200fe_fbank_fused.argtypes = [C.c_void_p, C.POINTER(FbankArgs), C.c_void_p]
     lib.b200fe_fbank_fused.restype = C.c_int
-    lib.b200fe_h2d_ragged.argtypes = [C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.b200fe_h2d_ragged.argtypes = [C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.b200fe_h2d_ragged.restype = C.c_int
     lib.b200fe_d2h_ragged.argtypes = [C.c_void_p, c_ll, c_ll, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.b200fe_d2h_ragged.restype = C.c_int

@@ -67,6 +67,29 @@ __global__ void __launch_bounds__(256) zero_pad_kernel(float* __restrict__ out, 
     }
 }
 
+// int16 PCM abs-max: peak = max |s16| / 2^15 (what max |x| is after soundfile's conversion)
+__global__ void __launch_bounds__(256) absmax_i16_kernel(const short* __restrict__ wav, long long stride, const long long* __restrict__ offsets,
+                                                         const long long* __restrict__ nsamp, float* __restrict__ peak)
+{
+    const int utt = blockIdx.y;
+    const long long n = nsamp[utt];
+    const short* x = wav + (offsets ? offsets[utt] : (long long)utt * stride);
+    const long long chunk = 256LL * 4 * 8;
+    const long long i0 = (long long)blockIdx.x * chunk;
+    if (i0 >= n) return;
+    int m = 0;
+    for (long long i = i0 + threadIdx.x; i < n && i < i0 + chunk; i += 256) { const int v = x[i]; m = max(m, v < 0 ? -v : v); }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ int sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = max(m, sm[w]);
+        atomicMax(reinterpret_cast<unsigned int*>(peak + utt), __float_as_uint((float)m * 3.0517578125e-05f));
+    }
+}
+
 struct PostArgs {
     float* feats;
     const long long* nsamp;

@@ -66,8 +66,15 @@ struct b200fe_plan {
     int ctas_per_sm;
 };
 
-static const void* plan_kernel(const b200fe_plan* p, bool peak)
+static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false)
 {
+    if (i16) {   // int16 PCM input, 512-point family
+        if (p->nload == 13) {
+            if (p->static_mel) return peak ? (const void*)fbank_fused_kernel<13, true, true, false, true> : (const void*)fbank_fused_kernel<13, true, false, false, true>;
+            return peak ? (const void*)fbank_fused_kernel<13, false, true, false, true> : (const void*)fbank_fused_kernel<13, false, false, false, true>;
+        }
+        return peak ? (const void*)fbank_fused_kernel<16, false, true, false, true> : (const void*)fbank_fused_kernel<16, false, false, false, true>;
+    }
     if (p->nfft == 256) {   // 8 kHz family: two real frames per complex FFT
         if (p->nload == 13) return peak ? (const void*)fbank_fused_kernel<13, false, true, true> : (const void*)fbank_fused_kernel<13, false, false, true>;
         return peak ? (const void*)fbank_fused_kernel<16, false, true, true> : (const void*)fbank_fused_kernel<16, false, false, true>;
@@ -261,6 +268,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     const void* kfn = plan_kernel(p, false);
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (p->nfft == 512) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    }
     if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kThreads, p->smem_bytes);
@@ -312,6 +323,19 @@ extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* ns
     return (int)n;
 }
 
+extern "C" int b200fe_peak_absmax_i16(const b200fe_plan* plan, const short* d_wav, long long wav_stride, const long long* d_wav_offsets,
+                                      const long long* d_nsamp, int batch, float* d_peak, void* stream)
+{
+    if (!plan || !d_wav || !d_nsamp || !d_peak || batch <= 0 || wav_stride <= 0) return fail(B200FE_EINVAL, "peak_absmax_i16: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(d_peak, 0, sizeof(float) * batch, st));
+    const long long chunk = 256LL * 4 * 8;
+    dim3 grid((unsigned)((wav_stride + chunk - 1) / chunk), (unsigned)batch);
+    absmax_i16_kernel<<<grid, 256, 0, st>>>(d_wav, wav_stride, d_wav_offsets, d_nsamp, d_peak);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, long long wav_stride, const long long* d_wav_offsets,
                                   const long long* d_nsamp, int batch, float* d_peak, void* stream)
 {
@@ -325,16 +349,16 @@ extern "C" int b200fe_peak_absmax(const b200fe_plan* plan, const float* d_wav, l
     return B200FE_OK;
 }
 
-extern "C" int b200fe_h2d_ragged(const float* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
-                                 int batch, float* d_packed, void* stream)
+extern "C" int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_nsamp, const long long* h_offsets,
+                                 int batch, void* d_packed, int elem_bytes, void* stream)
 {
-    if (!h_wav || !h_nsamp || !h_offsets || !d_packed || batch < 0) return fail(B200FE_EINVAL, "h2d_ragged: bad argument");
+    if (!h_wav || !h_nsamp || !h_offsets || !d_packed || batch < 0 || (elem_bytes != 2 && elem_bytes != 4)) return fail(B200FE_EINVAL, "h2d_ragged: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    // merge utterances whose source and destination ranges are both contiguous into one copy
     for (int u = 0; u < batch; ++u) {
         if (h_nsamp[u] <= 0) continue;
-        CUDA_TRY(cudaMemcpyAsync(d_packed + h_offsets[u], h_wav + (long long)u * h_stride, sizeof(float) * (size_t)h_nsamp[u],
-                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(d_packed) + h_offsets[u] * elem_bytes,
+                                 static_cast<const char*>(h_wav) + (long long)u * h_stride * elem_bytes,
+                                 (size_t)elem_bytes * (size_t)h_nsamp[u], cudaMemcpyHostToDevice, st));
     }
     return B200FE_OK;
 }
@@ -376,7 +400,12 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.log_floor = 1.1920928955078125e-07f;   // TA:21-22
     a.in_scale = (float)std::ldexp(1.0, p->o.audio_bit - 1);
     a.dither = p->o.dither; a.dither_seed = g->dither_seed; a.dither_noise = g->d_dither_noise;
-    a.window = g->d_peak ? p->d_window_plain : p->d_window_scaled;
+    const bool i16 = g->wav_dtype == 1;
+    if (g->wav_dtype != 0 && g->wav_dtype != 1) return fail(B200FE_EINVAL, "fbank_fused: wav_dtype must be 0 (float32) or 1 (int16)");
+    if (i16 && p->nfft != 512) return fail(B200FE_EINVAL, "fbank_fused: int16 input is implemented for the 512-point family only");
+    if (i16 && p->o.dither != 0.f) return fail(B200FE_EINVAL, "fbank_fused: dither with int16 input is not implemented");
+    // int16 samples already carry the 2^(bits-1) scale
+    a.window = (g->d_peak || i16) ? p->d_window_plain : p->d_window_scaled;
     a.twiddle = p->d_twiddle; a.split_tw = p->d_split_tw;
     a.cm_mean = g->d_cmvn_mean; a.cm_istd = g->d_cmvn_istd; a.cm_stride = g->cmvn_stride;
     a.masks = (g->n_freq_masks + g->n_time_masks) > 0 ? g->d_masks : nullptr;
@@ -389,7 +418,8 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     if (ntiles > 0x7fffffffLL) return fail(B200FE_EINVAL, "fbank_fused: too many tiles");
     a.ntiles = (int)ntiles;
     // packed input: the caller promises 4-sample aligned offsets through offsets_aligned
-    a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 && (g->d_wav_offsets ? g->offsets_aligned != 0 : (g->wav_stride % 4) == 0)) ? 1 : 0;
+    a.use_tma = ((reinterpret_cast<uintptr_t>(g->d_wav) & 15) == 0 &&
+                 (g->d_wav_offsets ? g->offsets_aligned != 0 : (g->wav_stride % (i16 ? 8 : 4)) == 0)) ? 1 : 0;
     a.tile_floats = p->tile_floats;
     memcpy(a.seg_start, p->seg_start, sizeof a.seg_start);
     memcpy(a.grp_begin, p->grp_begin, sizeof a.grp_begin);
@@ -410,7 +440,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     }
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm));
     void* kargs[] = {(void*)&a};
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
     return B200FE_OK;
 }
 

@@ -44,7 +44,7 @@ constexpr int kStages = 2;
 
 struct FbankArgs {
     // input
-    const float* wav;            // [B][wav_stride] fp32 waveform
+    const float* wav;            // [B][wav_stride] fp32 waveform, or int16 PCM when the kernel is instantiated with kI16
     long long wav_stride;
     const long long* wav_offsets; // optional [B]: utterance u starts at wav + wav_offsets[u] (packed / ragged input)
     const long long* nsamp;      // [B] valid samples
@@ -241,6 +241,46 @@ __device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* 
     for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
 }
 
+// int16 PCM variant of load_frame_single: the tile holds int16 samples; (float)s16 equals the float path's
+// x * 2^15 exactly, so the UNSCALED window table is used and the results are bit-identical.
+template <int NLOAD, bool kPeak>
+__device__ __forceinline__ void load_frame_single_i16(float2 (&v)[16], const short* __restrict__ xf, const float2* __restrict__ wl,
+                                                      const FrameCtx& c, int l)
+{
+    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) {
+        const int j = 2 * (l + 16 * n2);
+        const int w = *reinterpret_cast<const int*>(xf + 32 * n2);              // samples j (low half) and j + 1 (high half)
+        float2 xr = make_float2((float)(short)(w & 0xffff), (float)(w >> 16));
+        float xp = (float)((n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1]);   // replicate pad at the frame start (TA:195)
+        if (kPeak) {
+            // reference: soundfile's s16 / 2^15, then x / (max + 1e-9), rounded to fp32, times 2^15
+            xr.x = peak_div(xr.x * 3.0517578125e-05f, c.pmax, c.prcp) * c.pscale;
+            xr.y = peak_div(xr.y * 3.0517578125e-05f, c.pmax, c.prcp) * c.pscale;
+            xp = peak_div(xp * 3.0517578125e-05f, c.pmax, c.prcp) * c.pscale;
+        }
+        if (NLOAD == 16 || n2 == NLOAD - 1) {
+            if (j >= c.win) { xr.x = 0.f; xp = 0.f; }
+            if (j + 1 >= c.win) xr.y = 0.f;
+        }
+        acc2 = add2(acc2, xr);
+        v[n2].x = fmaf(-c.c_pre, xp, xr.x);
+        v[n2].y = fmaf(-c.c_pre, xr.x, xr.y);
+    }
+    float sum = acc2.x + acc2.y;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float ncdc = -(sum * c.inv_win * c.dc_coef);
+    float2 wv[NLOAD];
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) { wv[n2] = wl[16 * n2]; v[n2] = mul2(v[n2], wv[n2]); }
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) v[n2] = fma2(bc(ncdc), wv[n2], v[n2]);
+#pragma unroll
+    for (int n2 = NLOAD; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+}
+
 // 256-point family: two consecutive real frames a (at xa) and b (at xb) -> z[n] = ya[n] + j yb[n].
 template <int NLOAD, bool kPeak, bool kDither>
 __device__ __forceinline__ void load_frame_dual(float2 (&v)[16], const float* __restrict__ xa, const float* __restrict__ xb,
@@ -336,7 +376,8 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 // z[n] = ya[n] + j yb[n]; after the same 256-point complex FFT, 2 Xa[k] = Z[k] + conj Z[256-k] and
 // 2j Xb[k] = Z[k] - conj Z[256-k], so the conjugate-pair exchange yields both power spectra without any
 // split twiddle (k = 0..127; the Nyquist bin has zero mel weight, TA:627).
-template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual>
+// kI16: the waveform is int16 PCM (2 bytes per sample over PCIe / HBM); 512-point family only.
+template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false>
 __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -420,8 +461,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
         if (g.nvalid <= 0) return;
         const int nsmp = (g.nvalid - 1) * a.shift + a.win;
-        const uint32_t bytes = (uint32_t)((nsmp * 4 + 15) & ~15);
-        const float* src = a.wav + (a.wav_offsets ? __ldg(a.wav_offsets + g.utt) : (long long)g.utt * a.wav_stride) + (long long)g.f0 * a.shift;
+        const int esz = kI16 ? 2 : 4;
+        const uint32_t bytes = (uint32_t)((nsmp * esz + 15) & ~15);
+        const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + g.utt) : (long long)g.utt * a.wav_stride) + (long long)g.f0 * a.shift;
+        const char* src = reinterpret_cast<const char*>(a.wav) + eoff * esz;
         mbar_expect_tx(&bars[stage], bytes);
         tma_load_1d(smem + L.tile_off[stage], src, bytes, &bars[stage]);
     };
@@ -462,8 +505,15 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         } else if (nvalid > 0) {
             // generic path (unaligned base / stride): cooperative coalesced loads
             const int nsmp = (nvalid - 1) * a.shift + a.win;
-            const float* src = a.wav + (a.wav_offsets ? __ldg(a.wav_offsets + utt) : (long long)utt * a.wav_stride) + (long long)f0 * a.shift;
-            for (int i = tid; i < nsmp; i += kThreads) xs[i] = __ldg(src + i);
+            const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + utt) : (long long)utt * a.wav_stride) + (long long)f0 * a.shift;
+            if (kI16) {
+                const short* src = reinterpret_cast<const short*>(a.wav) + eoff;
+                short* xd = reinterpret_cast<short*>(xs);
+                for (int i = tid; i < nsmp; i += kThreads) xd[i] = __ldg(src + i);
+            } else {
+                const float* src = a.wav + eoff;
+                for (int i = tid; i < nsmp; i += kThreads) xs[i] = __ldg(src + i);
+            }
             __syncthreads();
         }
 
@@ -520,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                         fc.noise_b = a.dither_noise ? a.dither_noise + row + a.win : nullptr;
                     }
                     if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
+                    else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + fl * a.shift + 2 * l, wl, fc, l);
                     else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
                     fft256_halfwarp(v, tw, xbuf, l);
                     float2 rc[8];

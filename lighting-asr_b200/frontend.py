@@ -209,16 +209,18 @@ class GpuFbankFrontend(torch.nn.Module):
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
         packed = wav_offsets is not None
-        if wav.dtype != torch.float32 or wav.dim() != (1 if packed else 2):
-            raise ValueError("wav must be float32 (B, Nmax), or 1-D with wav_offsets")
+        if wav.dtype not in (torch.float32, torch.int16) or wav.dim() != (1 if packed else 2):
+            raise ValueError("wav must be float32 or int16 PCM, (B, Nmax) or 1-D with wav_offsets")
+        i16 = wav.dtype == torch.int16
+        esz = 2 if i16 else 4
         if not packed and wav.stride(1) != 1:
             wav = wav.contiguous()
         dev = wav.device
         B = len(wav_len) if packed else wav.shape[0]
         if packed:
             off_host = np.ascontiguousarray(wav_offsets, dtype=np.int64)
-            if (off_host % 4 != 0).any():
-                raise ValueError("wav_offsets must be multiples of 4 samples")
+            if (off_host % (16 // esz) != 0).any():
+                raise ValueError("wav_offsets must be multiples of 16 bytes")
             off_dev = torch.from_numpy(off_host).to(dev, non_blocking=True)
             row_stride = int(wav.numel())
             row_elems = int(wav.numel())
@@ -258,8 +260,9 @@ class GpuFbankFrontend(torch.nn.Module):
         peak = None
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
-            _lib.check(lib.b200fe_peak_absmax(plan.handle, _ptr(wav), row_stride if not packed else int(len_host.max()) if len_host is not None else row_stride,
-                                              _ptr(off_dev), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
+            absmax = lib.b200fe_peak_absmax_i16 if i16 else lib.b200fe_peak_absmax
+            _lib.check(absmax(plan.handle, _ptr(wav), row_stride if not packed else int(len_host.max()) if len_host is not None else row_stride,
+                              _ptr(off_dev), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
             self.launch_count += 2          # memset + abs-max kernel
 
         n_f = n_t = 0
@@ -307,13 +310,14 @@ class GpuFbankFrontend(torch.nn.Module):
         for b0 in range(0, B, group):
             nb = min(group, B - b0)
             a = _lib.FbankArgs()
+            a.wav_dtype = 1 if i16 else 0
             if packed:
                 a.d_wav = _ptr(wav)
                 a.wav_stride = row_stride
                 a.d_wav_offsets = off(off_dev, b0, 8)
                 a.offsets_aligned = 1
             else:
-                a.d_wav = off(wav, b0, wav.stride(0) * 4)
+                a.d_wav = off(wav, b0, wav.stride(0) * esz)
                 a.wav_stride = wav.stride(0)
             a.d_nsamp = off(len_dev, b0, 8)
             a.batch = nb
@@ -398,21 +402,23 @@ class GpuFbankFrontend(torch.nn.Module):
         case where the encoder consumes them in place)."""
         dev = torch.device(device)
         B, Nmax = wav_host.shape
-        if wav_host.dtype != torch.float32 or wav_host.stride(1) != 1:
-            raise ValueError("wav_host must be a float32 tensor with contiguous rows")
+        if wav_host.dtype not in (torch.float32, torch.int16) or wav_host.stride(1) != 1:
+            raise ValueError("wav_host must be a float32 or int16 tensor with contiguous rows")
+        esz = wav_host.element_size()
+        al = 16 // esz                                    # utterance starts are 16-byte aligned in the packed buffer
         len_host = np.ascontiguousarray(np.asarray(wav_len, dtype=np.int64).reshape(-1))
         T_host, win = self.frame_counts(len_host)
         if (len_host < win).any():
             raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
         Tmax, D = int(T_host.max()), self.num_mel_bins
         offs = np.zeros(B, dtype=np.int64)
-        np.cumsum((len_host[:-1] + 3) // 4 * 4, out=offs[1:])
-        total = int(offs[-1] + (len_host[-1] + 3) // 4 * 4)
-        key = (B, Nmax, Tmax, total, dev.index or 0)
+        np.cumsum((len_host[:-1] + al - 1) // al * al, out=offs[1:])
+        total = int(offs[-1] + (len_host[-1] + al - 1) // al * al)
+        key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype)
         c = self._host_cache.get(key)
         if c is None:
             self._host_cache.clear()
-            c = dict(wav=torch.zeros((total + 64,), dtype=torch.float32, device=dev),
+            c = dict(wav=torch.zeros((total + 64,), dtype=wav_host.dtype, device=dev),
                      feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
                      flen=torch.empty((B,), dtype=torch.int64, device=dev),
                      hfeats=torch.zeros((B, Tmax, D), dtype=torch.float32).pin_memory(),
@@ -431,7 +437,7 @@ class GpuFbankFrontend(torch.nn.Module):
         bounds = [0]
         acc = 0
         for b in range(B):
-            acc += int(len_host[b]) * 4
+            acc += int(len_host[b]) * esz
             if acc >= group_bytes:
                 bounds.append(b + 1)
                 acc = 0
@@ -439,12 +445,12 @@ class GpuFbankFrontend(torch.nn.Module):
             bounds.append(B)
         self.h2d_bytes = self.d2h_bytes = 0
         for b0, b1 in zip(bounds[:-1], bounds[1:]):
-            _lib.check(lib.b200fe_h2d_ragged(C.c_void_p(wav_host.data_ptr() + b0 * wav_host.stride(0) * 4), wav_host.stride(0),
+            _lib.check(lib.b200fe_h2d_ragged(C.c_void_p(wav_host.data_ptr() + b0 * wav_host.stride(0) * esz), wav_host.stride(0),
                                              C.c_void_p(len_host.ctypes.data + b0 * 8), C.c_void_p(offs.ctypes.data + b0 * 8), b1 - b0,
-                                             _ptr(c["wav"]), C.c_void_p(s_in.cuda_stream)), "b200fe_h2d_ragged")
+                                             _ptr(c["wav"]), esz, C.c_void_p(s_in.cuda_stream)), "b200fe_h2d_ragged")
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
-            self.h2d_bytes += int(len_host[b0:b1].sum()) * 4 + (b1 - b0) * 16
+            self.h2d_bytes += int(len_host[b0:b1].sum()) * esz + (b1 - b0) * 16
             main.wait_event(ev_in)
             self.forward(c["wav"], len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1],
                          wav_offsets=offs[b0:b1])

@@ -229,3 +229,26 @@ def test_dither_seeded_identically(lasr_b200):
     # per-frame-independent noise differs from a shared waveform only through the frame overlap; the
     # per-bin average log energy over ~1000 frames agrees to a few percent
     assert np.allclose(a[0].cpu().numpy().mean(0), ref.mean(0), atol=0.15)
+
+
+def test_int16_pcm_input_is_bit_identical(lasr_b200):
+    """int16 PCM ingest (what the audio file holds): (float)s16 == float32 sample * 2^15 exactly, so the
+    features equal those of the float32 waveform soundfile would hand to the reference (reader.py:24)."""
+    rng = np.random.default_rng(12)
+    lens = [16000, 401, 70001, 33333]
+    pcm = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
+    flt = [p.astype(np.float32) / np.float32(32768.0) for p in pcm]
+    wav_f, n = _pad_batch(flt, "cuda:0", align=8)
+    wav_i = torch.zeros(wav_f.shape, dtype=torch.int16)
+    for i, p in enumerate(pcm):
+        wav_i[i, : len(p)] = torch.from_numpy(p)
+    for kw in ({}, {"peak_norm": True}, {"cmvn": "utt_meanvar"}, {"num_mel_bins": 40}):
+        fe = lasr_b200.GpuFbankFrontend(**kw)
+        ref, rlen = fe(wav_f, n)
+        got, glen = fe(wav_i.cuda(), n)
+        assert torch.equal(got, ref) and torch.equal(glen, rlen), kw
+        hf, hl = fe.extract_host(wav_i.pin_memory(), n, group_bytes=100000)
+        torch.cuda.synchronize()
+        assert torch.equal(hf, ref.cpu()) and torch.equal(hl, rlen.cpu()), kw
+    ta = _ta_fbank(flt[0])
+    assert tol_violations(lasr_b200.GpuFbankFrontend()(wav_i.cuda()[:1], n[:1])[0][0].cpu().numpy(), ta) <= 2
