@@ -40,7 +40,7 @@ constexpr int kMaxMel = 128;
 constexpr int kMaxTimeMasks = 4;
 constexpr int kMaxFreqMasks = 4;
 constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
-constexpr int kStages = 2;
+constexpr int kStages = 1;         // one tile buffer: the next tile's TMA is issued right after the phase-A barrier
 
 struct FbankArgs {
     // input
@@ -109,14 +109,12 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     SmemLayout L;
     int o = 0;
     for (int s = 0; s < kStages; ++s) { L.tile_off[s] = o; o += tile_floats * 4; }
-    L.xbuf_off = o;
-    int xbytes = kHalfWarps * 16 * kXRow * 8;
-    int obytes = kFT * (nmel + 1) * 4;           // staging aliases the transposition buffers (dead after phase A)
-    o += (xbytes > obytes ? xbytes : obytes);
-    L.outs_off = L.xbuf_off;
+    L.xbuf_off = o; o += kHalfWarps * 16 * kXRow * 8;
+    // the staging tile is NOT aliased with anything: phase C of tile i overlaps phase A of tile i+1
+    L.outs_off = o; o += ((kFT * (nmel + 1) * 4 + 15) & ~15);
     L.pt_off = o; o += 64 * kPTStride * 16;
     L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
-    L.bar_off = o; o += 8 * kStages + 32;   // mbarriers + 2 tile descriptors (int4)
+    L.bar_off = o; o += 16 + 32;            // mbarrier slots (16 B) + 2 tile descriptors (int4)
     L.total = o;
     return L;
 }
@@ -440,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     // tile table -> sample count) never sit on any warp's critical path.
     struct Desc { int id, utt, f0, T; };
     const bool dyn = a.tile_table != nullptr;
-    int4* s_desc = reinterpret_cast<int4*>(bars + kStages);
+    int4* s_desc = reinterpret_cast<int4*>(bars + 2);          // 16-byte aligned: two 8-byte slots are reserved for mbarriers
     auto resolve = [&](int id) -> Desc {               // thread 0 only
         Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
         if (id < a.ntiles) {
@@ -485,11 +483,11 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
     if (a.use_tma && tid == 0 && cur.id < a.ntiles) issue_load(g, 0);
 
     for (; cur.id < a.ntiles; ++it) {
-        const int stage = it % kStages;
         const int utt = g.utt, f0 = g.f0, nvalid = g.nvalid, nrows = g.nrows;
-        float* xs = reinterpret_cast<float*>(smem + L.tile_off[stage]);
+        float* xs = reinterpret_cast<float*>(smem + L.tile_off[0]);
         const TileGeom gn = geom(nxt);
         Desc fut; fut.id = a.ntiles; fut.utt = 0; fut.f0 = 0; fut.T = 0;
+        int4 nxt_desc = make_int4(a.ntiles, 0, 0, 0);
         if (tid == 0) {
             // descriptor of the tile after next: its loads complete while this tile is being computed
             const int id2 = dyn ? atomicAdd(a.work_counter, 1) : nxt.id + (int)gridDim.x;
@@ -497,11 +495,11 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         }
 
         if (a.use_tma) {
-            // prefetch the next tile of this CTA into the other stage (its previous contents were
-            // consumed before the phase-A barrier of the previous iteration)
-            if (tid == 0 && nxt.id < a.ntiles) issue_load(gn, (it + 1) % kStages);
-            // a stage's mbarrier phase advances only for tiles that actually carried a load
-            if (nvalid > 0) { mbar_wait(&bars[stage], (phase_bits >> stage) & 1u); phase_bits ^= (1u << stage); }
+            // the tile buffer has been free since the last phase-A barrier: when the current tile carries no
+            // frames (padded grid) the next tile's load can go out right away, otherwise after this tile's phase A
+            if (nvalid <= 0 && tid == 0 && nxt.id < a.ntiles) issue_load(gn, 0);
+            // the mbarrier phase advances only for tiles that actually carried a load
+            if (nvalid > 0) { mbar_wait(&bars[0], phase_bits & 1u); phase_bits ^= 1u; }
         } else if (nvalid > 0) {
             // generic path (unaligned base / stride): cooperative coalesced loads
             const int nsmp = (nvalid - 1) * a.shift + a.win;
@@ -518,28 +516,6 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
         }
 
         if (nvalid > 0) {
-            // per-tile epilogue tables (visible after the phase-A barrier)
-            if (cm_per_utt && tid < nmel) {
-                s_mean[tid] = __ldg(a.cm_mean + (long long)utt * a.cm_stride + tid);
-                s_istd[tid] = __ldg(a.cm_istd + (long long)utt * a.cm_stride + tid);
-            }
-            if (zmask && tid < kMaxMel) {
-                const int* mk = a.masks + (long long)utt * nmask * 2;
-                bool m = false;
-#pragma unroll 1
-                for (int i = 0; i < a.n_fmask; ++i) m |= (tid >= __ldg(mk + 2 * i) && tid < __ldg(mk + 2 * i + 1));
-                const unsigned bal = __ballot_sync(0xffffffffu, m);
-                if (lane == 0) s_cmask[warp] = bal;
-            }
-            if (zmask && warp == 4) {
-                const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
-                bool m = false;
-#pragma unroll 1
-                for (int i = 0; i < a.n_tmask; ++i) m |= (f0 + lane >= __ldg(mk + 2 * i) && f0 + lane < __ldg(mk + 2 * i + 1));
-                const unsigned bal = __ballot_sync(0xffffffffu, m);
-                if (lane == 0) s_cmask[4] = bal;
-            }
-
             // ================= phase A: half-warp per frame (pair of frames in dual-256 mode) =================
             FrameCtx fc;
             fc.c_pre = c_pre; fc.inv_win = inv_win; fc.dc_coef = dc_coef; fc.win = a.win;
@@ -615,7 +591,33 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     }
                 }
             }
-            __syncthreads();   // PT complete; tile stage and transposition buffers are free
+            __syncthreads();   // B1: PT complete; the tile buffer is free; every warp has finished phase C of the previous tile
+            if (tid == 0) {
+                if (a.use_tma && nxt.id < a.ntiles) issue_load(gn, 0);
+                s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
+            }
+            // per-tile epilogue tables for phase C (written here: no warp is still reading the previous tile's)
+            if (cm_per_utt && tid < nmel) {
+                s_mean[tid] = __ldg(a.cm_mean + (long long)utt * a.cm_stride + tid);
+                s_istd[tid] = __ldg(a.cm_istd + (long long)utt * a.cm_stride + tid);
+            }
+            if (zmask && tid < kMaxMel) {
+                const int* mk = a.masks + (long long)utt * nmask * 2;
+                bool m = false;
+#pragma unroll 1
+                for (int i = 0; i < a.n_fmask; ++i) m |= (tid >= __ldg(mk + 2 * i) && tid < __ldg(mk + 2 * i + 1));
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) s_cmask[warp] = bal;
+            }
+            if (zmask && warp == 4) {
+                const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
+                bool m = false;
+#pragma unroll 1
+                for (int i = 0; i < a.n_tmask; ++i) m |= (f0 + lane >= __ldg(mk + 2 * i) && f0 + lane < __ldg(mk + 2 * i + 1));
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) s_cmask[4] = bal;
+            }
+
 
             // ================= phase B: warp = mel-bin group, lane = frame =================
             {
@@ -655,7 +657,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                     }
                 }
             }
-            __syncthreads();   // staging complete
+            __syncthreads();   // B2: staging complete; PT free for the next tile's phase A
+            nxt_desc = s_desc[it & 1];
         }
 
         // ================= phase C: epilogue + copy-out, zero padding, statistics =================
@@ -758,13 +761,17 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             }
         }
         // the staging area aliases the transposition buffers that the next phase A overwrites
-        // Publish the descriptor resolved above into the slot of the tile that just finished (all threads copied
-        // it before the previous closing barrier); the closing barrier also protects the staging area.
-        if (tid == 0) s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
-        __syncthreads();
+        // No closing barrier: a warp that finishes phase C goes straight to the next tile's phase A.  (A tile
+        // without frames has no B1 / B2, so the descriptor exchange gets its own barrier.)
+        if (nvalid <= 0) {
+            if (tid == 0) s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
+            __syncthreads();
+            nxt_desc = s_desc[it & 1];
+            __syncthreads();
+        }
         cur = nxt;
         g = gn;
-        { const int4 v = s_desc[it & 1]; nxt = Desc{v.x, v.y, v.z, v.w}; }
+        nxt = Desc{nxt_desc.x, nxt_desc.y, nxt_desc.z, nxt_desc.w};
     }
 }
 
