@@ -1,0 +1,63 @@
+"""GPU: the reference-facing plug-in points: registry transforms and the batched collate."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kaldi_fbank, lasr_frontend
+
+pytestmark = pytest.mark.gpu
+
+
+class Register(dict):
+    """Behavioural stand-in for lasr/utils/register.py:1-41 (register(name) decorator, override with a
+    warning, lookup by key) -- /root/reference is not present on the GPU box."""
+
+    def register(self, target):
+        def add(key, value):
+            if not callable(value):
+                raise Exception("register object must be callable")
+            if key in self:
+                print("warning: %s has been registered before, so we will overriden it" % key)
+            self[key] = value
+            return value
+        return (lambda x: add(target, x)) if not callable(target) else add(target.__name__, target)
+
+
+def test_registry_override_and_fused_chain(lasr_b200, capsys):
+    reg = Register()
+    reg.register("fbank:80")(lambda w: None)                       # the reference's own CPU transform
+    table = lasr_b200.lasr_plugin.install(reg, device="cuda:0")
+    assert "has been registered before" in capsys.readouterr().out   # override semantics of Register.register
+    assert set(table) <= set(reg.keys())
+    rng = np.random.default_rng(3)
+    wav = rng.uniform(-0.5, 0.5, 24001)                              # float64, as soundfile.read returns
+    out = reg["fbank:80"](wav)                                      # exactly one positional argument (dataset.py:196-197)
+    ref = lasr_frontend.wav_to_kaldi_fbank(wav, use_torchaudio=True)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == ref.shape
+    assert out.shape[0] == kaldi_fbank.num_frames(24001)             # wav_len = wav_array.shape[0] (dataset.py:198)
+    assert int((np.abs(out - ref) > 1e-5 + 1e-4 * np.abs(ref)).sum()) <= 1
+    fused = reg["b200:norm+fbank:80"](wav)                          # replaces audio_trans: [norm, "fbank:80"]
+    ref2 = lasr_frontend.wav_to_kaldi_fbank(lasr_frontend.voice_norm(wav), use_torchaudio=True)
+    assert int((np.abs(fused - ref2) > 1e-5 + 1e-4 * np.abs(ref2)).sum()) <= 1
+    t = lasr_b200.lasr_plugin.GpuTransform("cuda:0", return_tensor=True)(wav)   # ASRProcess path: torch.as_tensor(feats)
+    assert t.is_cuda and torch.equal(torch.as_tensor(t).cpu(), torch.from_numpy(out))
+    with pytest.raises(ValueError):
+        reg["fbank:80"](np.zeros((100, 2)))
+    with pytest.raises(AssertionError):
+        reg["fbank:80"](np.zeros(399))                               # torchaudio asserts on short input (TA:142)
+
+
+def test_batched_collate_matches_reference_batch_dict(lasr_b200):
+    rng = np.random.default_rng(4)
+    wavs = [rng.uniform(-0.5, 0.5, n) for n in (16000, 4800, 32001)]
+    for to_host in (False, True):
+        col = lasr_b200.lasr_plugin.B200Collate("cuda:0", to_host=to_host)
+        batch = col(wavs)
+        feats, flen = batch["wav_array"], batch["wav_len"]
+        assert feats.is_cuda != to_host and feats.dtype == torch.float32 and flen.dtype == torch.int64
+        ref = lasr_frontend.batch_list([lasr_frontend.wav_to_kaldi_fbank(w, use_torchaudio=True) for w in wavs], pad_value=0)
+        assert tuple(feats.shape) == ref.shape
+        assert flen.cpu().tolist() == [kaldi_fbank.num_frames(len(w)) for w in wavs]
+        g = feats.cpu().numpy()
+        assert int((np.abs(g - ref) > 1e-5 + 1e-4 * np.abs(ref)).sum()) <= 2
+        assert np.array_equal(g == 0, ref == 0)                      # identical zero padding
