@@ -355,12 +355,13 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 
 #define B200FE_MEL_DEVICE_CODE
 #define MGROUP_BEGIN(w) __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, float* __restrict__ orow) { \
-        float au = 0.f, ad = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
+        float au = 0.f, ad = 0.f, au1 = 0.f, ad1 = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
 #define MK(k, wu, wd) { if (((k) >> 2) != cur) { cur = (k) >> 2; p4 = pcol[cur * kPTStride]; } \
         const float p = ((k) & 3) == 0 ? p4.x : ((k) & 3) == 1 ? p4.y : ((k) & 3) == 2 ? p4.z : p4.w; \
-        if ((wu) != 0.f) au = fmaf((wu), p, au); if ((wd) != 0.f) ad = fmaf((wd), p, ad); }
-#define MEND0() { up_prev = au; au = 0.f; ad = 0.f; }
-#define MEND(j) { emit_bin(orow, (j), up_prev + ad); up_prev = au; au = 0.f; ad = 0.f; }
+        if ((k) & 1) { if ((wu) != 0.f) au1 = fmaf((wu), p, au1); if ((wd) != 0.f) ad1 = fmaf((wd), p, ad1); } \
+        else         { if ((wu) != 0.f) au = fmaf((wu), p, au);   if ((wd) != 0.f) ad = fmaf((wd), p, ad); } }
+#define MEND0() { up_prev = au + au1; au = 0.f; ad = 0.f; au1 = 0.f; ad1 = 0.f; }
+#define MEND(j) { emit_bin(orow, (j), up_prev + (ad + ad1)); up_prev = au + au1; au = 0.f; ad = 0.f; au1 = 0.f; ad1 = 0.f; }
 #define MGROUP_END(w) }
 #include "mel_static_default.inc"
 #undef MGROUP_BEGIN
@@ -670,7 +671,15 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 const bool wb = a.stats != nullptr;       // statistics read the transformed values back
                 const bool affine = a.cm_mean != nullptr;
                 const float lf = a.log_floor;
-                if (a.use_log != 0 && !zmask) {
+                if (kStaticMel && a.use_log != 0 && !zmask && !affine && !wb && obase != nullptr && nvalid == kFT) {
+                    // full tile, plain log-mel output: ten independent load -> log -> store chains per thread
+                    constexpr int kPer = kFT * B200FE_STATIC_NMEL / kThreads;
+                    float x[kPer];
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) { const int e = tid + i * kThreads; x[i] = outs[e + e / B200FE_STATIC_NMEL]; }
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) obase[tid + i * kThreads] = fast_log(fmaxf(x[i], lf));
+                } else if (a.use_log != 0 && !zmask) {
                     // fast path: element e = row * nmel + col <-> staging e + row
                     if (affine) {
 #pragma unroll 2
