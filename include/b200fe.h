@@ -68,10 +68,11 @@ int b200fe_window_shift(const b200fe_plan* plan);
 int b200fe_padded_window_size(const b200fe_plan* plan);
 long long b200fe_num_frames(const b200fe_plan* plan, long long num_samples);
 /* Introspection for tests / benchmarks: what = 0 straight-line mel path in use, 1 registers
- * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count. */
+ * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count, 5 frames
+ * per tile (the granularity of b200fe_build_tile_table). */
 int b200fe_plan_info(const b200fe_plan* plan, int what);
 
-/* Host helper: fills table[2*i] = utterance, table[2*i+1] = first frame for every tile of 32 frames
+/* Host helper: fills table[2*i] = utterance, table[2*i+1] = first frame for every tile (b200fe_plan_info(plan, 5) frames)
  * with at least one valid frame, in utterance order; returns the number of tiles (table may be NULL
  * to query the size), or a negative status. */
 int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host, int batch, int* table_host, int capacity);
@@ -122,7 +123,7 @@ typedef struct b200fe_fbank_args {
     const int* d_row_bounds;
     int n_row_classes;
     /* Optional compact work list for ragged batches (b200fe_build_tile_table): [n_tiles][2] int32
-     * (utterance, first frame) of every 32-frame tile that holds valid frames, consumed through the
+     * (utterance, first frame) of every tile that holds valid frames, consumed through the
      * atomic counter d_work_counter (4 bytes, reset by the call).  Padded rows are then zeroed by a
      * separate streaming kernel of the same call.  NULL = iterate the padded (batch x max_frames) grid. */
     const int* d_tile_table;

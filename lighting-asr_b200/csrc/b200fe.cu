@@ -214,12 +214,12 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         for (int j = 0; j < p->nmel; ++j) { cost[j] = (p->seg_start[j + 2] - p->seg_start[j]) * 0.5 + 6.0; tot += cost[j]; }
         int j = 0; double acc = 0;
         p->grp_begin[0] = 0;
-        for (int w = 1; w < 8; ++w) {
-            const double target = tot * w / 8.0;
+        for (int w = 1; w < kWarps; ++w) {
+            const double target = tot * w / (double)kWarps;
             while (j < p->nmel && acc + cost[j] * 0.5 < target) { acc += cost[j]; ++j; }
             p->grp_begin[w] = (short)j;
         }
-        p->grp_begin[8] = (short)p->nmel;
+        for (int w = kWarps; w <= 8; ++w) p->grp_begin[w] = (short)p->nmel;
     }
     // ---- FFT twiddles (double precision, rounded once) ----
     std::vector<float2> twd(256), stw(256);
@@ -302,6 +302,7 @@ extern "C" int b200fe_plan_info(const b200fe_plan* p, int what)
         case 2: return p->smem_bytes;
         case 3: return p->ctas_per_sm;
         case 4: return p->num_sms;
+        case 5: return kFT;
         default: return -1;
     }
 }

@@ -31,11 +31,17 @@
 
 namespace b200fe {
 
-constexpr int kFT = 32;             // frames per tile
-constexpr int kThreads = 256;       // 8 warps, 16 half-warps
-constexpr int kHalfWarps = 16;
+#ifndef B200FE_WARPS
+#define B200FE_WARPS 8              // warps per CTA: 8 (2 CTAs/SM, 32-frame tiles) or 6 (3 CTAs/SM, 24-frame tiles)
+#endif
+constexpr int kWarps = B200FE_WARPS;
+constexpr int kFT = 4 * kWarps;             // frames per tile: every half-warp transforms two frames
+constexpr int kThreads = 32 * kWarps;
+constexpr int kHalfWarps = 2 * kWarps;
+constexpr int kCtasPerSm = kWarps == 8 ? 2 : 3;
+constexpr bool kAliasStaging = kWarps != 8;   // 3 CTAs/SM only fit with the staging tile aliased onto the transposition buffers
 constexpr int kXRow = 17;           // padded row length (float2) of the transposition buffer
-constexpr int kPTStride = 33;       // PT4[k/4][frame] float4 groups; a row of 32 frames is padded to 33 groups
+constexpr int kPTStride = kFT + 1;   // PT4[k/4][frame] float4 groups; a row of kFT frames is padded by one group (4*(kFT+1) = 4 mod 32 words)
 constexpr int kMaxMel = 128;
 constexpr int kMaxTimeMasks = 4;
 constexpr int kMaxFreqMasks = 4;
@@ -109,9 +115,10 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     SmemLayout L;
     int o = 0;
     for (int s = 0; s < kStages; ++s) { L.tile_off[s] = o; o += tile_floats * 4; }
-    L.xbuf_off = o; o += kHalfWarps * 16 * kXRow * 8;
-    // the staging tile is NOT aliased with anything: phase C of tile i overlaps phase A of tile i+1
-    L.outs_off = o; o += ((kFT * (nmel + 1) * 4 + 15) & ~15);
+    L.xbuf_off = o;
+    const int xbytes = kHalfWarps * 16 * kXRow * 8, obytes = (kFT * (nmel + 1) * 4 + 15) & ~15;
+    if (kAliasStaging) { L.outs_off = o; o += (xbytes > obytes ? xbytes : obytes); }     // closing barrier per tile
+    else { o += xbytes; L.outs_off = o; o += obytes; }   // phase C of tile i overlaps phase A of tile i+1
     L.pt_off = o; o += 64 * kPTStride * 16;
     L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
     L.bar_off = o; o += 16 + 32;            // mbarrier slots (16 B) + 2 tile descriptors (int4)
@@ -377,7 +384,7 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 // split twiddle (k = 0..127; the Nyquist bin has zero mel weight, TA:627).
 // kI16: the waveform is int16 PCM (2 bytes per sample over PCIe / HBM); 512-point family only.
 template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false>
-__global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L = make_layout(a.tile_floats, a.nmel);
@@ -535,8 +542,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 // Frame slot inside the tile: the two half-warps of a warp store PT columns 4 frames apart
                 // (disjoint banks).  Both half-warps run in lock step (full-mask shuffles); a half-warp whose
                 // frame is past the utterance end computes on stale shared memory and skips its stores.
+                const int slot = warp + kWarps * sub;
                 const int fl = kDual ? (8 * (warp >> 1) + 2 * (warp & 1) + 4 * h2)            // frames fl (a), fl + 1 (b)
-                                     : ((warp & 3) + 4 * h2 + 8 * (warp >> 2) + 16 * sub);
+                                     : ((slot & 3) + 8 * (slot >> 2) + 4 * h2);
                 const bool fvalid = fl < nvalid;
                 if (fl - 4 * h2 < nvalid) {
                     float2 v[16];
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                             const float2 z = v[8];
                             float p = 4.0f * (z.x * z.x + z.y * z.y);
                             if (!use_power) p = sqrtf(p);
-                            pt[(32 * kPTStride + fl) * 4] = p;
+                            pt[(32 * kPTStride + fl) * 4] = p;      // bin 128 = group 32
                         }
                     }
                 }
@@ -625,16 +633,22 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
                 const int fl = lane;
                 float* orow = outs + fl * ostride;
                 const float4* pcol = reinterpret_cast<const float4*>(pt) + fl;
-                if (kStaticMel) {
+                if (fl >= kFT) {
+                    // 24-frame tiles leave lanes 24..31 idle in this phase
+                } else if (kStaticMel) {
                     switch (warp) {
                         case 0: mel_static_group0(pcol, orow); break;
                         case 1: mel_static_group1(pcol, orow); break;
                         case 2: mel_static_group2(pcol, orow); break;
                         case 3: mel_static_group3(pcol, orow); break;
                         case 4: mel_static_group4(pcol, orow); break;
+#if B200FE_WARPS == 8
                         case 5: mel_static_group5(pcol, orow); break;
                         case 6: mel_static_group6(pcol, orow); break;
                         default: mel_static_group7(pcol, orow); break;
+#else
+                        default: mel_static_group5(pcol, orow); break;
+#endif
                     }
                 } else {
                     const int jb = a.grp_begin[warp], je = a.grp_begin[warp + 1];
@@ -777,6 +791,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_fused_kernel(const __grid_c
             __syncthreads();
             nxt_desc = s_desc[it & 1];
             __syncthreads();
+        } else if (kAliasStaging) {
+            __syncthreads();      // the staging tile aliases the transposition buffers of the next phase A
         }
         cur = nxt;
         g = gn;

@@ -103,6 +103,7 @@ class FbankPlan:
         self.num_mel_bins = num_mel_bins
         self.window_size = self.lib.b200fe_window_size(h)
         self.window_shift = self.lib.b200fe_window_shift(h)
+        self.tile_frames = self.lib.b200fe_plan_info(h, 5)
         self.sample_frequency = sample_frequency
 
     def num_frames(self, n):
@@ -342,12 +343,13 @@ class GpuFbankFrontend(torch.nn.Module):
             if self.compact_tiles and len_host is not None:
                 # ragged batch: enumerate only tiles with valid frames (host lengths are known), dynamic scheduling
                 T_g = T_host[b0:b0 + nb]
-                nt = (T_g + 31) // 32
+                ft = plan.tile_frames
+                nt = (T_g + ft - 1) // ft
                 tot = int(nt.sum())
                 tab = np.empty((tot, 2), dtype=np.int32)
                 tab[:, 0] = np.repeat(np.arange(nb, dtype=np.int32), nt)
                 starts = np.cumsum(nt) - nt
-                tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(starts, nt)).astype(np.int32) * 32
+                tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(starts, nt)).astype(np.int32) * ft
                 tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
                 counter = torch.empty((1,), dtype=torch.int32, device=dev)
                 a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
