@@ -181,9 +181,32 @@ typedef struct b200fe_post_args {
     const int* d_masks;          /* as above; NULL = no SpecAugment */
     int n_freq_masks, n_time_masks;
     float* d_fills;              /* [batch][n_freq_masks + n_time_masks] outputs (required with masks) */
+    int fill_zero;               /* 1 = replace_with_zero: masked cells become 0 instead of the running mean */
 } b200fe_post_args;
 
 int b200fe_postpass(const b200fe_plan* plan, const b200fe_post_args* args, void* stream);
+
+/* SpecAugment time warp (R/lasr/utils/specaugment.py:4-32, the first step of the registry transform
+ * `specaug`, R/lasr/data/datatrans.py:136): per utterance, rows [0, center) are resized to `warped` rows and
+ * rows [center, T) to T - warped rows with Pillow's BICUBIC arithmetic (float64 coefficients and
+ * accumulation, one rounding to float32) -- bit-identical to the reference.  (center, warped) are drawn on
+ * the host with the reference's generator; center < 0 copies the utterance (T - W <= W, no draw).
+ * Out of place: d_out gets the warped features (padded rows zero) and, optionally, their statistics in the
+ * layout of b200fe_fbank_fused for the mean fills of the masks that follow. */
+typedef struct b200fe_warp_args {
+    const float* d_in;           /* [batch][max_frames][num_mel_bins] */
+    float* d_out;                /* same shape, must not alias d_in */
+    const long long* d_nsamp;    /* [batch] */
+    int batch;
+    int max_frames;
+    const int* d_warp;           /* [batch][2] int32 (center, warped) */
+    double* d_stats;             /* optional, zeroed by the caller */
+    long long stats_stride;
+    const int* d_row_bounds;
+    int n_row_classes;
+} b200fe_warp_args;
+
+int b200fe_time_warp(const b200fe_plan* plan, const b200fe_warp_args* args, void* stream);
 
 /* Global CMVN: [2][num_mel_bins + 1] Kaldi statistics (row 0 sums + count, row 1 sums of
  * squares + 0) on the HOST -> mean / inverse std vectors (float32, host). */

@@ -37,13 +37,22 @@ class PostArgs(C.Structure):
         ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
         ("cmvn_mode", C.c_int), ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p),
         ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("d_fills", C.c_void_p),
+        ("fill_zero", C.c_int),
+    ]
+
+
+class WarpArgs(C.Structure):
+    _fields_ = [
+        ("d_in", C.c_void_p), ("d_out", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
+        ("d_warp", C.c_void_p), ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p),
+        ("n_row_classes", C.c_int),
     ]
 
 
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table",
-    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_postpass", "b200fe_cmvn_from_stats",
+    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
 ]
 
 _lib = None
@@ -99,6 +108,8 @@ def load(build_if_missing=True):
     lib.b200fe_d2h_ragged.restype = C.c_int
     lib.b200fe_postpass.argtypes = [C.c_void_p, C.POINTER(PostArgs), C.c_void_p]
     lib.b200fe_postpass.restype = C.c_int
+    lib.b200fe_time_warp.argtypes = [C.c_void_p, C.POINTER(WarpArgs), C.c_void_p]
+    lib.b200fe_time_warp.restype = C.c_int
     lib.b200fe_cmvn_from_stats.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, c_fp, c_fp]
     lib.b200fe_cmvn_from_stats.restype = C.c_int
     _lib = lib

@@ -104,6 +104,7 @@ struct PostArgs {
     const int* masks;
     int n_fmask, n_tmask;
     float* fills;
+    int fill_zero;               // 1: replace_with_zero (fills are 0), 0: running mean fills
     int rows_per_cta;
 };
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a)
     const double cells = (double)T * (double)a.nmel;
     for (int i = 0; i < nm; ++i) {
         // numpy: x[...] = x.mean() evaluated on the current array (specaugment.py:74,105)
-        const double fill = cells > 0 ? (double)(float)(total / cells) : 0.0;
+        const double fill = (cells > 0 && !a.fill_zero) ? (double)(float)(total / cells) : 0.0;
         int lo = mk[2 * i], hi = mk[2 * i + 1];
         double delta = 0.0;
         if (i < a.n_fmask) {
@@ -221,6 +222,125 @@ __global__ void __launch_bounds__(256) postpass_kernel(const PostArgs a)
         float* ptr = base + (long long)r * a.nmel + d;
         if (hit >= 0) *ptr = s_fill[hit];
         else if (a.cmvn_mode != 0) *ptr = (*ptr - s_mean[d]) * s_istd[d];
+    }
+}
+
+// ---- SpecAugment time warp ----------------------------------------------------
+// R/lasr/utils/specaugment.py:15-32: rows [0, center) are resized to `warped` rows and rows [center, T)
+// to T - warped rows with PIL's BICUBIC filter.  Pillow (12.2, src/libImaging/Resample.c) evaluates this
+// for mode 'F' as: per output row, float64 coefficients bicubic((y + ymin - c + 0.5) / filterscale),
+// normalised by their sum; float64 accumulation of pixel * coefficient in source order; one rounding to
+// float32.  The kernel repeats exactly that arithmetic (explicit _rn operations, no FMA contraction), so
+// the result is bit-identical to the reference's.
+struct WarpArgs {
+    const float* in;
+    float* out;
+    const long long* nsamp;
+    int B, Tmax, nmel, win, shift;
+    const int* warp;             // [B][2] (center, warped); center < 0 = utterance too short, rows are copied
+    double* stats;               // optional row-class column sums + sums of squares of the WARPED features
+    long long stats_stride;
+    const int* row_bounds;
+    int n_cls;
+};
+
+__device__ __forceinline__ double pil_bicubic(double x)
+{
+    x = fabs(x);
+    if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, x), 2.5), x), x), 1.0);
+    if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), -0.5);
+    return 0.0;
+}
+
+constexpr int kWarpRows = 32;    // output rows per CTA
+constexpr int kWarpTaps = 32;    // >= ceil(2 * scale) * 2 + 1 for |in - out| <= 5
+
+__global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
+{
+    const int utt = blockIdx.y;
+    const long long n = a.nsamp[utt];
+    const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
+    const int r0 = blockIdx.x * kWarpRows;
+    if (r0 >= a.Tmax) return;
+    __shared__ double s_k[kWarpRows][kWarpTaps];
+    __shared__ int s_ymin[kWarpRows], s_n[kWarpRows];
+    extern __shared__ float s_tile[];              // [kWarpRows][nmel + 1]
+    const int center = a.warp[2 * utt], warped = a.warp[2 * utt + 1];
+    const float* src = a.in + (long long)utt * a.Tmax * a.nmel;
+    float* dst = a.out + (long long)utt * a.Tmax * a.nmel;
+    if (threadIdx.x < kWarpRows) {
+        const int row = r0 + threadIdx.x;
+        int ymin = row, cnt = 1;
+        s_k[threadIdx.x][0] = 1.0;
+        if (row < T && center >= 0) {
+            const bool left = row < warped;
+            const int in_size = left ? center : T - center;
+            const int out_size = left ? warped : T - warped;
+            const int xx = left ? row : row - warped;
+            const int base = left ? 0 : center;
+            if (in_size == out_size) {
+                ymin = base + xx;                                      // Pillow returns a copy when the size is unchanged
+            } else {
+                const double scale = (double)in_size / (double)out_size;
+                const double filterscale = scale < 1.0 ? 1.0 : scale;
+                const double support = __dmul_rn(2.0, filterscale);
+                const double c = __dmul_rn((double)xx + 0.5, scale);
+                const double ss = 1.0 / filterscale;
+                int xmin = (int)__dadd_rn(__dsub_rn(c, support), 0.5);
+                if (xmin < 0) xmin = 0;
+                int xmax = (int)__dadd_rn(__dadd_rn(c, support), 0.5);
+                if (xmax > in_size) xmax = in_size;
+                cnt = min(xmax - xmin, kWarpTaps);
+                double ww = 0.0;
+                for (int x = 0; x < cnt; ++x) {
+                    const double w = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), c), 0.5), ss));
+                    s_k[threadIdx.x][x] = w;
+                    ww = __dadd_rn(ww, w);
+                }
+                if (ww != 0.0)
+                    for (int x = 0; x < cnt; ++x) s_k[threadIdx.x][x] = s_k[threadIdx.x][x] / ww;
+                ymin = base + xmin;
+            }
+        }
+        s_ymin[threadIdx.x] = ymin;
+        s_n[threadIdx.x] = cnt;
+    }
+    __syncthreads();
+    const int ostride = a.nmel + 1;
+    for (int e = threadIdx.x; e < kWarpRows * a.nmel; e += 256) {
+        const int r = e / a.nmel, col = e - r * a.nmel, row = r0 + r;
+        if (row >= a.Tmax) break;
+        float v = 0.f;
+        if (row < T) {
+            const int ymin = s_ymin[r], cnt = s_n[r];
+            double acc = 0.0;
+            for (int y = 0; y < cnt; ++y) acc = __dadd_rn(acc, __dmul_rn((double)src[(long long)(ymin + y) * a.nmel + col], s_k[r][y]));
+            v = (float)acc;
+        }
+        dst[(long long)row * a.nmel + col] = v;
+        s_tile[r * ostride + col] = v;
+    }
+    if (a.stats == nullptr) return;
+    __syncthreads();
+    const int nvalid = min(max(T - r0, 0), kWarpRows);
+    if (nvalid <= 0) return;
+    const int nb = a.n_cls - 1;
+    const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
+    double* sb = a.stats + (long long)utt * a.stats_stride;
+    for (int j = threadIdx.x; j < a.nmel; j += 256) {
+        int cls = bounds ? row_class(bounds, nb, r0) : 0;
+        double s1 = 0.0, s2 = 0.0;
+        for (int fr = 0; fr < nvalid; ++fr) {
+            if (bounds) {
+                const int cc = row_class(bounds, nb, r0 + fr);
+                if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
+            }
+            const double x = (double)s_tile[fr * ostride + j];
+            s1 += x;
+            s2 = fma(x, x, s2);
+        }
+        atomicAdd(sb + (long long)cls * a.nmel + j, s1);
+        atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
     }
 }
 

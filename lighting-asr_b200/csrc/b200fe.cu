@@ -465,6 +465,7 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     a.cmvn_mode = g->cmvn_mode; a.cm_mean = g->d_cmvn_mean; a.cm_istd = g->d_cmvn_istd;
     a.masks = masks ? g->d_masks : nullptr; a.n_fmask = masks ? g->n_freq_masks : 0; a.n_tmask = masks ? g->n_time_masks : 0;
     a.fills = g->d_fills;
+    a.fill_zero = g->fill_zero;
     a.rows_per_cta = 64;
     cudaStream_t st = (cudaStream_t)stream;
     finalize_kernel<<<g->batch, 128, 0, st>>>(a);
@@ -475,6 +476,25 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
     if (vec) postpass_vec_kernel<<<grid, 256, 0, st>>>(a);
     else postpass_kernel<<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_time_warp(const b200fe_plan* p, const b200fe_warp_args* g, void* stream)
+{
+    if (!p || !g || !g->d_in || !g->d_out || !g->d_nsamp || !g->d_warp || g->batch <= 0 || g->max_frames <= 0)
+        return fail(B200FE_EINVAL, "time_warp: bad argument");
+    if (g->d_in == g->d_out) return fail(B200FE_EINVAL, "time_warp: in-place operation is not possible");
+    WarpArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = g->d_in; a.out = g->d_out; a.nsamp = g->d_nsamp; a.B = g->batch; a.Tmax = g->max_frames; a.nmel = p->nmel;
+    a.win = p->win; a.shift = p->shift; a.warp = g->d_warp;
+    a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds;
+    a.n_cls = g->d_stats ? (g->n_row_classes > 0 ? g->n_row_classes : 1) : 1;
+    if (a.n_cls > kMaxRowClasses) return fail(B200FE_EINVAL, "time_warp: too many row classes");
+    dim3 grid((unsigned)((g->max_frames + kWarpRows - 1) / kWarpRows), (unsigned)g->batch);
+    const size_t smem = (size_t)kWarpRows * (p->nmel + 1) * sizeof(float);
+    time_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }

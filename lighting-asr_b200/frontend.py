@@ -135,7 +135,7 @@ class GpuFbankFrontend(torch.nn.Module):
                  use_log_fbank=True, use_power=True, vtln_warp=1.0, window_type="povey", blackman_coeff=0.42,
                  audio_bit=16, peak_norm=False, cmvn="none", cmvn_stats=None, specaug=False,
                  max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2, replace_with_zero=False,
-                 consume_time_warp_draws=False, l2_chunk_bytes=None, compact_tiles=True):
+                 consume_time_warp_draws=False, time_warp=False, max_time_warp=5, l2_chunk_bytes=None, compact_tiles=True):
         super().__init__()
         if not snip_edges or use_energy or vtln_warp != 1.0 or not round_to_power_of_two:
             raise ValueError("snip_edges=False, use_energy=True, vtln_warp != 1 and round_to_power_of_two=False "
@@ -154,8 +154,22 @@ class GpuFbankFrontend(torch.nn.Module):
         self.cmvn = cmvn
         self.specaug = specaug
         self.replace_with_zero = replace_with_zero
+        # time_warp=True runs the registry transform `specaug` exactly as the reference does (warp, then masks,
+        # datatrans.py:136-150); the default is the masks-only scope of BASELINE.json's north_star
+        self.time_warp = bool(time_warp) and bool(specaug)
         self.sa = dict(max_freq_width=max_freq_width, n_freq_mask=n_freq_mask, max_time_width=max_time_width,
-                       n_time_mask=n_time_mask, consume_time_warp_draws=consume_time_warp_draws)
+                       n_time_mask=n_time_mask, consume_time_warp_draws=consume_time_warp_draws or self.time_warp,
+                       max_time_warp=max_time_warp)
+        self._pre = None
+        if self.time_warp:
+            # features before SpecAugment come from a child front end with the same options; the warp is
+            # out of place, so its output buffer is the final one
+            self._pre = GpuFbankFrontend(num_mel_bins=num_mel_bins, dither=dither, frame_length=frame_length, frame_shift=frame_shift,
+                                         high_freq=high_freq, low_freq=low_freq, preemphasis_coefficient=preemphasis_coefficient,
+                                         remove_dc_offset=remove_dc_offset, sample_frequency=sample_frequency, use_log_fbank=use_log_fbank,
+                                         use_power=use_power, window_type=window_type, blackman_coeff=blackman_coeff, audio_bit=audio_bit,
+                                         peak_norm=peak_norm, cmvn=cmvn, cmvn_stats=cmvn_stats, specaug=False,
+                                         l2_chunk_bytes=l2_chunk_bytes, compact_tiles=compact_tiles)
         self.l2_chunk_bytes = l2_chunk_bytes      # None: one launch per batch (measured fastest); else utterance groups
         self.compact_tiles = compact_tiles
         self._plans = {}
@@ -209,6 +223,8 @@ class GpuFbankFrontend(torch.nn.Module):
         a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
+        if self.time_warp:
+            return self._forward_time_warp(wav, wav_len, max_frames, masks, out, out_len, wav_offsets, dither_noise)
         packed = wav_offsets is not None
         if wav.dtype not in (torch.float32, torch.int16) or wav.dim() != (1 if packed else 2):
             raise ValueError("wav must be float32 or int16 PCM, (B, Nmax) or 1-D with wav_offsets")
@@ -269,8 +285,12 @@ class GpuFbankFrontend(torch.nn.Module):
         n_f = n_t = 0
         masks_dev = bounds_dev = None
         if self.specaug:
+            warp_np = None
             if masks is None:
-                m_np, b_np = _specaug.plan_batch(T_host, D, **self.sa)
+                if self.time_warp:
+                    m_np, b_np, warp_np = _specaug.plan_batch(T_host, D, return_warp=True, **self.sa)
+                else:
+                    m_np, b_np = _specaug.plan_batch(T_host, D, **self.sa)
             else:
                 m_np = np.ascontiguousarray(masks, dtype=np.int32)
                 n_f_, n_t_ = self.sa["n_freq_mask"], self.sa["n_time_mask"]
@@ -390,6 +410,51 @@ class GpuFbankFrontend(torch.nn.Module):
                 self.launch_count += 2      # finalize + in-place post pass
         self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak)
         return feats, feat_len
+
+    def _forward_time_warp(self, wav, wav_len, max_frames, masks, out, out_len, wav_offsets, dither_noise):
+        """norm -> fbank -> CMVN (child front end) -> time warp -> frequency / time masks: the registry
+        transform `specaug` exactly as the reference applies it (datatrans.py:136-150)."""
+        if masks is not None:
+            raise ValueError("explicit masks cannot be combined with time_warp (the warp draws precede them)")
+        dev = wav.device
+        len_host = np.asarray(wav_len.cpu() if torch.is_tensor(wav_len) else wav_len, dtype=np.int64).reshape(-1)
+        B, D = len(len_host), self.num_mel_bins
+        pre, flen = self._pre(wav, len_host, max_frames=max_frames, out_len=out_len, wav_offsets=wav_offsets, dither_noise=dither_noise)
+        self.launch_count += self._pre.launch_count
+        self._pre.launch_count = 0
+        Tmax = pre.shape[1]
+        T_host, _ = self.frame_counts(len_host)
+        m_np, b_np, w_np = _specaug.plan_batch(T_host, D, return_warp=True, **self.sa)
+        n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
+        n_cls = 2 * n_t + 1
+        masks_dev = torch.from_numpy(m_np).to(dev, non_blocking=True)
+        bounds_dev = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev, non_blocking=True)
+        warp_dev = torch.from_numpy(np.ascontiguousarray(w_np)).to(dev, non_blocking=True)
+        len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+        if out is not None:
+            if out.shape != pre.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == pre.data_ptr():
+                raise ValueError("out must be a distinct contiguous float32 (B, Tmax, D) tensor")
+            feats = out
+        else:
+            feats = torch.empty_like(pre)
+        stats = torch.zeros((B, n_cls + 1, D), dtype=torch.float64, device=dev)
+        fills = torch.empty((B, n_f + n_t), dtype=torch.float32, device=dev)
+        plan = self.plan(dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        w = _lib.WarpArgs()
+        w.d_in, w.d_out, w.d_nsamp, w.batch, w.max_frames = _ptr(pre), _ptr(feats), _ptr(len_dev), B, Tmax
+        w.d_warp, w.d_stats, w.stats_stride, w.d_row_bounds, w.n_row_classes = _ptr(warp_dev), _ptr(stats), (n_cls + 1) * D, _ptr(bounds_dev), n_cls
+        _lib.check(plan.lib.b200fe_time_warp(plan.handle, C.byref(w), stream), "b200fe_time_warp")
+        q = _lib.PostArgs()
+        q.d_feats, q.d_nsamp, q.batch, q.max_frames = _ptr(feats), _ptr(len_dev), B, Tmax
+        q.d_stats, q.stats_stride, q.d_row_bounds, q.n_row_classes = _ptr(stats), (n_cls + 1) * D, _ptr(bounds_dev), n_cls
+        q.cmvn_mode = 0
+        q.d_masks, q.n_freq_masks, q.n_time_masks, q.d_fills = _ptr(masks_dev), n_f, n_t, _ptr(fills)
+        q.fill_zero = int(self.replace_with_zero)
+        _lib.check(plan.lib.b200fe_postpass(plan.handle, C.byref(q), stream), "b200fe_postpass")
+        self.launch_count += 3          # warp + finalize + mask fill
+        self.last = dict(stats=stats, fills=fills, masks=masks_dev, warp=warp_dev, pre=pre)
+        return feats, flen
 
     # -- host-to-host path: the drop-in for the reference's collate_fn (features back on the host) --
     @torch.no_grad()

@@ -50,13 +50,14 @@ def install(register_trans, device="cuda:0", return_tensor=False, **fbank_kwargs
 
     ``fbank:80``                 -> GPU fbank (same defaults as WavToKaldiFbank)
     ``b200:norm+fbank:80``       -> peak norm + fbank in one launch (replaces ["norm", "fbank:80"])
-    ``b200:norm+fbank:80+specaug`` -> + SpecAugment masks (mean fill), masks-only RNG replay
+    ``b200:norm+fbank:80+specaug`` -> + the reference's SpecAugment: PIL-exact time warp, then 2 frequency / 2 time masks (mean fill)
     """
     base = dict(fbank_kwargs)
     table = {
         "fbank:80": GpuTransform(device, return_tensor, **base),
         "b200:norm+fbank:80": GpuTransform(device, return_tensor, peak_norm=True, **base),
-        "b200:norm+fbank:80+specaug": GpuTransform(device, return_tensor, peak_norm=True, specaug=True, **base),
+        # the reference's `specaug` always warps first (datatrans.py:136): time_warp=True is the exact drop-in
+        "b200:norm+fbank:80+specaug": GpuTransform(device, return_tensor, peak_norm=True, specaug=True, time_warp=True, **base),
     }
     for key, fn in table.items():
         register_trans.register(key)(fn)
@@ -102,11 +103,11 @@ def make_dataset_class():
         def __init__(self, wav_list=None, text_list=None, feats_list=None, tokenizer="char", audio_trans=("avgchannel",),
                      feats_trans=None, pad_audio=0, pad_feats=0, batch_sort=True, batch_size=32, batch_duration=320,
                      batch_bin=32 * 500 * 80, batch_type="size", max_duration=30, min_duration=0.3, text_freq=0.08,
-                     min_token=0, max_token=5000, device="cuda:0", peak_norm=True, cmvn="none", specaug=False):
+                     min_token=0, max_token=5000, device="cuda:0", peak_norm=True, cmvn="none", specaug=False, time_warp=True):
             super().__init__(wav_list, text_list, feats_list, tokenizer, list(audio_trans), feats_trans, pad_audio, pad_feats,
                              batch_sort, batch_size, batch_duration, batch_bin, batch_type, max_duration, min_duration,
                              text_freq, min_token, max_token)
-            self._collate = B200Collate(device, peak_norm=peak_norm, cmvn=cmvn, specaug=specaug)
+            self._collate = B200Collate(device, peak_norm=peak_norm, cmvn=cmvn, specaug=specaug, time_warp=time_warp)
 
         def collate_fn(self, batch):
             items = [x for b in batch for x in b]

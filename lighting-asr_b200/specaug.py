@@ -57,12 +57,14 @@ def plan_utterance(num_frames, num_mel, max_freq_width=27, n_freq_mask=2, max_ti
 
 
 def plan_batch(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2,
-               consume_time_warp_draws=False, max_time_warp=5):
+               consume_time_warp_draws=False, max_time_warp=5, return_warp=False):
     """Rectangles for a batch, utterances visited in order (dataset.py:190).
 
     Same draws, in the same order, as calling ``plan_utterance`` per utterance (tested), written as a
     tight loop because the RNG replay is the only per-utterance host work left on the path.
-    Returns (masks [B, n_f + n_t, 2] int32, row_bounds [B, 2 n_t] int32 sorted)."""
+    Returns (masks [B, n_f + n_t, 2] int32, row_bounds [B, 2 n_t] int32 sorted); with ``return_warp`` also
+    warps [B, 2] int32 = (center, warped) of the time warp that precedes the masks (specaugment.py:20-24),
+    (-1, -1) where the utterance is too short to be warped."""
     n_f, n_t = n_freq_mask, n_time_mask
     if n_f > MAX_FREQ_MASKS or n_t > MAX_TIME_MASKS:
         raise ValueError("at most %d frequency and %d time masks are supported" % (MAX_FREQ_MASKS, MAX_TIME_MASKS))
@@ -75,11 +77,14 @@ def plan_batch(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_w
     high = np.tile(np.array([max_freq_width] * (2 * n_f) + [max_time_width] * (2 * n_t), dtype=np.int64), B)
     draws = np.random.randint(0, high).reshape(B, n_f + n_t, 2).tolist() if B > 0 else []
     rows = []
+    warps = []
     for T, dr in zip(frame_lens, draws):
         T = int(T)
         if consume_time_warp_draws and T - max_time_warp > max_time_warp:
             center = rr(max_time_warp, T - max_time_warp)
-            rr(center - max_time_warp, center + max_time_warp)
+            warps.append((center, rr(center - max_time_warp, center + max_time_warp) + 1))
+        else:
+            warps.append((-1, -1))
         row = []
         for f, w in dr[:n_f]:
             f0 = rr(0, num_mel - f)
@@ -103,4 +108,6 @@ def plan_batch(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_w
         rows.append(row)
     masks = np.asarray(rows, dtype=np.int32).reshape(B, n_f + n_t, 2)
     bounds = np.sort(masks[:, n_f:].reshape(B, 2 * n_t), axis=1)
+    if return_warp:
+        return masks, np.ascontiguousarray(bounds), np.asarray(warps, dtype=np.int32).reshape(B, 2)
     return masks, np.ascontiguousarray(bounds)

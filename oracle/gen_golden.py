@@ -92,6 +92,26 @@ def main():
             reg["specaug"](x.copy())
             sg[key + "_rng_after_full"] = np.array([random.random(), np.random.rand()])
             cases.append(key)
+    # full registry transform outputs (time warp + masks) for the time-warp row F1 (smaller set: the arrays are stored)
+    full_cases = []
+    for seed in range(4):
+        for T in (11, 12, 39, 98, 300):
+            x = pattern(T)
+            random.seed(seed)
+            np.random.seed(seed)
+            sg["full_s%d_T%d" % (seed, T)] = reg["specaug"](x.copy())
+            full_cases.append("s%d_T%d" % (seed, T))
+    sg["full_cases"] = np.array(full_cases)
+    # the resize primitive itself: PIL BICUBIC on a float32 image, rows only
+    from PIL import Image
+    rs = np.random.RandomState(7)
+    pil_cases = []
+    for h, o in ((5, 1), (5, 10), (7, 12), (30, 26), (30, 35), (200, 203), (6, 1), (1, 4)):
+        img = rs.normal(10, 5, (h, 80)).astype(np.float32)
+        sg["pil_in_%d_%d" % (h, o)] = img
+        sg["pil_out_%d_%d" % (h, o)] = np.asarray(Image.fromarray(img).resize((80, o), Image.BICUBIC))
+        pil_cases.append("%d_%d" % (h, o))
+    sg["pil_cases"] = np.array(pil_cases)
     sg["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(OUT, "specaug_reference.npz"), **sg)
     print("wrote", os.listdir(OUT))

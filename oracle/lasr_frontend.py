@@ -67,6 +67,75 @@ def plan_time_masks(num_frames, T=40, n_mask=2):
     return out
 
 
+def _bicubic(x):
+    """Pillow's bicubic_filter (src/libImaging/Resample.c), a = -0.5."""
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_rows(src, out_rows):
+    """Vertical BICUBIC resize of a float32 (H, W) array exactly as ``Image.fromarray(src).resize((W, out_rows),
+    BICUBIC)`` computes it for mode 'F' (Pillow 12.2: precompute_coeffs + ImagingResampleVertical_32bpc:
+    float64 coefficients normalised per output row, float64 accumulation in source order, one rounding to
+    float32).  Verified bit for bit against Pillow in tests/test_oracle_golden.py."""
+    src = np.asarray(src, dtype=np.float32)
+    in_size = src.shape[0]
+    if out_rows == in_size:
+        return src.copy()
+    scale = filterscale = in_size / out_rows
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    out = np.empty((out_rows, src.shape[1]), dtype=np.float32)
+    s64 = src.astype(np.float64)
+    for xx in range(out_rows):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size)
+        k = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax - xmin)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        acc = np.zeros(src.shape[1], dtype=np.float64)
+        for y, w in enumerate(k):
+            acc = acc + s64[y + xmin] * w
+        out[xx] = acc.astype(np.float32)
+    return out
+
+
+def time_warp(x, max_time_warp=5):
+    """R/lasr/utils/specaugment.py:4-32 (mode "PIL", in place): no draw and no change when
+    t - W <= W; else center ~ randrange(W, t - W), warped ~ randrange(center - W, center + W) + 1 and the
+    two segments are resized to ``warped`` and ``t - warped`` rows.  Returns (x, (center, warped) | None)."""
+    t = x.shape[0]
+    w = max_time_warp
+    if t - w <= w:
+        return x, None
+    center = random.randrange(w, t - w)
+    warped = random.randrange(center - w, center + w) + 1
+    left = pil_bicubic_rows(x[:center], warped)
+    right = pil_bicubic_rows(x[center:], t - warped)
+    x[:warped] = left
+    x[warped:] = right
+    return x, (center, warped)
+
+
+def spec_augment_full(x, max_time_warp=5, **mask_kw):
+    """The registry transform ``specaug`` as the reference runs it (R/lasr/data/datatrans.py:136-150):
+    time warp, then frequency masks, then time masks."""
+    x, wp = time_warp(x, max_time_warp)
+    x, rects = spec_augment_masks(x, **mask_kw)
+    return x, wp, rects
+
+
 def spec_augment_masks(x, max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2,
                        replace_with_zero=False):
     """Masks-only part of R/lasr/data/datatrans.py:106-151 (freq_mask then time_mask, in place,

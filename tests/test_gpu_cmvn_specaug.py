@@ -154,3 +154,47 @@ def test_specaug_without_cmvn_mean_fill(lasr_b200):
         T = kaldi_fbank.num_frames(len(w))
         y, _ = lasr_frontend.spec_augment_masks(raw[i, :T].copy())
         assert _close(g[i, :T], y.astype(np.float64), rtol=1e-4, atol=2e-5) == 0
+
+
+def test_full_specaug_with_time_warp(lasr_b200):
+    """Row F1: warp + masks as the reference's registry transform `specaug` (datatrans.py:136-150).  The warp
+    repeats Pillow's float64 BICUBIC arithmetic, so the warped features are bit-identical to the oracle's
+    (itself pinned bit for bit to the reference); masks follow with the usual fill tolerance."""
+    rng = np.random.default_rng(13)
+    lens = [160000, 48000, 7 * 16000 + 77, 2000, 1840, 400 + 160 * 10]      # incl. T = 11 (no warp) and T = 10
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    T = [kaldi_fbank.num_frames(x) for x in lens]
+    for kw in ({}, {"cmvn": "utt_meanvar"}, {"replace_with_zero": True}):
+        base_kw = {k: v for k, v in kw.items() if k != "replace_with_zero"}
+        pre = lasr_b200.GpuFbankFrontend(**base_kw)(wav, n)[0].cpu().numpy()
+        fe = lasr_b200.GpuFbankFrontend(specaug=True, time_warp=True, **kw)
+        random.seed(21)
+        np.random.seed(21)
+        g = fe(wav, n)[0].cpu().numpy()
+        warps = fe.last["warp"].cpu().numpy()
+        random.seed(21)
+        np.random.seed(21)
+        for i in range(len(lens)):
+            x = pre[i, : T[i]].copy()
+            xw, wp = lasr_frontend.time_warp(x)
+            warped_only = xw.copy()
+            y, rects = lasr_frontend.spec_augment_masks(xw, replace_with_zero=kw.get("replace_with_zero", False))
+            assert (wp is None and warps[i, 0] < 0) or tuple(warps[i]) == wp
+            masked = np.zeros_like(y, dtype=bool)
+            for kind, lo, hi, _ in rects:
+                if kind == "f":
+                    masked[:, max(lo, 0):max(hi, 0)] = True
+                else:
+                    masked[max(lo, 0):max(hi, 0)] = True
+            gi = g[i, : T[i]]
+            assert np.array_equal(gi[~masked], warped_only[~masked])          # bit-identical warp
+            assert _close(gi[masked], y[masked].astype(np.float64), rtol=1e-4, atol=2e-5) == 0
+            assert np.all(g[i, T[i]:] == 0)
+        # both generators end where the reference's full transform leaves them
+        after = (random.random(), np.random.rand())
+        random.seed(21)
+        np.random.seed(21)
+        for i in range(len(lens)):
+            lasr_frontend.spec_augment_full(pre[i, : T[i]].copy())
+        assert after == (random.random(), np.random.rand())

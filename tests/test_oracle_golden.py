@@ -104,6 +104,24 @@ def test_specaug_masks_match_reference(sg):
         assert np.array_equal(np.packbits(z != x), sg[key + "_zero_changed"]), key
 
 
+def test_pil_bicubic_restatement_is_bit_exact(sg):
+    for key in sg["pil_cases"]:
+        h, o = (int(v) for v in key.split("_"))
+        got = lasr_frontend.pil_bicubic_rows(sg["pil_in_" + key], o)
+        assert np.array_equal(got, sg["pil_out_" + key]), key
+
+
+def test_full_specaug_with_time_warp_matches_reference(sg):
+    """Row F1: the registry transform ``specaug`` (warp + masks) as the reference runs it."""
+    for key in sg["full_cases"]:
+        seed, T = int(key.split("_")[0][1:]), int(key.split("_T")[1])
+        random.seed(seed)
+        np.random.seed(seed)
+        y, wp, _ = lasr_frontend.spec_augment_full(_pattern(T))
+        assert np.array_equal(y, sg["full_" + key]), key
+        assert (wp is None) == (T - 5 <= 5)
+
+
 def test_cmvn_definition():
     rng = np.random.default_rng(0)
     feats = [rng.normal(3, 2, (T, 80)).astype(np.float32) for T in (10, 57, 300)]
