@@ -693,6 +693,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     for (int i = 0; i < kPer; ++i) { const int e = tid + i * kThreads; x[i] = outs[e + e / B200FE_STATIC_NMEL]; }
 #pragma unroll
                     for (int i = 0; i < kPer; ++i) obase[tid + i * kThreads] = fast_log(fmaxf(x[i], lf));
+                } else if (kStaticMel && a.use_log != 0 && !zmask && !affine && wb && nvalid == kFT) {
+                    // full tile in statistics mode (utterance CMVN is applied by the post pass): same ten chains, the
+                    // log-mel values are also written back for the column reducers
+                    constexpr int kPer = kFT * B200FE_STATIC_NMEL / kThreads;
+                    float x[kPer];
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) { const int e = tid + i * kThreads; x[i] = outs[e + e / B200FE_STATIC_NMEL]; }
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) {
+                        const int e = tid + i * kThreads;
+                        x[i] = fast_log(fmaxf(x[i], lf));
+                        if (obase) obase[e] = x[i];
+                        outs[e + e / B200FE_STATIC_NMEL] = x[i];
+                    }
                 } else if (a.use_log != 0 && !zmask) {
                     // fast path: element e = row * nmel + col <-> staging e + row
                     if (affine) {
