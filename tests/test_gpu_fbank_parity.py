@@ -252,3 +252,46 @@ def test_int16_pcm_input_is_bit_identical(lasr_b200):
         assert torch.equal(hf, ref.cpu()) and torch.equal(hl, rlen.cpu()), kw
     ta = _ta_fbank(flt[0])
     assert tol_violations(lasr_b200.GpuFbankFrontend()(wav_i.cuda()[:1], n[:1])[0][0].cpu().numpy(), ta) <= 2
+
+
+def test_c_abi_argument_errors(lasr_b200):
+    """Error behaviour of the C ABI: negative status + message, no exception from the library itself."""
+    import ctypes as C
+    L = lasr_b200._lib
+    lib = L.load()
+    o = L.Opts()
+    lib.b200fe_default_opts(C.byref(o))
+    h = C.c_void_p()
+    o.num_mel_bins = 2                                   # torchaudio asserts num_bins > 3 (TA:449)
+    assert lib.b200fe_plan_create(C.byref(o), C.byref(h)) == -1 and b"num_mel_bins" in lib.b200fe_last_error()
+    o.num_mel_bins = 80
+    o.frame_length_ms = 40.0                             # 640 samples -> padded 1024: unsupported
+    assert lib.b200fe_plan_create(C.byref(o), C.byref(h)) == -1
+    o.frame_length_ms = 25.0
+    o.low_freq, o.high_freq = 5000.0, 100.0              # TA:460-462
+    assert lib.b200fe_plan_create(C.byref(o), C.byref(h)) == -1 and b"Nyquist" in lib.b200fe_last_error()
+    o.low_freq, o.high_freq = 20.0, 0.0
+    assert lib.b200fe_plan_create(C.byref(o), C.byref(h)) == 0
+    assert lib.b200fe_num_frames(h, 399) == 0 and lib.b200fe_num_frames(h, 160000) == 998
+    a = L.FbankArgs()
+    assert lib.b200fe_fbank_fused(h, C.byref(a), None) == -1          # no waveform
+    wav = torch.zeros((1, 1600), device="cuda:0")
+    n = torch.tensor([1600], device="cuda:0")
+    a.d_wav, a.wav_stride, a.d_nsamp, a.batch, a.max_frames = wav.data_ptr(), 1600, n.data_ptr(), 1, 8
+    assert lib.b200fe_fbank_fused(h, C.byref(a), None) == -1 and b"neither" in lib.b200fe_last_error()
+    out = torch.empty((1, 8, 80), device="cuda:0")
+    a.d_out = out.data_ptr()
+    a.n_time_masks = 9
+    assert lib.b200fe_fbank_fused(h, C.byref(a), None) == -1 and b"masks" in lib.b200fe_last_error()
+    a.n_time_masks = 0
+    a.wav_dtype = 7
+    assert lib.b200fe_fbank_fused(h, C.byref(a), None) == -1
+    a.wav_dtype = 0
+    assert lib.b200fe_fbank_fused(h, C.byref(a), None) == 0
+    torch.cuda.synchronize()
+    assert np.allclose(out.cpu().numpy(), -15.942385, atol=1e-5)
+    lib.b200fe_plan_destroy(h)
+    with pytest.raises(ValueError):
+        lasr_b200.GpuFbankFrontend()(torch.zeros((1, 16000), device="cuda:0", dtype=torch.float64), np.array([16000]))
+    with pytest.raises(ValueError):
+        lasr_b200.GpuFbankFrontend()(torch.zeros((1, 16000), device="cuda:0"), np.array([16001]))
