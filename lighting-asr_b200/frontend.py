@@ -551,19 +551,32 @@ class GpuFbankFrontend(torch.nn.Module):
         len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
         if stats is None:
             stats = torch.zeros((2, D + 1), dtype=torch.float64, device=dev)
-        acc = torch.zeros((2, D), dtype=torch.float64, device=dev)
         peak = None
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
             _lib.check(plan.lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), C.c_void_p(0), _ptr(len_dev), B, _ptr(peak), stream),
                        "b200fe_peak_absmax")
+        # per-utterance accumulators (no atomic contention on one 2 x D block), compact tile list, then one
+        # fp64 reduction over the batch
+        acc = torch.zeros((B, 2, D), dtype=torch.float64, device=dev)
         a = _lib.FbankArgs()
         a.d_wav, a.wav_stride, a.d_nsamp, a.batch = _ptr(wav), wav.stride(0), _ptr(len_dev), B
+        a.wav_dtype = 1 if wav.dtype == torch.int16 else 0
         a.d_peak = _ptr(peak)
         a.max_frames = int(T_host.max())
-        a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 0, 1
+        a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 2 * D, 1
+        if self.compact_tiles:
+            ft = plan.tile_frames
+            nt = (T_host + ft - 1) // ft
+            tot = int(nt.sum())
+            tab = np.empty((tot, 2), dtype=np.int32)
+            tab[:, 0] = np.repeat(np.arange(B, dtype=np.int32), nt)
+            tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(nt) - nt, nt)).astype(np.int32) * ft
+            tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
+            counter = torch.empty((1,), dtype=torch.int32, device=dev)
+            a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
         _lib.check(plan.lib.b200fe_fbank_fused(plan.handle, C.byref(a), stream), "b200fe_fbank_fused")
-        stats[:, :D] += acc
+        stats[:, :D] += acc.sum(0)
         stats[0, D] += float(T_host.sum())
         return stats
