@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "b200fe.cu")
 LIB = os.environ.get("B200FE_LIB") or os.path.join(HERE, "libb200fe.so")   # B200FE_LIB: A/B experiments with alternative builds
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("b200fe.cu", "fbank_kernel.cuh", "aux_kernels.cuh", "b200fe_common.cuh", "mel_static_default.inc")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("b200fe.cu", "fbank_kernel.cuh", "fbank_ws_kernel.cuh", "aux_kernels.cuh", "b200fe_common.cuh", "mel_static_default.inc")] + \
        [os.path.join(os.path.dirname(HERE), "include", "b200fe.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -7,11 +7,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "fbank_ws_kernel.cuh"
 #include "fbank_kernel.cuh"
 
 #define B200FE_MEL_HOST_TABLES
@@ -64,7 +66,16 @@ struct b200fe_plan {
     int nload;          // 13 or 16
     int static_mel;     // 1: tables equal the baked-in LASR default -> straight-line phase B
     int ctas_per_sm;
+    int use_ws;         // 1: the warp-specialised kernel (fbank_ws_kernel.cuh) serves this option set
+    int ws_smem_bytes;
 };
+
+static const void* ws_kernel(bool peak, bool i16)
+{
+    if (i16) return peak ? (const void*)fbank_ws_kernel<true, true> : (const void*)fbank_ws_kernel<false, true>;
+    return peak ? (const void*)fbank_ws_kernel<true, false> : (const void*)fbank_ws_kernel<false, false>;
+}
+static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : kFT; }
 
 static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false)
 {
@@ -277,6 +288,18 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kThreads, p->smem_bytes);
     if (e != cudaSuccess || occ < 1) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "fbank kernel cannot be resident (occ=%d): %s", occ, cudaGetErrorString(e)); }
     p->ctas_per_sm = occ;
+    // Experimental: B200FE_WS=1 routes LASR's default option set to the warp-specialised kernel (fbank_ws_kernel.cuh).
+    // Bit-identical output, but measured 25-30 % SLOWER than the phase-ordered kernel on B200, so it is
+    // opt-in and kept for A/B runs only.
+    p->use_ws = 0;
+    p->ws_smem_bytes = ws_layout(p->shift, p->win).total;
+    const char* want_ws = getenv("B200FE_WS");
+    if (p->static_mel && want_ws && want_ws[0] == '1' && (size_t)p->ws_smem_bytes <= prop.sharedMemPerBlockOptin) {
+        for (int v = 0; v < 4 && e == cudaSuccess; ++v)
+            e = cudaFuncSetAttribute(ws_kernel(v & 1, v & 2), cudaFuncAttributeMaxDynamicSharedMemorySize, p->ws_smem_bytes);
+        if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute (ws): %s", cudaGetErrorString(e)); }
+        p->use_ws = 1;
+    }
     *out = p;
     return B200FE_OK;
 }
@@ -302,7 +325,8 @@ extern "C" int b200fe_plan_info(const b200fe_plan* p, int what)
         case 2: return p->smem_bytes;
         case 3: return p->ctas_per_sm;
         case 4: return p->num_sms;
-        case 5: return kFT;
+        case 5: return plan_tile_frames(p);
+        case 6: return p->use_ws;
         default: return -1;
     }
 }
@@ -317,7 +341,7 @@ extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* ns
     long long n = 0;
     for (int u = 0; u < batch; ++u) {
         const long long T = b200fe_num_frames(p, nsamp[u]);
-        for (long long f0 = 0; f0 < T; f0 += kFT, ++n)
+        for (long long f0 = 0; f0 < T; f0 += plan_tile_frames(p), ++n)
             if (table && n < capacity) { table[2 * n] = u; table[2 * n + 1] = (int)f0; }
     }
     if (n > 0x7fffffffLL) return fail(B200FE_EINVAL, "build_tile_table: too many tiles");
@@ -412,7 +436,9 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.masks = (g->n_freq_masks + g->n_time_masks) > 0 ? g->d_masks : nullptr;
     a.n_fmask = g->n_freq_masks; a.n_tmask = g->n_time_masks; a.mask_zero = g->mask_zero;
     a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds; a.n_cls = n_cls;
-    a.tiles_per_utt = (g->max_frames + kFT - 1) / kFT;
+    const bool ws = p->use_ws != 0;
+    const int tile_ft = plan_tile_frames(p);
+    a.tiles_per_utt = (g->max_frames + tile_ft - 1) / tile_ft;
     const bool compact = g->d_tile_table != nullptr;
     if (compact && (!g->d_work_counter || g->n_tiles < 0)) return fail(B200FE_EINVAL, "fbank_fused: a tile table needs n_tiles and d_work_counter");
     const long long ntiles = compact ? (long long)g->n_tiles : (long long)a.tiles_per_utt * g->batch;
@@ -429,8 +455,8 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.tile_table = reinterpret_cast<const int2*>(g->d_tile_table);
     a.work_counter = g->d_work_counter;
     cudaStream_t st = (cudaStream_t)stream;
-    if (compact) {
-        CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
+    if (compact) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
+    if (compact || ws) {
         if (g->d_out) {
             const long long per_utt = (long long)g->max_frames * p->nmel;
             dim3 zg((unsigned)((per_utt + 8191) / 8192), (unsigned)g->batch);
@@ -439,8 +465,14 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         }
         if (ntiles == 0) return B200FE_OK;
     }
-    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm));
     void* kargs[] = {(void*)&a};
+    if (ws) {
+        // persistent, one CTA per SM: FFT warps / epilogue warps / producer warp hand tiles over through mbarrier rings
+        const int wgrid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms));
+        CUDA_TRY(cudaLaunchKernel(ws_kernel(g->d_peak != nullptr, i16), dim3(wgrid), dim3(kWsThreads), kargs, (size_t)p->ws_smem_bytes, st));
+        return B200FE_OK;
+    }
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm));
     CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
     return B200FE_OK;
 }

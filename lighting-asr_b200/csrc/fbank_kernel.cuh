@@ -439,6 +439,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     const float dc_coef = a.remove_dc ? (float)(1.0 - (double)a.preemph) : 0.0f;
     const bool zmask = a.mask_zero && a.masks != nullptr;
     const int nmask = a.n_fmask + a.n_tmask;
+    // statistics without SpecAugment row classes are reduced inside phase C (no staging write-back, no extra barrier)
+    const bool stats_fused = a.stats != nullptr && !zmask && (a.row_bounds == nullptr || a.n_cls <= 1) && nmel <= kThreads;
 
     // ---- tile scheduler ------------------------------------------------------------------------
     // Thread 0 resolves tile descriptors (id, utterance, first frame, frame count of the utterance) TWO tiles
@@ -681,7 +683,61 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         {
             float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * nmel : nullptr;
             const int nv = nvalid * nmel, nt = nrows * nmel;
-            if (nvalid > 0) {
+            if (nvalid > 0 && stats_fused) {
+                // Statistics mode without row classes: thread = (row part, column), element e = tid + k P with
+                // P = parts * nmel, so the copy-out stays coalesced AND every thread keeps one column: its sum and
+                // sum of squares (about a pivot, fp32 over <= 11 rows) never leave registers; one fp64 atomic pair
+                // per thread and tile.  No write-back to the staging tile, no extra barrier.
+                const bool affine = a.cm_mean != nullptr;
+                const bool lg = a.use_log != 0;
+                const float lf = a.log_floor;
+                const int parts = kThreads / nmel, P = parts * nmel;
+                if (tid < P) {
+                    const int rg = tid / nmel, col = tid - rg * nmel;
+                    const float* sp = outs + tid + rg;                  // staging index of e = tid: e + row
+                    const float cm = affine ? s_mean[col] : 0.f, ci = affine ? s_istd[col] : 1.f;
+                    float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+                    int cnt = 0;
+                    if (kStaticMel && nvalid == kFT) {
+                        constexpr int kIt = (kFT * B200FE_STATIC_NMEL + (kThreads / B200FE_STATIC_NMEL) * B200FE_STATIC_NMEL - 1) /
+                                            ((kThreads / B200FE_STATIC_NMEL) * B200FE_STATIC_NMEL);
+                        float x[kIt];
+#pragma unroll
+                        for (int k = 0; k < kIt; ++k) x[k] = (tid + k * P < nv) ? sp[k * (P + parts)] : 1.0f;
+#pragma unroll
+                        for (int k = 0; k < kIt; ++k) {
+                            if (lg) x[k] = fast_log(fmaxf(x[k], lf));
+                            if (affine) x[k] = (x[k] - cm) * ci;
+                        }
+                        pivot = x[0];
+#pragma unroll
+                        for (int k = 0; k < kIt; ++k) {
+                            if (tid + k * P < nv) {
+                                if (obase) obase[tid + k * P] = x[k];
+                                const float dd = x[k] - pivot;
+                                s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
+                            }
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int e = tid, k = 0; e < nv; e += P, ++k) {
+                            float x = sp[k * (P + parts)];
+                            if (lg) x = fast_log(fmaxf(x, lf));
+                            if (affine) x = (x - cm) * ci;
+                            if (obase) obase[e] = x;
+                            if (cnt == 0) pivot = x;
+                            const float dd = x - pivot;
+                            s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
+                        }
+                    }
+                    if (cnt > 0) {
+                        double* sb = a.stats + (long long)utt * a.stats_stride;
+                        const double dp = (double)pivot, d1 = (double)s1;
+                        atomicAdd(sb + col, d1 + cnt * dp);
+                        atomicAdd(sb + (long long)a.n_cls * nmel + col, (double)s2 + 2.0 * dp * d1 + cnt * dp * dp);
+                    }
+                }
+            } else if (nvalid > 0) {
                 const bool wb = a.stats != nullptr;       // statistics read the transformed values back
                 const bool affine = a.cm_mean != nullptr;
                 const float lf = a.log_floor;
@@ -756,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             }
         }
         if (a.out_len != nullptr && f0 == 0 && nrows > 0 && tid == 0) a.out_len[utt] = g.T;
-        if (a.stats != nullptr && nvalid > 0) {
+        if (a.stats != nullptr && nvalid > 0 && !stats_fused) {
             // Column statistics of what phase C wrote back into the staging tile.  thread = (column j, row
             // part); fp32 partial sums over <= 11 rows, flushed with fp64 atomics.
             __syncthreads();

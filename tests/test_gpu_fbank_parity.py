@@ -295,3 +295,32 @@ def test_c_abi_argument_errors(lasr_b200):
         lasr_b200.GpuFbankFrontend()(torch.zeros((1, 16000), device="cuda:0", dtype=torch.float64), np.array([16000]))
     with pytest.raises(ValueError):
         lasr_b200.GpuFbankFrontend()(torch.zeros((1, 16000), device="cuda:0"), np.array([16001]))
+
+
+def test_warp_specialised_kernel_matches_default(lasr_b200, monkeypatch):
+    """The opt-in warp-specialised kernel (B200FE_WS=1, fbank_ws_kernel.cuh) shares phase A with the default kernel:
+    features bit-identical on ragged float / int16 / unaligned input, statistics equal to fp64 rounding."""
+    rng = np.random.default_rng(11)
+    n = np.round(rng.uniform(0.3, 5.0, 20) * 16000).astype(np.int64)
+    n[0] = 401; n[1] = 400 + 160 * 23; n[2] = 400 + 160 * 24; n[3] = 559
+    wavs = [rng.uniform(-0.5, 0.5, k) for k in n]
+    wav, n = _pad_batch(wavs, "cuda:0")
+    wi = torch.round(wav * 32767).to(torch.int16)
+
+    def run():
+        fe = lasr_b200.GpuFbankFrontend()
+        fp = lasr_b200.GpuFbankFrontend(peak_norm=True)
+        fu = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+        res = [fe(wav, n)[0], fe(wi, n)[0], fe(wav[:, 1:], n - 1)[0], fp(wav, n)[0], fu(wav, n)[0], fe.accumulate_stats(wav, n)]
+        torch.cuda.synchronize()
+        info = fe.plan(wav.device).lib.b200fe_plan_info(fe.plan(wav.device).handle, 6)
+        return [r.cpu().numpy() for r in res], info
+
+    base, ws0 = run()
+    monkeypatch.setenv("B200FE_WS", "1")
+    alt, ws1 = run()
+    assert ws0 == 0 and ws1 == 1
+    for k in range(4):
+        assert np.array_equal(base[k], alt[k]), k
+    assert np.allclose(base[4], alt[4], rtol=0, atol=1e-5)
+    assert np.allclose(base[5], alt[5], rtol=1e-9, atol=0)
