@@ -161,6 +161,14 @@ int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_
 int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                       float* h_feats, void* stream);
 
+/* Ragged row copy in ONE kernel launch: row u = d_nbytes[u] bytes from src + d_src_off[u] to dst + d_dst_off[u] (byte
+ * offsets; the three arrays are device-readable, max_bytes >= every d_nbytes[u]).  Either side may be PINNED host memory
+ * (under unified addressing the SMs read / write it over PCIe), which replaces the per-utterance cudaMemcpyAsync of
+ * b200fe_h2d_ragged / b200fe_d2h_ragged -- the GPU-side counterpart of the reference's collate copy loop
+ * (lasr/data/dataset.py:8-22, one numpy row assignment per utterance).  16-byte aligned rows move as 128-bit accesses. */
+int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
+                       const long long* d_nbytes, int batch, long long max_bytes, void* stream);
+
 /* Turns per-utterance statistics into (a) utterance CMVN vectors and (b) the SpecAugment mean
  * fills of R/lasr/utils/specaugment.py:71-74,102-105 (each mask is filled with the mean of the
  * CURRENT array, i.e. after CMVN and after all earlier masks), evaluated in closed form from the

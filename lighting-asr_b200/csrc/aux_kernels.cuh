@@ -67,6 +67,47 @@ __global__ void __launch_bounds__(256) zero_pad_kernel(float* __restrict__ out, 
     }
 }
 
+// Ragged row copy by a kernel: row u = nbytes[u] bytes from src + src_off[u] to dst + dst_off[u].  Either side may be
+// pinned (mapped) host memory: the SMs then read / write it over PCIe directly, so a whole batch of variable-length
+// utterances moves in ONE launch instead of one DMA set-up per utterance (measured on B200 / PCIe 5 x16: 256 x 1.15 MB
+// cudaMemcpyAsync 46.7 GB/s, one contiguous copy 55.5 GB/s).  Persistent grid over (row, 32 kB chunk) pairs.
+constexpr int kCopyThreads = 256;
+constexpr int kCopyChunk = kCopyThreads * 16 * 8;
+__global__ void __launch_bounds__(kCopyThreads) ragged_copy_kernel(const char* __restrict__ src, const long long* __restrict__ src_off,
+                                                                   char* __restrict__ dst, const long long* __restrict__ dst_off,
+                                                                   const long long* __restrict__ nbytes, int B, int chunks_per_row)
+{
+    const long long total = (long long)B * chunks_per_row;
+    for (long long v = blockIdx.x; v < total; v += gridDim.x) {
+        const int u = (int)(v / chunks_per_row);
+        const long long c0 = (v - (long long)u * chunks_per_row) * kCopyChunk;
+        const long long nb = nbytes[u];
+        if (c0 >= nb) continue;
+        const char* s = src + src_off[u];
+        char* d = dst + dst_off[u];
+        const long long lim = min(nb, c0 + (long long)kCopyChunk);
+        if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+            uint4 vreg[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const long long off = c0 + ((long long)r * kCopyThreads + threadIdx.x) * 16;
+                if (off + 16 <= lim) vreg[r] = __ldcs(reinterpret_cast<const uint4*>(s + off));
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const long long off = c0 + ((long long)r * kCopyThreads + threadIdx.x) * 16;
+                if (off + 16 <= lim) __stcs(reinterpret_cast<uint4*>(d + off), vreg[r]);
+                else if (off < lim) for (long long q = off; q < lim; ++q) d[q] = s[q];      // < 16 trailing bytes of the row
+            }
+        } else if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)nb) & 3) == 0) {
+            for (long long off = c0 + threadIdx.x * 4; off < lim; off += kCopyThreads * 4)
+                *reinterpret_cast<unsigned*>(d + off) = *reinterpret_cast<const unsigned*>(s + off);
+        } else {
+            for (long long off = c0 + threadIdx.x; off < lim; off += kCopyThreads) d[off] = s[off];
+        }
+    }
+}
+
 // int16 PCM abs-max: peak = max |s16| / 2^15 (what max |x| is after soundfile's conversion)
 __global__ void __launch_bounds__(256) absmax_i16_kernel(const short* __restrict__ wav, long long stride, const long long* __restrict__ offsets,
                                                          const long long* __restrict__ nsamp, float* __restrict__ peak)

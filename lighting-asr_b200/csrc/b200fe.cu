@@ -388,6 +388,29 @@ extern "C" int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const lo
     return B200FE_OK;
 }
 
+extern "C" int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
+                                  const long long* d_nbytes, int batch, long long max_bytes, void* stream)
+{
+    if (!src || !dst || !d_src_off || !d_dst_off || !d_nbytes || batch < 0 || max_bytes < 0) return fail(B200FE_EINVAL, "copy_ragged: bad argument");
+    if (batch == 0 || max_bytes == 0) return B200FE_OK;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long cpr = (max_bytes + kCopyChunk - 1) / kCopyChunk;
+    if (cpr > 0x7fffffffLL) return fail(B200FE_EINVAL, "copy_ragged: row too long");
+    const long long total = cpr * batch;
+    // Few CTAs on purpose: PCIe needs ~100 kB in flight (16 CTAs x 32 kB), and SMs that wait on system-memory reads slow
+    // co-resident compute kernels down (measured), so the copy is confined to a handful of SMs.
+    static const int env_ctas = []() { const char* e = getenv("B200FE_COPY_CTAS"); return e ? atoi(e) : 0; }();
+    const int want = env_ctas > 0 ? env_ctas : 16;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(total, (long long)want));
+    (void)sms;
+    ragged_copy_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(static_cast<const char*>(src), d_src_off, static_cast<char*>(dst), d_dst_off,
+                                                                        d_nbytes, batch, (int)cpr);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                                  float* h_feats, void* stream)
 {

@@ -172,6 +172,10 @@ class GpuFbankFrontend(torch.nn.Module):
                                          l2_chunk_bytes=l2_chunk_bytes, compact_tiles=compact_tiles)
         self.l2_chunk_bytes = l2_chunk_bytes      # None: one launch per batch (measured fastest); else utterance groups
         self.compact_tiles = compact_tiles
+        # extract_host: one copy kernel per group over pinned host memory instead of one DMA per utterance
+        self.kernel_h2d = True
+        self.overlap_calls = True       # extract_host: the H2D copies of the next call may start before this call's D2H tail ends
+        self.kernel_d2h = True
         self._plans = {}
         self._host_cache = {}
         self.launch_count = 0           # kernels launched by this object (bench.py reports it)
@@ -458,7 +462,27 @@ class GpuFbankFrontend(torch.nn.Module):
 
     # -- host-to-host path: the drop-in for the reference's collate_fn (features back on the host) --
     @torch.no_grad()
-    def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True):
+    @staticmethod
+    def pack_host(wavs, dtype=torch.float32, pin=True):
+        """Packs a list of 1-D utterances (what the reference's collate loop receives, dataset.py:190-206) into ONE
+        host buffer with 16-byte aligned starts -- the layout extract_host moves with a single DMA per group.
+        Returns (packed CPU tensor, lengths int64, offsets int64)."""
+        esz = torch.empty((), dtype=dtype).element_size()
+        al = 16 // esz
+        lens = np.array([len(w) for w in wavs], dtype=np.int64)
+        offs = np.zeros(len(wavs), dtype=np.int64)
+        np.cumsum((lens[:-1] + al - 1) // al * al, out=offs[1:])
+        total = int(offs[-1] + (lens[-1] + al - 1) // al * al) if len(wavs) else 0
+        buf = torch.zeros((total,), dtype=dtype)
+        if pin:
+            buf = buf.pin_memory()
+        view = buf.numpy()
+        for w, o, k in zip(wavs, offs, lens):
+            view[o:o + k] = w
+        return buf, lens, offs
+
+    @torch.no_grad()
+    def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True, wav_offsets=None):
         """Pipelined H2D copy -> fused kernels -> D2H copy over utterance groups on three streams.
 
         wav_host: zero-padded float32 CPU tensor (B, Nmax), ideally pinned (what batch_list builds).
@@ -468,24 +492,35 @@ class GpuFbankFrontend(torch.nn.Module):
         AudioDataSet.collate_fn hands to the trainer, dataset.py:222-232), else CUDA tensors (the
         case where the encoder consumes them in place)."""
         dev = torch.device(device)
-        B, Nmax = wav_host.shape
-        if wav_host.dtype not in (torch.float32, torch.int16) or wav_host.stride(1) != 1:
-            raise ValueError("wav_host must be a float32 or int16 tensor with contiguous rows")
+        packed_in = wav_offsets is not None
+        if wav_host.dtype not in (torch.float32, torch.int16) or wav_host.stride(-1) != 1 or wav_host.dim() != (1 if packed_in else 2):
+            raise ValueError("wav_host must be a float32 or int16 tensor, (B, Nmax) with contiguous rows or 1-D with wav_offsets")
         esz = wav_host.element_size()
         al = 16 // esz                                    # utterance starts are 16-byte aligned in the packed buffer
         len_host = np.ascontiguousarray(np.asarray(wav_len, dtype=np.int64).reshape(-1))
+        B = len(len_host)
+        Nmax = int(wav_host.shape[-1])
         T_host, win = self.frame_counts(len_host)
         if (len_host < win).any():
             raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
         Tmax, D = int(T_host.max()), self.num_mel_bins
-        offs = np.zeros(B, dtype=np.int64)
-        np.cumsum((len_host[:-1] + al - 1) // al * al, out=offs[1:])
-        total = int(offs[-1] + (len_host[-1] + al - 1) // al * al)
-        key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype)
+        if packed_in:
+            # packed host input (pack_host): the device buffer mirrors it, one DMA per utterance group
+            offs = np.ascontiguousarray(np.asarray(wav_offsets, dtype=np.int64).reshape(-1))
+            if (offs % al != 0).any() or (np.diff(offs) < len_host[:-1]).any() or offs[-1] + len_host[-1] > Nmax:
+                raise ValueError("wav_offsets must be ascending, 16-byte aligned and leave room for every utterance")
+            total = Nmax
+        else:
+            offs = np.zeros(B, dtype=np.int64)
+            np.cumsum((len_host[:-1] + al - 1) // al * al, out=offs[1:])
+            total = int(offs[-1] + (len_host[-1] + al - 1) // al * al)
+        key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype, packed_in)
         c = self._host_cache.get(key)
         if c is None:
             self._host_cache.clear()
-            c = dict(wav=torch.zeros((total + 64,), dtype=wav_host.dtype, device=dev),
+            # two staging buffers: the H2D copies of call k+1 overlap the compute / D2H tail of call k
+            c = dict(wavs=[torch.zeros((total + 64,), dtype=wav_host.dtype, device=dev) for _ in range(2)],
+                     wav_free=[None, None], turn=0,
                      feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
                      flen=torch.empty((B,), dtype=torch.int64, device=dev),
                      hfeats=torch.zeros((B, Tmax, D), dtype=torch.float32).pin_memory(),
@@ -497,9 +532,30 @@ class GpuFbankFrontend(torch.nn.Module):
         # rows to bring back per utterance: valid now, or valid in the previous batch held by the host buffer
         d2h_rows = np.ascontiguousarray(np.maximum(T_host, c["hrows"]).astype(np.int64))
         main = torch.cuda.current_stream(dev)
+        # Pinned host buffers are read / written by ONE copy kernel per group (b200fe_copy_ragged) instead of one DMA
+        # set-up per utterance; byte offsets and sizes of every row, device resident:
+        #   0: host row start   1: packed device start   2: valid bytes   3: feature block start   4: feature bytes to bring back
+        kh2d = self.kernel_h2d and wav_host.is_pinned() and not packed_in
+        kd2h = self.kernel_d2h and return_host
+        if kh2d or kd2h:
+            tab = np.stack([np.arange(B, dtype=np.int64) * ((0 if packed_in else wav_host.stride(0)) * esz), offs * esz, len_host * esz,
+                            np.arange(B, dtype=np.int64) * (Tmax * D * 4), d2h_rows * (D * 4)])
+            tab_dev = torch.from_numpy(np.ascontiguousarray(tab)).to(dev, non_blocking=True)
+            tptr = tab_dev.data_ptr()
+            c["tabs"] = (c.get("tabs", ()) + (tab_dev,))[-2:]        # alive until the copy kernels of this call have run
+            ev_tab = torch.cuda.Event()
+            ev_tab.record(main)
         s_in, s_out = c["s_in"], c["s_out"]
-        s_in.wait_stream(main)
+        slot = c["turn"] & 1
+        c["turn"] += 1
+        dwav = c["wavs"][slot]
+        if not self.overlap_calls:
+            s_in.wait_stream(main)
+        elif c["wav_free"][slot] is not None:
+            s_in.wait_event(c["wav_free"][slot])          # the call that last read this staging buffer has finished computing
         s_out.wait_stream(main)
+        if kh2d:
+            s_in.wait_event(ev_tab)
         # utterance groups of ~group_bytes of valid audio
         bounds = [0]
         acc = 0
@@ -512,24 +568,44 @@ class GpuFbankFrontend(torch.nn.Module):
             bounds.append(B)
         self.h2d_bytes = self.d2h_bytes = 0
         for b0, b1 in zip(bounds[:-1], bounds[1:]):
-            _lib.check(lib.b200fe_h2d_ragged(C.c_void_p(wav_host.data_ptr() + b0 * wav_host.stride(0) * esz), wav_host.stride(0),
-                                             C.c_void_p(len_host.ctypes.data + b0 * 8), C.c_void_p(offs.ctypes.data + b0 * 8), b1 - b0,
-                                             _ptr(c["wav"]), esz, C.c_void_p(s_in.cuda_stream)), "b200fe_h2d_ragged")
+            if packed_in:
+                o0 = int(offs[b0])
+                o1 = int(offs[b1]) if b1 < B else int(offs[-1] + len_host[-1])
+                with torch.cuda.stream(s_in):
+                    dwav[o0:o1].copy_(wav_host[o0:o1], non_blocking=True)
+            elif kh2d:
+                _lib.check(lib.b200fe_copy_ragged(C.c_void_p(wav_host.data_ptr()), C.c_void_p(tptr + (0 * B + b0) * 8), _ptr(dwav),
+                                                  C.c_void_p(tptr + (1 * B + b0) * 8), C.c_void_p(tptr + (2 * B + b0) * 8), b1 - b0,
+                                                  int(len_host[b0:b1].max()) * esz, C.c_void_p(s_in.cuda_stream)), "b200fe_copy_ragged")
+                self.launch_count += 1
+            else:
+                _lib.check(lib.b200fe_h2d_ragged(C.c_void_p(wav_host.data_ptr() + b0 * wav_host.stride(0) * esz), wav_host.stride(0),
+                                                 C.c_void_p(len_host.ctypes.data + b0 * 8), C.c_void_p(offs.ctypes.data + b0 * 8), b1 - b0,
+                                                 _ptr(dwav), esz, C.c_void_p(s_in.cuda_stream)), "b200fe_h2d_ragged")
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
-            self.h2d_bytes += int(len_host[b0:b1].sum()) * esz + (b1 - b0) * 16
+            self.h2d_bytes += ((o1 - o0) * esz if packed_in else int(len_host[b0:b1].sum()) * esz) + (b1 - b0) * 16
             main.wait_event(ev_in)
-            self.forward(c["wav"], len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1],
+            self.forward(dwav, len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1],
                          wav_offsets=offs[b0:b1])
             if return_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
                 s_out.wait_event(ev_c)
-                _lib.check(lib.b200fe_d2h_ragged(C.c_void_p(c["feats"].data_ptr() + b0 * Tmax * D * 4), D, Tmax,
-                                                 C.c_void_p(d2h_rows.ctypes.data + b0 * 8), b1 - b0,
-                                                 C.c_void_p(c["hfeats"].data_ptr() + b0 * Tmax * D * 4), C.c_void_p(s_out.cuda_stream)),
-                           "b200fe_d2h_ragged")
+                if kd2h:
+                    _lib.check(lib.b200fe_copy_ragged(_ptr(c["feats"]), C.c_void_p(tptr + (3 * B + b0) * 8), C.c_void_p(c["hfeats"].data_ptr()),
+                                                      C.c_void_p(tptr + (3 * B + b0) * 8), C.c_void_p(tptr + (4 * B + b0) * 8), b1 - b0,
+                                                      int(d2h_rows[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
+                    self.launch_count += 1
+                else:
+                    _lib.check(lib.b200fe_d2h_ragged(C.c_void_p(c["feats"].data_ptr() + b0 * Tmax * D * 4), D, Tmax,
+                                                     C.c_void_p(d2h_rows.ctypes.data + b0 * 8), b1 - b0,
+                                                     C.c_void_p(c["hfeats"].data_ptr() + b0 * Tmax * D * 4), C.c_void_p(s_out.cuda_stream)),
+                               "b200fe_d2h_ragged")
                 self.d2h_bytes += int(d2h_rows[b0:b1].sum()) * D * 4
+        ev_free = torch.cuda.Event()
+        ev_free.record(main)
+        c["wav_free"][slot] = ev_free
         if return_host:
             with torch.cuda.stream(s_out):
                 c["hlen"].copy_(c["flen"], non_blocking=True)

@@ -324,3 +324,67 @@ def test_warp_specialised_kernel_matches_default(lasr_b200, monkeypatch):
         assert np.array_equal(base[k], alt[k]), k
     assert np.allclose(base[4], alt[4], rtol=0, atol=1e-5)
     assert np.allclose(base[5], alt[5], rtol=1e-9, atol=0)
+
+
+def test_extract_host_layouts_and_copy_engines(lasr_b200):
+    """extract_host gives the same bits whatever moves the data: padded or packed (pack_host) pinned input, copy kernel
+    (b200fe_copy_ragged over mapped host memory) or per-utterance DMA, calls overlapped or not, float32 or int16."""
+    rng = np.random.default_rng(21)
+    n = np.round(rng.uniform(0.2, 3.0, 12) * 16000).astype(np.int64)
+    n[0] = 400; n[5] = 16001; n[7] = 16003
+    wavs = [rng.uniform(-0.5, 0.5, k).astype(np.float32) for k in n]
+    wav, n = _pad_batch(wavs, "cuda:0", align=1)             # odd row stride: unaligned rows for the copy kernel too
+    for dtype in (torch.float32, torch.int16):
+        srcs = wavs if dtype == torch.float32 else [np.round(w * 32767).astype(np.int16) for w in wavs]
+        dev_in = wav if dtype == torch.float32 else torch.round(wav * 32767).to(torch.int16)
+        for kw in ({}, {"cmvn": "utt_meanvar"}):
+            fe = lasr_b200.GpuFbankFrontend(**kw)
+            ref, rlen = fe(dev_in, n)
+            host = dev_in.cpu().pin_memory()
+            pk, lens, offs = lasr_b200.GpuFbankFrontend.pack_host(srcs, dtype=dtype)
+            assert np.array_equal(lens, n) and (offs % (16 // pk.element_size()) == 0).all()
+            for kh, kd, ov in ((True, True, True), (False, False, False), (True, False, True), (False, True, False)):
+                fe.kernel_h2d, fe.kernel_d2h, fe.overlap_calls = kh, kd, ov
+                for _ in range(3):                                           # back-to-back calls exercise both staging buffers
+                    hf, hl = fe.extract_host(host, n, group_bytes=150000)
+                torch.cuda.synchronize()
+                assert torch.equal(hf, ref.cpu()) and torch.equal(hl, rlen.cpu()), (dtype, kw, kh, kd, ov)
+                for _ in range(3):
+                    hf, hl = fe.extract_host(pk, lens, wav_offsets=offs, group_bytes=150000)
+                torch.cuda.synchronize()
+                assert torch.equal(hf, ref.cpu()) and torch.equal(hl, rlen.cpu()), (dtype, kw, kh, kd, ov, "packed")
+                df, dl = fe.extract_host(pk, lens, wav_offsets=offs, return_host=False)
+                torch.cuda.synchronize()
+                assert torch.equal(df, ref) and torch.equal(dl, rlen)
+    with pytest.raises(ValueError):
+        fe.extract_host(pk, lens, wav_offsets=offs + 1)
+
+
+def test_copy_ragged_c_abi(lasr_b200):
+    """b200fe_copy_ragged: rows of arbitrary byte length / alignment, device <-> pinned host, exact bytes and nothing else."""
+    import ctypes as C
+    lib = lasr_b200._lib.load()
+    rng = np.random.default_rng(5)
+    B = 9
+    nb = np.array([0, 1, 15, 16, 17, 4096, 32768, 32769, 100003], dtype=np.int64)
+    src_off = np.zeros(B, dtype=np.int64); dst_off = np.zeros(B, dtype=np.int64)
+    src_off[1:] = np.cumsum(nb[:-1] + 32)[:]; dst_off[1:] = np.cumsum(nb[:-1] + 48)[:]
+    src_off[3] += 3; dst_off[4] += 4                      # byte-misaligned and 4-byte aligned rows
+    src_off = (src_off // 16 * 16); dst_off = (dst_off // 16 * 16); src_off[3] += 3; dst_off[3] += 3; src_off[4] += 4; dst_off[4] += 8
+    total_s, total_d = int(src_off[-1] + nb[-1] + 64), int(dst_off[-1] + nb[-1] + 64)
+    data = torch.from_numpy(rng.integers(0, 256, total_s, dtype=np.uint8))
+    tab = torch.from_numpy(np.stack([src_off, dst_off, nb])).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for src, mk in ((data.pin_memory(), lambda: torch.full((total_d,), 7, dtype=torch.uint8, device="cuda")),      # host -> device
+                    (data.cuda(), lambda: torch.full((total_d,), 7, dtype=torch.uint8).pin_memory())):              # device -> host
+        dst = mk()
+        rc = lib.b200fe_copy_ragged(C.c_void_p(src.data_ptr()), C.c_void_p(tab.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    C.c_void_p(tab.data_ptr() + B * 8), C.c_void_p(tab.data_ptr() + 2 * B * 8), B, int(nb.max()), st)
+        assert rc == 0, lib.b200fe_last_error()
+        torch.cuda.synchronize()
+        want = np.full(total_d, 7, dtype=np.uint8)
+        s_np = data.numpy()
+        for u in range(B):
+            want[dst_off[u]: dst_off[u] + nb[u]] = s_np[src_off[u]: src_off[u] + nb[u]]
+        assert np.array_equal(dst.cpu().numpy(), want)
+    assert lib.b200fe_copy_ragged(None, None, None, None, None, 1, 1, st) == -1
