@@ -161,6 +161,17 @@ int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_
 int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                       float* h_feats, void* stream);
 
+/* Encoder source mask without a host round trip.  The reference builds it on the CPU from `xlen.tolist()`
+ * (lasr/model/e2e_ctc_att/e2e_base.py:19-20 -> make_pad_mask, lasr/utils/mask.py:5-45, then `~mask`, unsqueeze(-2)):
+ *   subsample == 1:  d_mask [batch][1][max_frames]          = (t < frames[b])          -- the mask the encoder receives
+ *   subsample == 4:  d_mask [batch][1][((T-1)/2-1)/2]       = (4 i < frames[b])        -- what Conv2dSubsampling returns
+ *                    (x_mask[:, :, :-2:2][:, :, :-2:2], lasr/modules/net/transformer/subsampling.py:60)
+ * d_len holds frame counts (the batch dict's wav_len) or, with len_is_samples != 0, sample counts (frames derived with the
+ * plan's window / shift, TA:63-67).  d_out_len (optional) = number of true cells per utterance (hs_len of
+ * E2E_CTC_ATT.subfunction, e2e_base.py:47-49).  Masks are bytes (torch.bool layout). */
+int b200fe_src_mask(const b200fe_plan* plan, const long long* d_len, int len_is_samples, int batch, int max_frames,
+                    int subsample, unsigned char* d_mask, long long* d_out_len, void* stream);
+
 /* Ragged row copy in ONE kernel launch: row u = d_nbytes[u] bytes from src + d_src_off[u] to dst + d_dst_off[u] (byte
  * offsets; the three arrays are device-readable, max_bytes >= every d_nbytes[u]).  Either side may be PINNED host memory
  * (under unified addressing the SMs read / write it over PCIe), which replaces the per-utterance cudaMemcpyAsync of

@@ -52,7 +52,7 @@ class WarpArgs(C.Structure):
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table",
-    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
+    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
 ]
 
 _lib = None
@@ -108,6 +108,8 @@ def load(build_if_missing=True):
     lib.b200fe_d2h_ragged.restype = C.c_int
     lib.b200fe_copy_ragged.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_ll, C.c_void_p]
     lib.b200fe_copy_ragged.restype = C.c_int
+    lib.b200fe_src_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.b200fe_src_mask.restype = C.c_int
     lib.b200fe_postpass.argtypes = [C.c_void_p, C.POINTER(PostArgs), C.c_void_p]
     lib.b200fe_postpass.restype = C.c_int
     lib.b200fe_time_warp.argtypes = [C.c_void_p, C.POINTER(WarpArgs), C.c_void_p]

@@ -108,6 +108,25 @@ __global__ void __launch_bounds__(kCopyThreads) ragged_copy_kernel(const char* _
     }
 }
 
+// Encoder source mask on the device (replaces the host round trip `make_pad_mask(xlen.tolist(), max_length=T)`,
+// lasr/model/e2e_ctc_att/e2e_base.py:19-20 -> lasr/utils/mask.py:5-45): mask[b][0][i] = (i * step < frames[b]) for
+// i < Tout, where step = 1 is the encoder input mask and step = 4, Tout = ((T-1)/2-1)/2 is what Conv2dSubsampling
+// hands on (x_mask[:, :, :-2:2][:, :, :-2:2], lasr/modules/net/transformer/subsampling.py:60).  out_len[b] = number of
+// true cells (E2E_CTC_ATT.subfunction, e2e_base.py:47-49).  frames come from sample counts when win > 0.
+__global__ void __launch_bounds__(256) src_mask_kernel(const long long* __restrict__ len, int win, int shift, int Tout, int step,
+                                                       unsigned char* __restrict__ mask, long long* __restrict__ out_len)
+{
+    const int b = blockIdx.y;
+    long long T = len[b];
+    if (win > 0) T = T >= win ? 1 + (T - win) / shift : 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < Tout; i += gridDim.x * 256)
+        mask[(long long)b * Tout + i] = ((long long)i * step < T) ? 1 : 0;
+    if (out_len != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long cnt = T <= 0 ? 0 : (T + step - 1) / step;
+        out_len[b] = cnt < Tout ? cnt : Tout;
+    }
+}
+
 // int16 PCM abs-max: peak = max |s16| / 2^15 (what max |x| is after soundfile's conversion)
 __global__ void __launch_bounds__(256) absmax_i16_kernel(const short* __restrict__ wav, long long stride, const long long* __restrict__ offsets,
                                                          const long long* __restrict__ nsamp, float* __restrict__ peak)

@@ -388,6 +388,22 @@ extern "C" int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const lo
     return B200FE_OK;
 }
 
+extern "C" int b200fe_src_mask(const b200fe_plan* plan, const long long* d_len, int len_is_samples, int batch, int max_frames,
+                               int subsample, unsigned char* d_mask, long long* d_out_len, void* stream)
+{
+    if (!d_len || batch <= 0 || max_frames < 0) return fail(B200FE_EINVAL, "src_mask: bad argument");
+    if (len_is_samples && !plan) return fail(B200FE_EINVAL, "src_mask: a plan is needed to turn sample counts into frame counts");
+    if (subsample != 1 && subsample != 4) return fail(B200FE_EINVAL, "src_mask: subsample must be 1 (encoder input) or 4 (after Conv2dSubsampling)");
+    const int Tout = subsample == 1 ? max_frames : (max_frames >= 7 ? ((max_frames - 1) / 2 - 1) / 2 : 0);
+    if (Tout > 0 && !d_mask) return fail(B200FE_EINVAL, "src_mask: mask buffer missing");
+    if (Tout == 0 && !d_out_len) return B200FE_OK;
+    dim3 grid((unsigned)std::max(1, std::min(64, (Tout + 255) / 256)), (unsigned)batch);
+    src_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_len, len_is_samples ? plan->win : 0, len_is_samples ? plan->shift : 1, Tout, subsample,
+                                                            d_mask, d_out_len);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
                                   const long long* d_nbytes, int batch, long long max_bytes, void* stream)
 {

@@ -114,6 +114,25 @@ def main():
     sg["pil_cases"] = np.array(pil_cases)
     sg["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(OUT, "specaug_reference.npz"), **sg)
+    # ---- encoder masks: make_pad_mask / Conv2dSubsampling's mask slicing / subfunction (row F2) ----
+    from lasr.utils.mask import make_pad_mask
+    mk = {}
+    mcases = []
+    rs = np.random.RandomState(3)
+    for ci, (lens, T) in enumerate((([5, 3, 2], 5), ([1, 7, 8, 6], 8), ([998] * 3 + [1], 998), (list(rs.randint(1, 3499, 16)), 3498),
+                                    ([11, 12, 13, 14, 15, 16], 16), ([6, 2], 6), ([3498, 98], 3600))):
+        xlen = torch.tensor(lens)
+        src = (~make_pad_mask(xlen.tolist(), max_length=T)).unsqueeze(-2)
+        sub = src[:, :, :-2:2][:, :, :-2:2]
+        mk["c%d_len" % ci] = np.asarray(lens, dtype=np.int64)
+        mk["c%d_T" % ci] = np.asarray(T)
+        mk["c%d_pad" % ci] = make_pad_mask(xlen.tolist(), max_length=T).numpy()
+        mk["c%d_src" % ci] = src.numpy()
+        mk["c%d_sub" % ci] = sub.numpy()
+        mk["c%d_hslen" % ci] = torch.sum(sub.byte(), dim=-1).squeeze(-1).numpy()
+        mcases.append(ci)
+    mk["cases"] = np.asarray(mcases)
+    np.savez_compressed(os.path.join(OUT, "mask_reference.npz"), **mk)
     print("wrote", os.listdir(OUT))
 
 

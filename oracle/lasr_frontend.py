@@ -215,3 +215,22 @@ def frontend_chain(wav, peak_norm=False, cmvn="none", global_stats=None, specaug
     if specaug:
         x, rects = spec_augment_masks(x)
     return x, rects
+
+
+def make_pad_mask(lengths, max_length=-1):
+    """lasr/utils/mask.py:5-45 for the (B, Tmax) case: True where t >= lengths[b], Tmax = max(max(lengths), max_length)."""
+    lengths = [int(v) for v in lengths]
+    maxlen = max(max(lengths), int(max_length))
+    return np.arange(maxlen)[None, :] >= np.asarray(lengths)[:, None]
+
+
+def src_mask(xlen, max_frames):
+    """(~make_pad_mask(xlen.tolist(), max_length=T)).unsqueeze(-2)  (lasr/model/e2e_ctc_att/e2e_base.py:19-20)."""
+    return ~make_pad_mask(xlen, max_frames)[:, None, :]
+
+
+def subsampled_mask(xlen, max_frames):
+    """Conv2dSubsampling's returned mask x_mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:60) and
+    hs_len = sum(mask) (E2E_CTC_ATT.subfunction, e2e_base.py:47-49)."""
+    m = src_mask(xlen, max_frames)[:, :, :-2:2][:, :, :-2:2]
+    return m, m.sum(-1).squeeze(-1)

@@ -61,3 +61,38 @@ def test_batched_collate_matches_reference_batch_dict(lasr_b200):
         g = feats.cpu().numpy()
         assert int((np.abs(g - ref) > 1e-5 + 1e-4 * np.abs(ref)).sum()) <= 2
         assert np.array_equal(g == 0, ref == 0)                      # identical zero padding
+
+
+def test_device_masks_match_reference(lasr_b200):
+    """Row F2: the encoder masks from the device-resident frame counts equal the reference's host-built ones bit for bit
+    (goldens from lasr.utils.mask.make_pad_mask, the slicing of subsampling.py:60 and subfunction, e2e_base.py:47-49)."""
+    import os
+    import numpy as np
+    from oracle import lasr_frontend
+    mk = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mask_reference.npz"))
+    M = lasr_b200.mask
+    for ci in mk["cases"]:
+        lens, T = mk["c%d_len" % ci], int(mk["c%d_T" % ci])
+        d = torch.from_numpy(lens).cuda()
+        assert np.array_equal(M.make_pad_mask(d, max_length=T).cpu().numpy(), mk["c%d_pad" % ci])
+        src = M.src_mask(d, T)
+        assert src.dtype == torch.bool and np.array_equal(src.cpu().numpy(), mk["c%d_src" % ci])
+        sub, hs = M.subsampled_mask(d, T)
+        assert np.array_equal(sub.cpu().numpy(), mk["c%d_sub" % ci]) and np.array_equal(hs.cpu().numpy(), mk["c%d_hslen" % ci])
+    # straight from sample counts, chained after the front end without touching the host
+    rng = np.random.default_rng(2)
+    n = np.round(rng.uniform(0.1, 4.0, 9) * 16000).astype(np.int64)
+    fe = lasr_b200.GpuFbankFrontend()
+    wav = torch.zeros((9, int(n.max())), device="cuda")
+    feats, flen = fe(wav, n)
+    T = feats.shape[1]
+    m1, l1 = M.src_mask_from_samples(fe.plan(wav.device), torch.from_numpy(n).cuda(), T)
+    assert torch.equal(m1, M.src_mask(flen, T)) and torch.equal(l1, flen)
+    m4, l4 = M.src_mask_from_samples(fe.plan(wav.device), torch.from_numpy(n).cuda(), T, subsample=4)
+    want, whs = lasr_frontend.subsampled_mask(flen.cpu().numpy(), T)
+    assert np.array_equal(m4.cpu().numpy(), want) and np.array_equal(l4.cpu().numpy(), whs)
+    # (B, T, D)-shaped request, as make_pad_mask(lengths, xs, length_dim=1)
+    pad3 = M.make_pad_mask(flen, feats, 1)
+    assert pad3.shape == feats.shape and torch.equal(pad3[:, :, 0], ~M.src_mask(flen, T).squeeze(1))
+    with pytest.raises(RuntimeError):
+        M.src_mask(flen.cpu(), T)

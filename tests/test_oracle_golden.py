@@ -132,3 +132,15 @@ def test_cmvn_definition():
     assert np.allclose(mean, cat.mean(0)) and np.allclose(istd, 1 / cat.std(0))
     y = lasr_frontend.utterance_cmvn(feats[2])
     assert np.allclose(y.mean(0), 0, atol=1e-5) and np.allclose(y.std(0), 1, atol=1e-4)
+
+
+def test_masks_match_reference_fixture():
+    """make_pad_mask / the encoder source mask / Conv2dSubsampling's mask slicing / hs_len against the reference's own
+    functions (oracle/gen_golden.py: lasr.utils.mask.make_pad_mask + the slicing of subsampling.py:60)."""
+    mk = np.load(os.path.join(GOLD, "mask_reference.npz"))
+    for ci in mk["cases"]:
+        lens, T = mk["c%d_len" % ci], int(mk["c%d_T" % ci])
+        assert np.array_equal(lasr_frontend.make_pad_mask(lens, T), mk["c%d_pad" % ci])
+        assert np.array_equal(lasr_frontend.src_mask(lens, T), mk["c%d_src" % ci])
+        sub, hs = lasr_frontend.subsampled_mask(lens, T)
+        assert np.array_equal(sub, mk["c%d_sub" % ci]) and np.array_equal(hs, mk["c%d_hslen" % ci])
