@@ -29,14 +29,18 @@ WORKLOAD = "C2: 256 utts, 1-35 s @16 kHz (LibriSpeech-shaped), 80-dim kaldi fban
 SR = 16000.0
 
 
-def make_batch(seed, B=256):
-    """SURVEY 8(d) C2 inputs: seed 1 (+rank); durations uniform(1,35) s; N(0,0.1^2) clipped to +-1."""
-    rng = np.random.default_rng(seed)
-    n = np.round(rng.uniform(1.0, 35.0, B) * SR).astype(np.int64)
+def make_batch(rank=0, world=1, B=256):
+    """SURVEY 8(d) C2 inputs: durations uniform(1,35) s from seed 1, N(0,0.1^2) clipped to +-1.  With N ranks the global
+    batch is N x 256 utterances sharded per utterance, length-balanced (cmvn.shard_utterances): every rank
+    gets the same amount of audio to within one utterance, so the max-over-ranks time measures the machine, not the draw."""
+    import lasr_b200
+    n_all = np.round(np.random.default_rng(1).uniform(1.0, 35.0, B * world) * SR).astype(np.int64)
+    mine = lasr_b200.cmvn.shard_utterances(n_all, world)[rank] if world > 1 else np.arange(B)
+    n = n_all[mine]
     nmax = int((n.max() + 3) // 4 * 4)
-    wav = np.zeros((B, nmax), dtype=np.float32)
-    for i in range(B):
-        wav[i, : n[i]] = np.clip(rng.normal(0.0, 0.1, n[i]), -1.0, 1.0).astype(np.float32)
+    wav = np.zeros((len(n), nmax), dtype=np.float32)
+    for i, u in enumerate(mine):
+        wav[i, : n[i]] = np.clip(np.random.default_rng([1, int(u)]).normal(0.0, 0.1, n[i]), -1.0, 1.0).astype(np.float32)
     return wav, n
 
 
@@ -93,7 +97,7 @@ def reference_arm(args, rank, world, out):
     if rank != 0:
         return
     from oracle import cpu_baseline
-    wav, n = make_batch(1)
+    wav, n = make_batch()
     wavs = [wav[i, : n[i]].astype(np.float64) for i in range(len(n))]      # soundfile.read hands float64 to the transforms
     cores = os.cpu_count() or 1
     hours = float(n.sum()) / SR / 3600.0
@@ -109,7 +113,7 @@ def reference_arm(args, rank, world, out):
         pool.close()
         pool.join()
     val = hours * args.steps / dt
-    line = {"impl": "reference", "metric": "audio-hours/sec", "value": val, "unit": "audio-h/s", "n_gpus": 0,
+    line = {"impl": "reference", "metric": "audio-hours/sec", "value": val, "unit": "audio-h/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "inputs": "host float64 waveforms (what soundfile.read returns)"},
@@ -159,7 +163,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    wav_np, n = make_batch(1 + rank)
+    wav_np, n = make_batch(rank, world)
     B = len(n)
     fe = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
     T, _ = fe.frame_counts(n)
@@ -298,7 +302,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "audio_hours_per_gpu_step": hours,
                        "l2": "inputs (%.0f MB/step/GPU) exceed the 126 MB L2; no flush needed" % (wav_np.nbytes / 1e6),
-                       "parallelism": "utterance-sharded x%d, no data-path collective" % world},
+                       "parallelism": "global batch of %d utterances sharded per utterance (length-balanced) x%d, no data-path collective" % (256 * world, world)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "kernel": "fbank_fused_kernel<13,true,false,false> + zero_pad_kernel (every fused launch of one step)",
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": fused_per_step_ms,

@@ -21,6 +21,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _h2d(arr, dev):
+    """Small host -> device upload (length vectors, tile tables, mask descriptors).  Pageable on purpose: the driver
+    stages < 64 kB copies inline in the compute stream's command buffer, whereas a pinned source goes through the H2D
+    copy engine -- measured +15 us per step of DMA latency in front of the fused launch, and a stall behind the 32 MB
+    waveform copies inside extract_host (profiles/r01_e2e_copy_variants.txt)."""
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(dev, non_blocking=True)
+
+
 def _torch_window(window_type, size, blackman_coeff):
     """Same torch expressions as torchaudio (TA:86-113) so the table matches bit for bit."""
     import math
@@ -242,7 +250,7 @@ class GpuFbankFrontend(torch.nn.Module):
             off_host = np.ascontiguousarray(wav_offsets, dtype=np.int64)
             if (off_host % (16 // esz) != 0).any():
                 raise ValueError("wav_offsets must be multiples of 16 bytes")
-            off_dev = torch.from_numpy(off_host).to(dev, non_blocking=True)
+            off_dev = _h2d(off_host, dev)
             row_stride = int(wav.numel())
             row_elems = int(wav.numel())
         else:
@@ -256,7 +264,7 @@ class GpuFbankFrontend(torch.nn.Module):
             len_dev = wav_len.to(torch.int64).contiguous()
         else:
             len_host = np.asarray(wav_len, dtype=np.int64).reshape(-1)
-            len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+            len_dev = _h2d(len_host, dev)
         if len_host is not None:
             T_host, win = self.frame_counts(len_host)
             if (len_host < win).any():
@@ -300,8 +308,8 @@ class GpuFbankFrontend(torch.nn.Module):
                 n_f_, n_t_ = self.sa["n_freq_mask"], self.sa["n_time_mask"]
                 b_np = np.sort(m_np[:, n_f_:].reshape(B, -1), axis=1).astype(np.int32)
             n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
-            masks_dev = torch.from_numpy(m_np).to(dev, non_blocking=True)
-            bounds_dev = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev, non_blocking=True)
+            masks_dev = _h2d(m_np, dev)
+            bounds_dev = _h2d(b_np, dev)
         mean_fill = self.specaug and not self.replace_with_zero
         utt_cmvn = self.cmvn in ("utt_mean", "utt_meanvar")
         need_post = mean_fill or utt_cmvn
@@ -374,7 +382,7 @@ class GpuFbankFrontend(torch.nn.Module):
                 tab[:, 0] = np.repeat(np.arange(nb, dtype=np.int32), nt)
                 starts = np.cumsum(nt) - nt
                 tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(starts, nt)).astype(np.int32) * ft
-                tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
+                tab_dev = _h2d(tab, dev)
                 counter = torch.empty((1,), dtype=torch.int32, device=dev)
                 a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
                 self.launch_count += 2          # counter memset + zero-pad kernel
@@ -431,10 +439,10 @@ class GpuFbankFrontend(torch.nn.Module):
         m_np, b_np, w_np = _specaug.plan_batch(T_host, D, return_warp=True, **self.sa)
         n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
         n_cls = 2 * n_t + 1
-        masks_dev = torch.from_numpy(m_np).to(dev, non_blocking=True)
-        bounds_dev = torch.from_numpy(np.ascontiguousarray(b_np)).to(dev, non_blocking=True)
-        warp_dev = torch.from_numpy(np.ascontiguousarray(w_np)).to(dev, non_blocking=True)
-        len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+        masks_dev = _h2d(m_np, dev)
+        bounds_dev = _h2d(b_np, dev)
+        warp_dev = _h2d(w_np, dev)
+        len_dev = _h2d(len_host, dev)
         if out is not None:
             if out.shape != pre.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == pre.data_ptr():
                 raise ValueError("out must be a distinct contiguous float32 (B, Tmax, D) tensor")
@@ -624,7 +632,7 @@ class GpuFbankFrontend(torch.nn.Module):
         B, D = wav.shape[0], self.num_mel_bins
         len_host = np.asarray(wav_len.cpu() if torch.is_tensor(wav_len) else wav_len, dtype=np.int64).reshape(-1)
         T_host, win = self.frame_counts(len_host)
-        len_dev = torch.from_numpy(len_host).to(dev, non_blocking=True)
+        len_dev = _h2d(len_host, dev)
         if stats is None:
             stats = torch.zeros((2, D + 1), dtype=torch.float64, device=dev)
         peak = None
@@ -649,7 +657,7 @@ class GpuFbankFrontend(torch.nn.Module):
             tab = np.empty((tot, 2), dtype=np.int32)
             tab[:, 0] = np.repeat(np.arange(B, dtype=np.int32), nt)
             tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(nt) - nt, nt)).astype(np.int32) * ft
-            tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
+            tab_dev = _h2d(tab, dev)
             counter = torch.empty((1,), dtype=torch.int32, device=dev)
             a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
         _lib.check(plan.lib.b200fe_fbank_fused(plan.handle, C.byref(a), stream), "b200fe_fbank_fused")
