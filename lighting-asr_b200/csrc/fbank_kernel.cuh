@@ -34,6 +34,17 @@ namespace b200fe {
 #ifndef B200FE_WARPS
 #define B200FE_WARPS 8              // warps per CTA: 8 (2 CTAs/SM, 32-frame tiles) or 6 (3 CTAs/SM, 24-frame tiles)
 #endif
+// Two scheduling variants kept behind macros because they were measured SLOWER on B200 (A/B on one box, C2 plain launch:
+// 0.3285 ms baseline): issuing the next tile's TMA as soon as every warp holds its last frames in registers instead of
+// after the phase-A barrier (0.3422 ms: the transfer then competes with phase A for the shared-memory pipe), and routing
+// the plain copy-out through the (row part, column) mapping of the statistics path (0.3400 ms: 240 of 256 threads, 11 rounds).
+#ifndef B200FE_EARLY_TMA
+#define B200FE_EARLY_TMA 0
+#endif
+#ifndef B200FE_ROWPART_PLAIN
+#define B200FE_ROWPART_PLAIN 0
+#endif
+constexpr bool kEarlyTma = B200FE_EARLY_TMA != 0;
 constexpr int kWarps = B200FE_WARPS;
 constexpr int kFT = 4 * kWarps;             // frames per tile: every half-warp transforms two frames
 constexpr int kThreads = 32 * kWarps;
@@ -422,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_init(&bars[kStages], kWarps);        // "tile consumed": every warp has its last frames in registers
         fence_mbar_init();
     }
     // global CMVN vectors (or the identity) are staged once; per-utterance vectors per tile
@@ -441,6 +453,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     const int nmask = a.n_fmask + a.n_tmask;
     // statistics without SpecAugment row classes are reduced inside phase C (no staging write-back, no extra barrier)
     const bool stats_fused = a.stats != nullptr && !zmask && (a.row_bounds == nullptr || a.n_cls <= 1) && nmel <= kThreads;
+    // the same thread <-> (row part, column) mapping serves the plain copy-out: constant strides, no index arithmetic
+    const bool rowpart_c = !zmask && nmel <= kThreads && (stats_fused || (B200FE_ROWPART_PLAIN != 0 && a.stats == nullptr));
 
     // ---- tile scheduler ------------------------------------------------------------------------
     // Thread 0 resolves tile descriptors (id, utterance, first frame, frame count of the utterance) TWO tiles
@@ -478,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     };
 
     int it = 0;
-    uint32_t phase_bits = 0;
+    uint32_t phase_bits = 0, consumed_phase = 0;
     if (tid == 0) {
         const int id0 = dyn ? atomicAdd(a.work_counter, 1) : (int)blockIdx.x;
         const int id1 = dyn ? atomicAdd(a.work_counter, 1) : (int)(blockIdx.x + gridDim.x);
@@ -548,7 +562,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 const int fl = kDual ? (8 * (warp >> 1) + 2 * (warp & 1) + 4 * h2)            // frames fl (a), fl + 1 (b)
                                      : ((slot & 3) + 8 * (slot >> 2) + 4 * h2);
                 const bool fvalid = fl < nvalid;
-                if (fl - 4 * h2 < nvalid) {
+                const bool last_pass = kDual || sub == 1;
+                if (fl - 4 * h2 >= nvalid) {
+                    if (kEarlyTma && last_pass && a.use_tma && lane == 0) mbar_arrive(&bars[kStages]);
+                } else {
                     float2 v[16];
                     if (!kStaticMel && a.dither != 0.f) {      // generic kernels only; the static (LASR default) path has dither 0
                         const long long row = ((long long)utt * a.Tmax + f0 + fl) * a.win;
@@ -559,6 +576,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
                     else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + fl * a.shift + 2 * l, wl, fc, l);
                     else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
+                    if (kEarlyTma && last_pass && a.use_tma) {
+                        // this warp no longer needs the tile buffer: once all warps say so, the next tile's TMA goes out
+                        // (about half a tile earlier than after the phase-A barrier)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[kStages]);
+                    }
                     fft256_halfwarp(v, tw, xbuf, l);
                     float2 rc[8];
                     pair_exchange(v, rc, l, h2);
@@ -602,9 +625,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     }
                 }
             }
-            __syncthreads();   // B1: PT complete; the tile buffer is free; every warp has finished phase C of the previous tile
+            if (kEarlyTma && a.use_tma) {
+                if (tid == 0) {
+                    mbar_wait(&bars[kStages], consumed_phase);
+                    if (nxt.id < a.ntiles) issue_load(gn, 0);
+                }
+                consumed_phase ^= 1u;
+            }
+            __syncthreads();   // B1: PT complete; every warp has finished phase C of the previous tile
             if (tid == 0) {
-                if (a.use_tma && nxt.id < a.ntiles) issue_load(gn, 0);
+                if (!kEarlyTma && a.use_tma && nxt.id < a.ntiles) issue_load(gn, 0);
                 s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
             }
             // per-tile epilogue tables for phase C (written here: no warp is still reading the previous tile's)
@@ -683,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         {
             float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * nmel : nullptr;
             const int nv = nvalid * nmel, nt = nrows * nmel;
-            if (nvalid > 0 && stats_fused) {
+            if (nvalid > 0 && rowpart_c) {
                 // Statistics mode without row classes: thread = (row part, column), element e = tid + k P with
                 // P = parts * nmel, so the copy-out stays coalesced AND every thread keeps one column: its sum and
                 // sum of squares (about a pivot, fp32 over <= 11 rows) never leave registers; one fp64 atomic pair
@@ -710,13 +740,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             if (affine) x[k] = (x[k] - cm) * ci;
                         }
                         pivot = x[0];
+                        if (stats_fused) {
 #pragma unroll
-                        for (int k = 0; k < kIt; ++k) {
-                            if (tid + k * P < nv) {
-                                if (obase) obase[tid + k * P] = x[k];
-                                const float dd = x[k] - pivot;
-                                s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
+                            for (int k = 0; k < kIt; ++k) {
+                                if (tid + k * P < nv) {
+                                    if (obase) obase[tid + k * P] = x[k];
+                                    const float dd = x[k] - pivot;
+                                    s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
+                                }
                             }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kIt; ++k) if (tid + k * P < nv) obase[tid + k * P] = x[k];
                         }
                     } else {
 #pragma unroll 2
@@ -730,7 +765,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
                         }
                     }
-                    if (cnt > 0) {
+                    if (stats_fused && cnt > 0) {
                         double* sb = a.stats + (long long)utt * a.stats_stride;
                         const double dp = (double)pivot, d1 = (double)s1;
                         atomicAdd(sb + col, d1 + cnt * dp);
