@@ -20,7 +20,7 @@ for dt in (torch.float32, torch.int16):
     for mode in sys.argv[1:]:
         fe = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
         fe.kernel_h2d = mode[0] == "k"; fe.kernel_d2h = mode[1] == "k"
-        packed = mode[0] == "p"; fe.overlap_calls = len(mode) < 3
+        packed = mode[0] == "p"; fe.overlap_calls = "n" not in mode[2:]
         call = (lambda rh: fe.extract_host(pk, lens, device=dev, return_host=rh, wav_offsets=offs, group_bytes=GB)) if packed else (lambda rh: fe.extract_host(wp, n, device=dev, return_host=rh, group_bytes=GB))
         out = []
         for rh in (True, False):
