@@ -144,6 +144,11 @@ typedef struct b200fe_fbank_args {
      * holds; d_wav then points to int16 and strides / offsets count int16 samples, offsets multiples of 8
      * for the TMA loader).  (float)s16 == float32 sample * 2^15 exactly, so both give identical features. */
     int wav_dtype;
+    /* Lock-step streaming: non-zero promises that EVERY utterance of this call yields exactly max_frames frames
+     * (d_nsamp[u] in [(max_frames-1)*shift + window, max_frames*shift + window) for all u).  With max_frames <= 16 the
+     * fused kernel then packs several utterances into one 32-frame tile (8 streams x 4 frames for a 40 ms push).
+     * Ignored together with peak normalisation, statistics, masks, per-utterance CMVN, dither or a tile table. */
+    int uniform_frames;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

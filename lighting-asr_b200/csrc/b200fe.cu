@@ -63,6 +63,7 @@ struct b200fe_plan {
     float2 w_updn[256];
     int tile_floats;
     int smem_bytes;
+    int multi_tile_floats, multi_smem_bytes;   // multi-utterance tiles (streaming)
     int nload;          // 13 or 16
     int static_mel;     // 1: tables equal the baked-in LASR default -> straight-line phase B
     int ctas_per_sm;
@@ -77,8 +78,14 @@ static const void* ws_kernel(bool peak, bool i16)
 }
 static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : kFT; }
 
-static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false)
+static bool plan_has_multi(const b200fe_plan* p) { return p->nload == 13 && (p->static_mel || p->nfft == 256); }
+
+static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false)
 {
+    if (multi) {   // multi-utterance tiles (lock-step streaming): the two default option sets, float32, no peak normalisation
+        if (p->nfft == 256) return (const void*)fbank_fused_kernel<13, false, false, true, false, true>;
+        return (const void*)fbank_fused_kernel<13, true, false, false, false, true>;
+    }
     if (i16) {   // int16 PCM input, 512-point family
         if (p->nload == 13) {
             if (p->static_mel) return peak ? (const void*)fbank_fused_kernel<13, true, true, false, true> : (const void*)fbank_fused_kernel<13, true, false, false, true>;
@@ -247,6 +254,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     p->nload = (p->win > 12 * per_reg && p->win <= 13 * per_reg) ? 13 : 16;
     // a frame reads up to per_reg*nload samples from its start (zero-weighted past the window)
     p->tile_floats = ((kFT - 1) * p->shift + per_reg * p->nload + 3) & ~3;
+    // multi-utterance tiles (lock-step streaming) get their own, larger tile buffer: room for kFT/4 utterances of 4 frames
+    // (a 40 ms push); only those launches pay the extra shared memory
+    p->multi_tile_floats = std::max(p->tile_floats, (kFT / 4) * ((3 * p->shift + per_reg * p->nload + 3) & ~3));
+    p->multi_smem_bytes = make_layout(p->multi_tile_floats, p->nmel).total;
     p->smem_bytes = make_layout(p->tile_floats, p->nmel).total;
 
     cudaError_t e = cudaGetDevice(&p->device);
@@ -279,6 +290,8 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     const void* kfn = plan_kernel(p, false);
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess && plan_has_multi(p))
+        e = cudaFuncSetAttribute(plan_kernel(p, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (p->nfft == 512) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -493,6 +506,19 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
 
     a.tile_table = reinterpret_cast<const int2*>(g->d_tile_table);
     a.work_counter = g->d_work_counter;
+    // Lock-step streaming (every utterance yields exactly max_frames frames): tiles take several utterances, so a 4-frame
+    // push fills a 32-frame tile with 8 streams instead of occupying one tile per stream.
+    if (g->uniform_frames && plan_has_multi(p) && !i16 && !compact && !ws && g->max_frames <= kFT / 2 && !g->d_peak && !g->d_stats && !a.masks &&
+        !(g->d_cmvn_mean && g->cmvn_stride != 0) && p->o.dither == 0.f && (p->nfft != 256 || g->max_frames % 2 == 0)) {
+        const int per_reg = p->nfft == 512 ? 32 : 16;
+        const int span = ((g->max_frames - 1) * p->shift + per_reg * p->nload + 3) & ~3;
+        const int upt = std::min(kFT / g->max_frames, p->multi_tile_floats / span);
+        if (upt >= 2) {
+            a.multi_fpu = g->max_frames; a.multi_upt = upt; a.multi_span = span;
+            a.ntiles = (g->batch + upt - 1) / upt;
+            a.tile_floats = p->multi_tile_floats;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (compact) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
     if (compact || ws) {
@@ -511,8 +537,9 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         CUDA_TRY(cudaLaunchKernel(ws_kernel(g->d_peak != nullptr, i16), dim3(wgrid), dim3(kWsThreads), kargs, (size_t)p->ws_smem_bytes, st));
         return B200FE_OK;
     }
-    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms * p->ctas_per_sm));
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16), dim3(grid), dim3(kThreads), kargs, (size_t)p->smem_bytes, st));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0), dim3(grid), dim3(kThreads), kargs,
+                              (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
     return B200FE_OK;
 }
 

@@ -109,6 +109,9 @@ struct FbankArgs {
     int* work_counter;
     int use_tma;
     int tile_floats;             // floats reserved per tile stage
+    // multi-utterance tiles (lock-step streaming: every utterance yields exactly Tmax = multi_fpu frames): a tile takes
+    // multi_upt consecutive utterances, multi_fpu frames each; utterance j's samples sit at j * multi_span in the tile buffer
+    int multi_fpu, multi_upt, multi_span;
     // mel tables (warp-uniform, read through the constant bank) -- generic (non-static) phase B
     short seg_start[kMaxMel + 3];   // k where segment s begins, s = 0..nmel+1  (segment s feeds bin s (up) and s-1 (down))
     short grp_begin[9];             // mel bins handled by warp w: [grp_begin[w], grp_begin[w+1])
@@ -394,7 +397,8 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 // 2j Xb[k] = Z[k] - conj Z[256-k], so the conjugate-pair exchange yields both power spectra without any
 // split twiddle (k = 0..127; the Nyquist bin has zero mel weight, TA:627).
 // kI16: the waveform is int16 PCM (2 bytes per sample over PCIe / HBM); 512-point family only.
-template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false>
+// kMulti: multi-utterance tiles for lock-step streaming (instantiated for the two default option sets only).
+template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false, bool kMulti = false>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -462,10 +466,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     // tile table -> sample count) never sit on any warp's critical path.
     struct Desc { int id, utt, f0, T; };
     const bool dyn = a.tile_table != nullptr;
+    constexpr bool multi = kMulti;
     int4* s_desc = reinterpret_cast<int4*>(bars + 2);          // 16-byte aligned: two 8-byte slots are reserved for mbarriers
     auto resolve = [&](int id) -> Desc {               // thread 0 only
         Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
         if (id < a.ntiles) {
+            if (multi) {                                    // the tile's utterances form one run of consecutive output rows
+                d.utt = id * a.multi_upt;
+                d.T = a.multi_fpu * min(a.multi_upt, a.B - d.utt);
+                return d;
+            }
             if (dyn) { const int2 e = __ldg(a.tile_table + id); d.utt = e.x; d.f0 = e.y; }
             else { d.utt = (int)((unsigned)id / (unsigned)a.tiles_per_utt); d.f0 = (id - d.utt * a.tiles_per_utt) * kFT; }
             const unsigned n = (unsigned)__ldg(a.nsamp + d.utt);       // < 2^31 samples per utterance
@@ -482,8 +492,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     };
     auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
         if (g.nvalid <= 0) return;
-        const int nsmp = (g.nvalid - 1) * a.shift + a.win;
         const int esz = kI16 ? 2 : 4;
+        if (multi) {
+            const int nu = g.nvalid / a.multi_fpu;
+            const uint32_t bytes = (uint32_t)((((a.multi_fpu - 1) * a.shift + a.win) * esz + 15) & ~15);
+            mbar_expect_tx(&bars[stage], bytes * (uint32_t)nu);
+            for (int j = 0; j < nu; ++j) {
+                const long long eoff = a.wav_offsets ? __ldg(a.wav_offsets + g.utt + j) : (long long)(g.utt + j) * a.wav_stride;
+                tma_load_1d(smem + L.tile_off[stage] + (size_t)j * a.multi_span * esz, reinterpret_cast<const char*>(a.wav) + eoff * esz, bytes, &bars[stage]);
+            }
+            return;
+        }
+        const int nsmp = (g.nvalid - 1) * a.shift + a.win;
         const uint32_t bytes = (uint32_t)((nsmp * esz + 15) & ~15);
         const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + g.utt) : (long long)g.utt * a.wav_stride) + (long long)g.f0 * a.shift;
         const char* src = reinterpret_cast<const char*>(a.wav) + eoff * esz;
@@ -526,15 +546,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             if (nvalid > 0) { mbar_wait(&bars[0], phase_bits & 1u); phase_bits ^= 1u; }
         } else if (nvalid > 0) {
             // generic path (unaligned base / stride): cooperative coalesced loads
-            const int nsmp = (nvalid - 1) * a.shift + a.win;
-            const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + utt) : (long long)utt * a.wav_stride) + (long long)f0 * a.shift;
-            if (kI16) {
-                const short* src = reinterpret_cast<const short*>(a.wav) + eoff;
-                short* xd = reinterpret_cast<short*>(xs);
-                for (int i = tid; i < nsmp; i += kThreads) xd[i] = __ldg(src + i);
-            } else {
-                const float* src = a.wav + eoff;
-                for (int i = tid; i < nsmp; i += kThreads) xs[i] = __ldg(src + i);
+            const int nu = multi ? nvalid / a.multi_fpu : 1;
+            const int nsmp = ((multi ? a.multi_fpu : nvalid) - 1) * a.shift + a.win;
+            for (int j = 0; j < nu; ++j) {
+                const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + utt + j) : (long long)(utt + j) * a.wav_stride) + (long long)f0 * a.shift;
+                if (kI16) {
+                    const short* src = reinterpret_cast<const short*>(a.wav) + eoff;
+                    short* xd = reinterpret_cast<short*>(xs) + j * a.multi_span;
+                    for (int i = tid; i < nsmp; i += kThreads) xd[i] = __ldg(src + i);
+                } else {
+                    const float* src = a.wav + eoff;
+                    float* xd = xs + j * a.multi_span;
+                    for (int i = tid; i < nsmp; i += kThreads) xd[i] = __ldg(src + i);
+                }
             }
             __syncthreads();
         }
@@ -573,9 +597,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                         fc.noise_a = a.dither_noise ? a.dither_noise + row : nullptr;
                         fc.noise_b = a.dither_noise ? a.dither_noise + row + a.win : nullptr;
                     }
-                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + l, xs + (fl + 1) * a.shift + l, wls, fc, l);
-                    else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + fl * a.shift + 2 * l, wl, fc, l);
-                    else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + fl * a.shift + 2 * l, wl, fc, l);
+                    // sample offset of the frame inside the tile buffer (multi-utterance tiles: slot -> (utterance, frame))
+                    int foff = fl * a.shift;
+                    if (multi) { const int uj = fl / a.multi_fpu; foff = uj * a.multi_span + (fl - uj * a.multi_fpu) * a.shift; }
+                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + foff + l, xs + foff + a.shift + l, wls, fc, l);
+                    else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + foff + 2 * l, wl, fc, l);
+                    else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + foff + 2 * l, wl, fc, l);
                     if (kEarlyTma && last_pass && a.use_tma) {
                         // this warp no longer needs the tile buffer: once all warps say so, the next tile's TMA goes out
                         // (about half a tile earlier than after the phase-A barrier)
@@ -846,7 +873,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 }
             }
         }
-        if (a.out_len != nullptr && f0 == 0 && nrows > 0 && tid == 0) a.out_len[utt] = g.T;
+        if (multi) {
+            if (a.out_len != nullptr && tid * a.multi_fpu < nvalid) a.out_len[utt + tid] = a.multi_fpu;
+        } else if (a.out_len != nullptr && f0 == 0 && nrows > 0 && tid == 0) a.out_len[utt] = g.T;
         if (a.stats != nullptr && nvalid > 0 && !stats_fused) {
             // Column statistics of what phase C wrote back into the staging tile.  thread = (column j, row
             // part); fp32 partial sums over <= 11 rows, flushed with fp64 atomics.

@@ -230,7 +230,8 @@ class GpuFbankFrontend(torch.nn.Module):
 
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None, dither_noise=None):
+    def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None, dither_noise=None,
+                uniform_frames=False):
         """``wav_offsets`` (int64 host array, multiples of 4) switches to the packed layout: ``wav`` is then
         a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
         if not wav.is_cuda:
@@ -344,6 +345,7 @@ class GpuFbankFrontend(torch.nn.Module):
             nb = min(group, B - b0)
             a = _lib.FbankArgs()
             a.wav_dtype = 1 if i16 else 0
+            a.uniform_frames = 1 if uniform_frames else 0      # lock-step streaming: every utterance yields exactly max_frames frames
             if packed:
                 a.d_wav = _ptr(wav)
                 a.wav_stride = row_stride

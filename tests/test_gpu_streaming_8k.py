@@ -95,3 +95,27 @@ def test_streaming_equals_offline(lasr_b200, sf, chunk):
         tol = 1e-5 + 1e-4 * ref.abs()
         assert float((d > tol).float().mean()) <= 1e-4 and float(d.max()) < 5e-3 and float(d.mean()) < 1e-5
     assert online.shape[1] == kaldi_fbank.num_frames(pos, int(sf * 0.025), int(sf * 0.01))
+
+
+@pytest.mark.parametrize("sf,chunk", [(16000.0, 640), (8000.0, 320)])
+def test_streaming_many_streams_wraps_and_global_cmvn(lasr_b200, sf, chunk):
+    """Multi-stream tiles (8 streams x 4 frames per 32-frame tile), a stream count that leaves a partial last tile, the sliding
+    window wrapping several times (small max_chunk -> small buffer), and global CMVN applied in the fused launch."""
+    S, nchunks = 27, 440
+    rng = np.random.default_rng(9)
+    audio = torch.from_numpy(rng.uniform(-0.5, 0.5, (S, chunk * nchunks)).astype(np.float32)).to(DEV)
+    n = np.full(S, chunk * nchunks, dtype=np.int64)
+    stats = lasr_b200.GpuFbankFrontend(sample_frequency=sf).accumulate_stats(audio, n).cpu().numpy()
+    for kw in ({}, {"cmvn": "global", "cmvn_stats": stats}):
+        st = lasr_b200.StreamingFbank(S, device=DEV, sample_frequency=sf, max_chunk=chunk, **kw)
+        assert st.width < chunk * nchunks // 2                      # the buffer is exhausted more than once
+        online = torch.cat([st.push(audio[:, c * chunk:(c + 1) * chunk]) for c in range(nchunks)], dim=1)
+        off = lasr_b200.GpuFbankFrontend(sample_frequency=sf, **kw)(audio, n)[0]
+        assert online.shape == off.shape
+        assert torch.equal(online, off)
+    # one and two streams (no packing possible / a single partial tile)
+    for S1 in (1, 2):
+        st = lasr_b200.StreamingFbank(S1, device=DEV, sample_frequency=sf)
+        online = torch.cat([st.push(audio[:S1, c * chunk:(c + 1) * chunk]) for c in range(20)], dim=1)
+        off = lasr_b200.GpuFbankFrontend(sample_frequency=sf)(audio[:S1, : 20 * chunk].contiguous(), n[:S1] * 0 + 20 * chunk)[0]
+        assert torch.equal(online, off)
