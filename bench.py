@@ -254,6 +254,25 @@ def main():
     barrier()
     e2e_i16_ms = g0.elapsed_time(g1)
     h2d_i16, d2h_i16 = fe.h2d_bytes, fe.d2h_bytes
+    # packed feature output: (sum T, 80) without padding rows, one DMA per group in both directions
+    for _ in range(2):
+        fe.extract_host(pk_pin, pk_len, device=dev, wav_offsets=pk_off, packed_out=True)
+    barrier()
+    g0.record()
+    for _ in range(args.steps):
+        fe.extract_host(pk_pin, pk_len, device=dev, wav_offsets=pk_off, packed_out=True)
+    g1.record()
+    barrier()
+    e2e_pk_ms = g0.elapsed_time(g1)
+    for _ in range(2):
+        fe.extract_host(pcm_pin, pcm_len, device=dev, wav_offsets=pcm_off, packed_out=True)
+    barrier()
+    g0.record()
+    for _ in range(args.steps):
+        fe.extract_host(pcm_pin, pcm_len, device=dev, wav_offsets=pcm_off, packed_out=True)
+    g1.record()
+    barrier()
+    e2e_pk16_ms = g0.elapsed_time(g1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the path's only collective: all-reduce of the global CMVN statistics ----
@@ -271,12 +290,12 @@ def main():
         ar_us = g0.elapsed_time(g1) / 20 * 1e3
 
     # max over ranks of the device time, sum over ranks of the work
-    red = torch.tensor([ms_total, e2e_ms, e2e_dev_ms, e2e_i16_ms, e2e_pad_ms], dtype=torch.float64, device=dev)
+    red = torch.tensor([ms_total, e2e_ms, e2e_dev_ms, e2e_i16_ms, e2e_pad_ms, e2e_pk_ms, e2e_pk16_ms], dtype=torch.float64, device=dev)
     work = torch.tensor([hours, float(alg_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, e2e_dev_ms, e2e_i16_ms, e2e_pad_ms = (float(x) for x in red.cpu())
+    ms_total, e2e_ms, e2e_dev_ms, e2e_i16_ms, e2e_pad_ms, e2e_pk_ms, e2e_pk16_ms = (float(x) for x in red.cpu())
     hours_all = float(work[0])
 
     if rank == 0:
@@ -321,6 +340,11 @@ def main():
                       "e2e_int16_pcm_host_input": {"value": hours_all / (e2e_i16_ms / args.steps * 1e-3), "unit": "audio-h/s",
                                                    "ms_per_step": e2e_i16_ms / args.steps, "h2d_bytes_per_step": h2d_i16,
                                                    "d2h_bytes_per_step": d2h_i16},
+                      "e2e_packed_feature_output": {"value": hours_all / (e2e_pk_ms / args.steps * 1e-3), "unit": "audio-h/s",
+                                                    "ms_per_step": e2e_pk_ms / args.steps,
+                                                    "api": "extract_host(..., packed_out=True): (sum T, 80) pinned features + lengths + row offsets, one DMA per group each way"},
+                      "e2e_int16_in_packed_out": {"value": hours_all / (e2e_pk16_ms / args.steps * 1e-3), "unit": "audio-h/s",
+                                                  "ms_per_step": e2e_pk16_ms / args.steps},
                       "global_cmvn_stats_allreduce_us": ar_us},
         }
         if world == 1 and not args.no_cpu_baseline:

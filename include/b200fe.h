@@ -149,6 +149,10 @@ typedef struct b200fe_fbank_args {
      * fused kernel then packs several utterances into one 32-frame tile (8 streams x 4 frames for a 40 ms push).
      * Ignored together with peak normalisation, statistics, masks, per-utterance CMVN, dither or a tile table. */
     int uniform_frames;
+    /* Packed feature output: [batch] first output ROW of every utterance, ascending; d_out is then
+     * [sum of frames][num_mel_bins] with no padding rows (utterance u occupies rows [d_out_offsets[u],
+     * d_out_offsets[u] + frames[u])).  NULL = the reference's zero-padded [batch][max_frames][num_mel_bins] layout. */
+    const long long* d_out_offsets;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);
@@ -206,6 +210,7 @@ typedef struct b200fe_post_args {
     int n_freq_masks, n_time_masks;
     float* d_fills;              /* [batch][n_freq_masks + n_time_masks] outputs (required with masks) */
     int fill_zero;               /* 1 = replace_with_zero: masked cells become 0 instead of the running mean */
+    const long long* d_feat_offsets; /* optional [batch]: d_feats is packed as written with d_out_offsets */
 } b200fe_post_args;
 
 int b200fe_postpass(const b200fe_plan* plan, const b200fe_post_args* args, void* stream);

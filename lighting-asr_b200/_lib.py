@@ -28,6 +28,7 @@ class FbankArgs(C.Structure):
         ("d_tile_table", C.c_void_p), ("n_tiles", C.c_int), ("d_work_counter", C.c_void_p),
         ("d_wav_offsets", C.c_void_p), ("offsets_aligned", C.c_int),
         ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p), ("wav_dtype", C.c_int), ("uniform_frames", C.c_int),
+        ("d_out_offsets", C.c_void_p),
     ]
 
 
@@ -37,7 +38,7 @@ class PostArgs(C.Structure):
         ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
         ("cmvn_mode", C.c_int), ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p),
         ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("d_fills", C.c_void_p),
-        ("fill_zero", C.c_int),
+        ("fill_zero", C.c_int), ("d_feat_offsets", C.c_void_p),
     ]
 
 

@@ -166,6 +166,7 @@ struct PostArgs {
     float* fills;
     int fill_zero;               // 1: replace_with_zero (fills are 0), 0: running mean fills
     int rows_per_cta;
+    const long long* feat_offsets;   // optional [B] first row of every utterance (packed features)
 };
 
 // One CTA (128 threads, thread d = mel column d) per utterance.
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(256) postpass_kernel(const PostArgs a)
         s_istd[threadIdx.x] = a.cm_istd[(long long)utt * a.nmel + threadIdx.x];
     }
     __syncthreads();
-    float* base = a.feats + (long long)utt * a.Tmax * a.nmel;
+    float* base = a.feats + (a.feat_offsets != nullptr ? a.feat_offsets[utt] : (long long)utt * a.Tmax) * a.nmel;
     const int total = (r1 - r0) * a.nmel;
     for (int e = threadIdx.x; e < total; e += 256) {
         const int r = r0 + e / a.nmel, d = e % a.nmel;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
             if (i < a.n_tmask) { tlo[i] = mk[2 * (a.n_fmask + i)]; thi[i] = mk[2 * (a.n_fmask + i) + 1]; tfill[i] = fl[a.n_fmask + i]; }
     }
     const bool need_read = a.cmvn_mode != 0;
-    float4* base = reinterpret_cast<float4*>(a.feats + (long long)utt * a.Tmax * a.nmel);
+    float4* base = reinterpret_cast<float4*>(a.feats + (a.feat_offsets != nullptr ? a.feat_offsets[utt] : (long long)utt * a.Tmax) * a.nmel);
     for (int r = r0 + slot; r < r1; r += slots) {
         int thit = -1; float tf = 0.f;
 #pragma unroll

@@ -471,6 +471,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     memset(&a, 0, sizeof a);
     a.wav = g->d_wav; a.wav_stride = g->wav_stride; a.wav_offsets = g->d_wav_offsets; a.nsamp = g->d_nsamp; a.peak = g->d_peak; a.B = g->batch;
     a.out = g->d_out; a.out_len = g->d_out_len; a.Tmax = g->max_frames; a.nmel = p->nmel;
+    a.out_offsets = g->d_out ? g->d_out_offsets : nullptr;
     a.win = p->win; a.shift = p->shift;
     a.remove_dc = p->o.remove_dc_offset; a.use_power = p->o.use_power; a.use_log = p->o.use_log_fbank;
     a.preemph = p->o.preemphasis_coefficient;
@@ -488,7 +489,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.masks = (g->n_freq_masks + g->n_time_masks) > 0 ? g->d_masks : nullptr;
     a.n_fmask = g->n_freq_masks; a.n_tmask = g->n_time_masks; a.mask_zero = g->mask_zero;
     a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds; a.n_cls = n_cls;
-    const bool ws = p->use_ws != 0;
+    const bool ws = p->use_ws != 0 && !g->d_out_offsets;        // the experimental kernel writes the padded layout only
     const int tile_ft = plan_tile_frames(p);
     a.tiles_per_utt = (g->max_frames + tile_ft - 1) / tile_ft;
     const bool compact = g->d_tile_table != nullptr;
@@ -508,7 +509,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.work_counter = g->d_work_counter;
     // Lock-step streaming (every utterance yields exactly max_frames frames): tiles take several utterances, so a 4-frame
     // push fills a 32-frame tile with 8 streams instead of occupying one tile per stream.
-    if (g->uniform_frames && plan_has_multi(p) && !i16 && !compact && !ws && g->max_frames <= kFT / 2 && !g->d_peak && !g->d_stats && !a.masks &&
+    if (g->uniform_frames && plan_has_multi(p) && !i16 && !compact && !ws && !g->d_out_offsets && g->max_frames <= kFT / 2 && !g->d_peak && !g->d_stats && !a.masks &&
         !(g->d_cmvn_mean && g->cmvn_stride != 0) && p->o.dither == 0.f && (p->nfft != 256 || g->max_frames % 2 == 0)) {
         const int per_reg = p->nfft == 512 ? 32 : 16;
         const int span = ((g->max_frames - 1) * p->shift + per_reg * p->nload + 3) & ~3;
@@ -522,7 +523,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     cudaStream_t st = (cudaStream_t)stream;
     if (compact) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
     if (compact || ws) {
-        if (g->d_out) {
+        if (g->d_out && !g->d_out_offsets) {                      // packed output has no padding rows
             const long long per_utt = (long long)g->max_frames * p->nmel;
             dim3 zg((unsigned)((per_utt + 8191) / 8192), (unsigned)g->batch);
             zero_pad_kernel<<<zg, 256, 0, st>>>(g->d_out, g->d_nsamp, g->max_frames, p->nmel, p->win, p->shift);
@@ -564,6 +565,7 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     a.masks = masks ? g->d_masks : nullptr; a.n_fmask = masks ? g->n_freq_masks : 0; a.n_tmask = masks ? g->n_time_masks : 0;
     a.fills = g->d_fills;
     a.fill_zero = g->fill_zero;
+    a.feat_offsets = g->d_feat_offsets;
     a.rows_per_cta = 64;
     cudaStream_t st = (cudaStream_t)stream;
     finalize_kernel<<<g->batch, 128, 0, st>>>(a);

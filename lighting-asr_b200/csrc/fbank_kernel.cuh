@@ -69,6 +69,7 @@ struct FbankArgs {
     int B;
     // output
     float* out;                  // [B][Tmax][nmel] (nullptr in statistics-only mode)
+    const long long* out_offsets; // optional [B] first output row of every utterance: packed [sum T][nmel] output, no padding rows
     long long* out_len;          // [B] frames per utterance (optional)
     int Tmax;
     int nmel;
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         TileGeom g;
         g.utt = d.utt; g.f0 = d.f0; g.T = d.T;
         g.nvalid = min(max(d.T - d.f0, 0), kFT);
-        g.nrows = dyn ? g.nvalid : min(a.Tmax - d.f0, kFT);
+        g.nrows = (dyn || a.out_offsets != nullptr) ? g.nvalid : min(a.Tmax - d.f0, kFT);
         return g;
     };
     auto issue_load = [&](const TileGeom& g, int stage) {      // called by thread 0 only
@@ -738,7 +739,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         // ================= phase C: epilogue + copy-out, zero padding, statistics =================
         // element e = row * nmel + col of the tile (contiguous in global memory) <-> staging row*(nmel+1)+col
         {
-            float* obase = a.out != nullptr ? a.out + ((long long)utt * a.Tmax + f0) * nmel : nullptr;
+            const long long orow0 = a.out_offsets != nullptr ? __ldg(a.out_offsets + utt) : (long long)utt * a.Tmax;
+            float* obase = a.out != nullptr ? a.out + (orow0 + f0) * nmel : nullptr;
             const int nv = nvalid * nmel, nt = nrows * nmel;
             if (nvalid > 0 && rowpart_c) {
                 // Statistics mode without row classes: thread = (row part, column), element e = tid + k P with

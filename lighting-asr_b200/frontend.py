@@ -231,12 +231,14 @@ class GpuFbankFrontend(torch.nn.Module):
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None, dither_noise=None,
-                uniform_frames=False):
+                uniform_frames=False, packed_out=False):
         """``wav_offsets`` (int64 host array, multiples of 4) switches to the packed layout: ``wav`` is then
         a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
         if self.time_warp:
+            if packed_out:
+                raise ValueError("packed_out is not available together with time_warp")
             return self._forward_time_warp(wav, wav_len, max_frames, masks, out, out_len, wav_offsets, dither_noise)
         packed = wav_offsets is not None
         if wav.dtype not in (torch.float32, torch.int16) or wav.dim() != (1 if packed else 2):
@@ -277,12 +279,23 @@ class GpuFbankFrontend(torch.nn.Module):
         else:
             T_host, Tmax = None, int(max_frames)
         D = self.num_mel_bins
+        ooff_dev = ooff_host = None
+        if packed_out:
+            # packed features: utterance b occupies rows [offsets[b], offsets[b] + T_b) of a (sum T, D) tensor
+            if len_host is None:
+                raise ValueError("packed_out needs host lengths (the row offsets are their prefix sums)")
+            ooff_host = np.zeros(B, dtype=np.int64)
+            np.cumsum(T_host[:-1], out=ooff_host[1:])
+            ooff_dev = _h2d(ooff_host, dev)
+            oshape = (int(T_host.sum()), D)
+        else:
+            oshape = (B, Tmax, D)
         if out is not None:
-            if out.shape != (B, Tmax, D) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
-                raise ValueError("out must be a contiguous float32 (B, Tmax, D) tensor on the input's device")
+            if tuple(out.shape) != oshape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+                raise ValueError("out must be a contiguous float32 %s tensor on the input's device" % (oshape,))
             feats = out
         else:
-            feats = torch.empty((B, Tmax, D), dtype=torch.float32, device=dev)
+            feats = torch.empty(oshape, dtype=torch.float32, device=dev)
         feat_len = out_len if out_len is not None else torch.empty((B,), dtype=torch.int64, device=dev)
         cur_stream = torch.cuda.current_stream(dev)
         stream = C.c_void_p(cur_stream.cuda_stream)
@@ -357,7 +370,11 @@ class GpuFbankFrontend(torch.nn.Module):
             a.d_nsamp = off(len_dev, b0, 8)
             a.batch = nb
             a.d_peak = off(peak, b0, 4)
-            a.d_out = off(feats, b0, Tmax * D * 4)
+            if packed_out:
+                a.d_out = _ptr(feats)
+                a.d_out_offsets = off(ooff_dev, b0, 8)
+            else:
+                a.d_out = off(feats, b0, Tmax * D * 4)
             a.d_out_len = off(feat_len, b0, 8)
             a.max_frames = Tmax
             if self.dither != 0.0:
@@ -406,6 +423,7 @@ class GpuFbankFrontend(torch.nn.Module):
             if need_post:
                 q = _lib.PostArgs()
                 q.d_feats = a.d_out
+                q.d_feat_offsets = a.d_out_offsets
                 q.d_nsamp = a.d_nsamp
                 q.batch = nb
                 q.max_frames = Tmax
@@ -422,7 +440,7 @@ class GpuFbankFrontend(torch.nn.Module):
                     q.d_fills = off(fills, b0, (n_f + n_t) * 4)
                 _lib.check(lib.b200fe_postpass(plan.handle, C.byref(q), stream), "b200fe_postpass")
                 self.launch_count += 2      # finalize + in-place post pass
-        self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak)
+        self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak, feat_offsets=ooff_host)
         return feats, feat_len
 
     def _forward_time_warp(self, wav, wav_len, max_frames, masks, out, out_len, wav_offsets, dither_noise):
@@ -492,7 +510,8 @@ class GpuFbankFrontend(torch.nn.Module):
         return buf, lens, offs
 
     @torch.no_grad()
-    def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True, wav_offsets=None):
+    def extract_host(self, wav_host, wav_len, device="cuda:0", group_bytes=32 << 20, return_host=True, wav_offsets=None,
+                     packed_out=False):
         """Pipelined H2D copy -> fused kernels -> D2H copy over utterance groups on three streams.
 
         wav_host: zero-padded float32 CPU tensor (B, Nmax), ideally pinned (what batch_list builds).
@@ -500,7 +519,11 @@ class GpuFbankFrontend(torch.nn.Module):
         buffer (b200fe_h2d_ragged) that the fused kernel reads through per-utterance offsets.
         Returns (feats, feat_len): pinned CPU tensors when ``return_host`` (what
         AudioDataSet.collate_fn hands to the trainer, dataset.py:222-232), else CUDA tensors (the
-        case where the encoder consumes them in place)."""
+        case where the encoder consumes them in place).
+
+        ``wav_offsets`` (from ``pack_host``): ``wav_host`` is the 1-D packed pinned buffer, moved with one DMA per group.
+        ``packed_out``: features come back packed, ``(sum T, D)`` with no padding rows, as ``(feats, feat_len,
+        row_offsets)`` -- one DMA per group in both directions."""
         dev = torch.device(device)
         packed_in = wav_offsets is not None
         if wav_host.dtype not in (torch.float32, torch.int16) or wav_host.stride(-1) != 1 or wav_host.dim() != (1 if packed_in else 2):
@@ -524,16 +547,19 @@ class GpuFbankFrontend(torch.nn.Module):
             offs = np.zeros(B, dtype=np.int64)
             np.cumsum((len_host[:-1] + al - 1) // al * al, out=offs[1:])
             total = int(offs[-1] + (len_host[-1] + al - 1) // al * al)
-        key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype, packed_in)
+        foff = np.zeros(B + 1, dtype=np.int64)                     # first feature row of every utterance in the packed layout
+        np.cumsum(T_host, out=foff[1:])
+        rows_total = int(foff[-1])
+        key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype, packed_in, packed_out, rows_total if packed_out else 0)
         c = self._host_cache.get(key)
         if c is None:
             self._host_cache.clear()
             # two staging buffers: the H2D copies of call k+1 overlap the compute / D2H tail of call k
             c = dict(wavs=[torch.zeros((total + 64,), dtype=wav_host.dtype, device=dev) for _ in range(2)],
                      wav_free=[None, None], turn=0,
-                     feats=torch.empty((B, Tmax, D), dtype=torch.float32, device=dev),
+                     feats=torch.empty((rows_total, D) if packed_out else (B, Tmax, D), dtype=torch.float32, device=dev),
                      flen=torch.empty((B,), dtype=torch.int64, device=dev),
-                     hfeats=torch.zeros((B, Tmax, D), dtype=torch.float32).pin_memory(),
+                     hfeats=torch.zeros((rows_total, D) if packed_out else (B, Tmax, D), dtype=torch.float32).pin_memory(),
                      hlen=torch.empty((B,), dtype=torch.int64, pin_memory=True),
                      hrows=np.zeros(B, dtype=np.int64),      # rows of the host buffer that are not known to be zero
                      s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev))
@@ -546,7 +572,7 @@ class GpuFbankFrontend(torch.nn.Module):
         # set-up per utterance; byte offsets and sizes of every row, device resident:
         #   0: host row start   1: packed device start   2: valid bytes   3: feature block start   4: feature bytes to bring back
         kh2d = self.kernel_h2d and wav_host.is_pinned() and not packed_in
-        kd2h = self.kernel_d2h and return_host
+        kd2h = self.kernel_d2h and return_host and not packed_out
         if kh2d or kd2h:
             tab = np.stack([np.arange(B, dtype=np.int64) * ((0 if packed_in else wav_host.stride(0)) * esz), offs * esz, len_host * esz,
                             np.arange(B, dtype=np.int64) * (Tmax * D * 4), d2h_rows * (D * 4)])
@@ -597,12 +623,18 @@ class GpuFbankFrontend(torch.nn.Module):
             ev_in.record(s_in)
             self.h2d_bytes += ((o1 - o0) * esz if packed_in else int(len_host[b0:b1].sum()) * esz) + (b1 - b0) * 16
             main.wait_event(ev_in)
-            self.forward(dwav, len_host[b0:b1], max_frames=Tmax, out=c["feats"][b0:b1], out_len=c["flen"][b0:b1],
-                         wav_offsets=offs[b0:b1])
+            r0, r1 = int(foff[b0]), int(foff[b1])
+            self.forward(dwav, len_host[b0:b1], max_frames=Tmax, out=c["feats"][r0:r1] if packed_out else c["feats"][b0:b1],
+                         out_len=c["flen"][b0:b1], wav_offsets=offs[b0:b1], packed_out=packed_out)
             if return_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
                 s_out.wait_event(ev_c)
+                if packed_out:
+                    with torch.cuda.stream(s_out):
+                        c["hfeats"][r0:r1].copy_(c["feats"][r0:r1], non_blocking=True)
+                    self.d2h_bytes += (r1 - r0) * D * 4
+                    continue
                 if kd2h:
                     _lib.check(lib.b200fe_copy_ragged(_ptr(c["feats"]), C.c_void_p(tptr + (3 * B + b0) * 8), C.c_void_p(c["hfeats"].data_ptr()),
                                                       C.c_void_p(tptr + (3 * B + b0) * 8), C.c_void_p(tptr + (4 * B + b0) * 8), b1 - b0,
@@ -623,8 +655,8 @@ class GpuFbankFrontend(torch.nn.Module):
             self.d2h_bytes += B * 8
             main.wait_stream(s_out)
             c["hrows"] = T_host.astype(np.int64).copy()
-            return c["hfeats"], c["hlen"]
-        return c["feats"], c["flen"]
+            return (c["hfeats"], c["hlen"], foff[:-1].copy()) if packed_out else (c["hfeats"], c["hlen"])
+        return (c["feats"], c["flen"], foff[:-1].copy()) if packed_out else (c["feats"], c["flen"])
 
     # -- global CMVN statistics (Kaldi compute-cmvn-stats), one fused pass without feature output --
     @torch.no_grad()

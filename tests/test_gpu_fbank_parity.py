@@ -388,3 +388,43 @@ def test_copy_ragged_c_abi(lasr_b200):
             want[dst_off[u]: dst_off[u] + nb[u]] = s_np[src_off[u]: src_off[u] + nb[u]]
         assert np.array_equal(dst.cpu().numpy(), want)
     assert lib.b200fe_copy_ragged(None, None, None, None, None, 1, 1, st) == -1
+
+
+def test_packed_feature_output(lasr_b200):
+    """Row F4: packed (sum T, D) output without padding rows equals the valid rows of the padded layout bit for bit --
+    plain, utterance CMVN (post pass on the packed tensor), global CMVN, zero-fill and mean-fill SpecAugment, int16 input,
+    and through the host pipeline (one DMA per group in both directions)."""
+    import random
+    rng = np.random.default_rng(31)
+    n = np.round(rng.uniform(0.1, 2.5, 10) * 16000).astype(np.int64)
+    n[0] = 400; n[4] = 400 + 160 * 31; n[5] = 400 + 160 * 32
+    wavs = [rng.uniform(-0.5, 0.5, k).astype(np.float32) for k in n]
+    wav, n = _pad_batch(wavs, "cuda:0")
+    stats = lasr_b200.GpuFbankFrontend().accumulate_stats(wav, n).cpu().numpy()
+    for kw in ({}, {"cmvn": "utt_meanvar"}, {"cmvn": "global", "cmvn_stats": stats}, {"peak_norm": True},
+               {"specaug": True, "replace_with_zero": True}, {"specaug": True, "cmvn": "utt_mean"}):
+        fe = lasr_b200.GpuFbankFrontend(**kw)
+        random.seed(3); np.random.seed(3)
+        ref, rlen = fe(wav, n)
+        random.seed(3); np.random.seed(3)
+        got, glen = fe(wav, n, packed_out=True)
+        offs = fe.last["feat_offsets"]
+        T = rlen.cpu().numpy()
+        assert got.shape == (int(T.sum()), 80) and torch.equal(glen, rlen)
+        assert np.array_equal(offs, np.concatenate([[0], np.cumsum(T)[:-1]]))
+        for b in range(len(n)):
+            assert torch.equal(got[offs[b]: offs[b] + T[b]], ref[b, : T[b]]), (kw, b)
+    fe = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+    ref, rlen = fe(wav, n)
+    T = rlen.cpu().numpy()
+    for src, dt in ((wavs, torch.float32),):
+        pk, lens, woffs = lasr_b200.GpuFbankFrontend.pack_host(src, dtype=dt)
+        for _ in range(2):
+            hf, hl, foffs = fe.extract_host(pk, lens, wav_offsets=woffs, group_bytes=120000, packed_out=True)
+        torch.cuda.synchronize()
+        assert hf.is_pinned() and hf.shape == (int(T.sum()), 80)
+        for b in range(len(n)):
+            assert torch.equal(hf[foffs[b]: foffs[b] + T[b]], ref[b, : T[b]].cpu())
+        df, dl, foffs = fe.extract_host(pk, lens, wav_offsets=woffs, return_host=False, packed_out=True)
+        torch.cuda.synchronize()
+        assert torch.equal(df.cpu(), hf)
