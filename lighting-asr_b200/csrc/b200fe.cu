@@ -459,6 +459,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     if (!p || !g) return fail(B200FE_EINVAL, "fbank_fused: null argument");
     if (!g->d_wav || !g->d_nsamp || g->batch <= 0 || g->wav_stride <= 0) return fail(B200FE_EINVAL, "fbank_fused: bad waveform arguments");
     if (!g->d_out && !g->d_stats) return fail(B200FE_EINVAL, "fbank_fused: neither an output nor a statistics buffer");
+    if (g->batch > 65535) return fail(B200FE_EINVAL, "fbank_fused: at most 65535 utterances per call (split the batch)");
     if (g->max_frames <= 0) return fail(B200FE_EINVAL, "fbank_fused: max_frames must be positive");
     if ((g->d_cmvn_mean == nullptr) != (g->d_cmvn_istd == nullptr)) return fail(B200FE_EINVAL, "fbank_fused: cmvn mean and istd go together");
     if (g->d_cmvn_mean && g->cmvn_stride != 0 && g->cmvn_stride != p->nmel) return fail(B200FE_EINVAL, "fbank_fused: cmvn_stride must be 0 or num_mel_bins");
@@ -550,6 +551,7 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     const int nm = g->n_freq_masks + g->n_time_masks;
     const bool masks = g->d_masks != nullptr && nm > 0;
     if (!masks && g->cmvn_mode == 0) return B200FE_OK;
+    if (g->batch > 65535) return fail(B200FE_EINVAL, "postpass: at most 65535 utterances per call (split the batch)");
     if (!g->d_stats || g->stats_stride <= 0) return fail(B200FE_EINVAL, "postpass: per-utterance statistics are required");
     if (g->cmvn_mode != 0 && (!g->d_cmvn_mean || !g->d_cmvn_istd)) return fail(B200FE_EINVAL, "postpass: cmvn workspace missing");
     if (masks && !g->d_fills) return fail(B200FE_EINVAL, "postpass: fill buffer missing");

@@ -428,3 +428,67 @@ def test_packed_feature_output(lasr_b200):
         df, dl, foffs = fe.extract_host(pk, lens, wav_offsets=woffs, return_host=False, packed_out=True)
         torch.cuda.synchronize()
         assert torch.equal(df.cpu(), hf)
+
+
+def test_signal_zoo_against_live_torchaudio(lasr_b200):
+    """Deterministic signals with extreme spectra (tones, chirp, impulses, DC steps, clipping, near-silence, int16-quantised
+    speech-like mixtures): the tolerance against live torchaudio holds on every cell that carries at least 1e-4 of its frame's
+    energy; in the weaker cells the GPU's error against the fp64 oracle stays within 2x of torchaudio-fp32's own, band by band;
+    padded rows are exactly zero."""
+    sr, N = 16000, 16000 * 3
+    t = np.arange(N) / sr
+    rng = np.random.default_rng(77)
+    zoo = {
+        "tone_440": 0.5 * np.sin(2 * np.pi * 440 * t),
+        "tone_7900": 0.25 * np.sin(2 * np.pi * 7900 * t),
+        "two_tones": 0.3 * np.sin(2 * np.pi * 97 * t) + 0.001 * np.sin(2 * np.pi * 3211 * t),
+        "chirp": 0.4 * np.sin(2 * np.pi * (50 + 2600 * t) * t),
+        "impulses": (np.arange(N) % 997 == 0).astype(np.float64) * 0.9,
+        "dc_steps": np.where((np.arange(N) // 4000) % 2 == 0, 0.7, -0.2) + 1e-3 * rng.standard_normal(N),
+        "clipped": np.clip(3.0 * np.sin(2 * np.pi * 220 * t) + 0.2 * rng.standard_normal(N), -1, 1),
+        "quiet": 3e-5 * rng.standard_normal(N),
+        "silence_then_noise": np.concatenate([np.zeros(N // 2), 0.1 * rng.standard_normal(N - N // 2)]),
+        "pcm_speechlike": np.round((0.3 * np.sin(2 * np.pi * 180 * t) * (1 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.05 * np.sin(2 * np.pi * 2300 * t)
+                                    + 0.01 * rng.standard_normal(N)) * 32768) / 32768,
+    }
+    names = list(zoo)
+    wavs = [zoo[k][: N - 137 * i] for i, k in enumerate(names)]          # ragged on purpose
+    wav, n = _pad_batch(wavs, "cuda:0")
+    fe = lasr_b200.GpuFbankFrontend()
+    feats, flen = fe(wav, n)
+    torch.cuda.synchronize()
+    g = feats.cpu().numpy()
+    assert np.isfinite(g).all()
+    report = {}
+    for i, k in enumerate(names):
+        w = wavs[i].astype(np.float32)
+        ta = _ta_fbank(w)
+        T = ta.shape[0]
+        assert int(flen[i]) == T and np.all(g[i, T:] == 0)
+        ref64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64)
+        lin64 = lasr_frontend.wav_to_kaldi_fbank(w, dtype=np.float64, use_log_fbank=False)
+        # Tonal signals put most mel bins 60-100 dB under the frame energy, and a large DC offset cancels in the mean
+        # removal: there fp32 rounding noise of ANY implementation dominates.  torchaudio-fp32 itself misses the tolerance
+        # against exact (fp64) arithmetic in cells whose energy is below ~1e-4 of the frame's (measured: "two_tones" 72 of
+        # 2204 cells in [1e-8, 1e-7); "dc_steps" 8 of 4672 in [1e-6, 1e-4); none above 1e-4), and two CPU fp32 evaluations with
+        # the same operation order (torchaudio vs the numpy oracle) differ by more than the tolerance in the same bands.
+        # So: strict tolerance against torchaudio above 1e-4 of the frame energy; below that, band by band, the GPU must be
+        # as close to the fp64 truth as torchaudio-fp32 is (violation count and worst error within 2x).
+        ratio = lin64 / np.maximum(lin64.sum(axis=1, keepdims=True), 1e-300)
+        tol = 1e-5 + 1e-4 * np.abs(ta)
+        strict = ratio >= 1e-4
+        hard = int((np.abs(g[i, :T] - ta)[strict] > tol[strict]).sum())
+        e_gpu, e_ta = np.abs(g[i, :T] - ref64), np.abs(ta - ref64)
+        report[k] = dict(strict_cells=int(strict.sum()), hard=hard, max_vs_ta_strict=float(np.abs(g[i, :T] - ta)[strict].max()) if strict.any() else 0.0)
+        assert hard == 0, (k, report[k])
+        for lo, hi in ((1e-6, 1e-4), (1e-8, 1e-6), (0.0, 1e-8)):
+            band = (ratio >= lo) & (ratio < hi)
+            if not band.any():
+                continue
+            v_gpu, v_ta = int((e_gpu[band] > tol[band]).sum()), int((e_ta[band] > tol[band]).sum())
+            m_gpu, m_ta = float(e_gpu[band].max()), float(e_ta[band].max())
+            report[k]["band_%g" % hi] = (int(band.sum()), v_gpu, v_ta, m_gpu, m_ta)
+            assert v_gpu <= 2 * v_ta + 0.02 * band.sum() + 5, (k, report[k])
+            assert m_gpu <= 2 * m_ta + 1e-3, (k, report[k])
+    for k, v in report.items():
+        print(k, v)
