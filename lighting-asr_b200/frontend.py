@@ -491,9 +491,10 @@ class GpuFbankFrontend(torch.nn.Module):
     # -- host-to-host path: the drop-in for the reference's collate_fn (features back on the host) --
     @torch.no_grad()
     @staticmethod
-    def pack_host(wavs, dtype=torch.float32, pin=True):
+    def pack_host(wavs, dtype=torch.float32, pin=True, out=None):
         """Packs a list of 1-D utterances (what the reference's collate loop receives, dataset.py:190-206) into ONE
         host buffer with 16-byte aligned starts -- the layout extract_host moves with a single DMA per group.
+        ``out``: a (pinned) 1-D tensor to reuse when it is large enough (pinning costs milliseconds; a loader keeps one).
         Returns (packed CPU tensor, lengths int64, offsets int64)."""
         esz = torch.empty((), dtype=dtype).element_size()
         al = 16 // esz
@@ -501,12 +502,16 @@ class GpuFbankFrontend(torch.nn.Module):
         offs = np.zeros(len(wavs), dtype=np.int64)
         np.cumsum((lens[:-1] + al - 1) // al * al, out=offs[1:])
         total = int(offs[-1] + (lens[-1] + al - 1) // al * al) if len(wavs) else 0
-        buf = torch.zeros((total,), dtype=dtype)
-        if pin:
-            buf = buf.pin_memory()
+        if out is not None and out.dtype == dtype and out.dim() == 1 and out.numel() >= total:
+            buf = out[:total]
+        else:
+            buf = torch.empty((total,), dtype=dtype)
+            if pin:
+                buf = buf.pin_memory()
         view = buf.numpy()
-        for w, o, k in zip(wavs, offs, lens):
+        for w, o, k, nxt in zip(wavs, offs, lens, list(offs[1:]) + [total]):
             view[o:o + k] = w
+            view[o + k:nxt] = 0                       # alignment gap
         return buf, lens, offs
 
     @torch.no_grad()

@@ -30,6 +30,8 @@ class GpuTransform:
         self.device = torch.device(device)
         self.return_tensor = return_tensor
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
+        # Register.register prints `value.__name__` when it overrides a key (lasr/utils/register.py:10-11)
+        self.__name__ = "GpuTransform"
 
     def __call__(self, wav):
         w = np.asarray(wav)
@@ -75,14 +77,15 @@ class B200Collate:
         self.device = torch.device(device)
         self.to_host = to_host
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
+        self._pinned = None             # packed pinned staging buffer, grown on demand and reused across batches
 
     def __call__(self, wavs):
-        n = np.array([len(w) for w in wavs], dtype=np.int64)
-        nmax = int((n.max() + 3) // 4 * 4)
-        host = torch.zeros((len(wavs), nmax), dtype=torch.float32).pin_memory()
-        for i, w in enumerate(wavs):
-            host[i, : n[i]] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
-        feats, flen = self.frontend.extract_host(host, n, device=self.device, return_host=self.to_host)
+        need = sum((len(w) + 3) // 4 * 4 for w in wavs)
+        if self._pinned is None or self._pinned.numel() < need:
+            self._pinned = torch.empty((int(need * 1.25) + 64,), dtype=torch.float32).pin_memory()
+        # utterances back to back in one pinned buffer: one DMA per group instead of a padded (B, Nmax) batch
+        host, n, offs = GpuFbankFrontend.pack_host(wavs, out=self._pinned)
+        feats, flen = self.frontend.extract_host(host, n, device=self.device, return_host=self.to_host, wav_offsets=offs)
         if self.to_host:
             return {"wav_array": feats.clone(), "wav_len": flen.clone()}
         torch.cuda.current_stream(self.device).synchronize()

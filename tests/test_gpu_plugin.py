@@ -17,7 +17,7 @@ class Register(dict):
             if not callable(value):
                 raise Exception("register object must be callable")
             if key in self:
-                print("warning: %s has been registered before, so we will overriden it" % key)
+                print("warning: %s has been registered before, so we will overriden it" % value.__name__)   # register.py:10-11
             self[key] = value
             return value
         return (lambda x: add(target, x)) if not callable(target) else add(target.__name__, target)

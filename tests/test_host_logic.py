@@ -147,3 +147,41 @@ def test_no_cpu_path(lasr_b200):
         lasr_b200.GpuFbankFrontend(snip_edges=False)
     with pytest.raises(ValueError):
         lasr_b200.GpuFbankFrontend(cmvn="global")
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "lasr")), reason="the reference checkout is only present in the build container")
+def test_plugin_points_with_the_real_reference(lasr_b200, capsys):
+    """The two plug-in points of SURVEY 8(b) against the UNMODIFIED reference code (no GPU needed: plans are created lazily):
+    the transform registry accepts the overrides with its own warning, and BaseConfig.check_kwargs accepts the YAML keys of
+    the dataset class (every key is a named __init__ parameter; unknown keys raise as they do for the reference's classes)."""
+    import sys
+    import types
+    for name in ("librosa", "soundfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from lasr.data.datatrans import register_trans
+    from lasr.utils.generater import BaseConfig
+    before = register_trans["fbank:80"]
+    try:
+        table = lasr_b200.lasr_plugin.install(register_trans, device="cuda:0", return_tensor=True)
+        assert "has been registered before" in capsys.readouterr().out          # lasr/utils/register.py:10-12
+        assert register_trans["fbank:80"] is table["fbank:80"] and "b200:norm+fbank:80" in register_trans
+        assert callable(register_trans["b200:norm+fbank:80+specaug"])
+        with pytest.raises(KeyError):
+            register_trans["no-such-transform"]
+    finally:
+        register_trans.register("fbank:80")(before)
+    cls = lasr_b200.lasr_plugin.make_dataset_class()
+    assert cls.__mro__[1].__name__ == "BatchAudioDataSet"
+    kwargs = dict(wav_list="wav.scp", text_list="text", batch_type="duration", batch_duration=500, peak_norm=True,
+                  cmvn="utt_meanvar", specaug=True, device="cuda:0")
+    cfg = BaseConfig("lasr_b200.lasr_plugin:B200BatchAudioDataSet", kwargs)                 # runs check_kwargs (generater.py:91-99)
+    assert cfg.conf_class is cls
+    with pytest.raises(ValueError):
+        BaseConfig("lasr_b200.lasr_plugin:B200BatchAudioDataSet", dict(kwargs, not_a_parameter=1))
+    # the front-end class itself is config-loadable too (model-side wrappers construct it from YAML)
+    BaseConfig("lasr_b200:GpuFbankFrontend", dict(num_mel_bins=80, cmvn="global", cmvn_stats=[[0.0] * 80, [1.0] * 80], specaug=True))
