@@ -123,6 +123,8 @@ def make_dataset_class():
                 wavs.append(w)
             out = {k: [it[k] for it in items] for k in items[0]}
             out.update(self._collate(wavs))
+            # the dummy (B, 1, 1) feature block MergeBatch builds when no feats scp is given (dataset.py:208-215)
+            out["feats_array"] = torch.from_numpy(batch_list([np.zeros((1, 1)) for _ in items], pad_value=self.pad_feats))
             out["token_id"] = torch.from_numpy(batch_list(out["token_id"], pad_value=self.tokenizer.ID_VALUE_PAD, dtype=np.int64))
             out["token_len"] = torch.from_numpy(np.array(out["token_len"], dtype=np.int64))
             return out
