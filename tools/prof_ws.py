@@ -1,3 +1,4 @@
+"""Small driver for ncu: a few launches of the fused kernel on a uniform 256 x 18 s batch (B200FE_WS=1 profiles the experimental kernel)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

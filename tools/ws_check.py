@@ -1,4 +1,4 @@
-"""Ad-hoc A/B: parity dump + timings of the fused launch for one library build (B200FE_LIB / B200FE_NO_WS)."""
+"""Ad-hoc A/B: parity dump + timings of the fused launch for one library build (B200FE_LIB selects the build, B200FE_WS=1 the experimental warp-specialised kernel)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

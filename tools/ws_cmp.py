@@ -1,3 +1,4 @@
+"""Compares the /tmp/ws_<tag>.npz dumps written by tools/ws_check.py (run on the same box): max |diff| and unequal cells per output."""
 import sys, numpy as np
 a = np.load("/tmp/ws_%s.npz" % sys.argv[1])
 for t in sys.argv[2:]:
