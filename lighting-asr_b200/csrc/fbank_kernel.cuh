@@ -41,6 +41,9 @@ namespace b200fe {
 #ifndef B200FE_EARLY_TMA
 #define B200FE_EARLY_TMA 0
 #endif
+#ifndef B200FE_XP_SHFL
+#define B200FE_XP_SHFL 0
+#endif
 #ifndef B200FE_ROWPART_PLAIN
 #define B200FE_ROWPART_PLAIN 0
 #endif
@@ -221,11 +224,26 @@ __device__ __forceinline__ void load_frame_single(float2 (&v)[16], const float* 
                                                   const FrameCtx& c, int l)
 {
     float2 acc2 = make_float2(0.f, 0.f);
+#if B200FE_XP_SHFL
+    // x[j-1] is the previous lane's second sample (lane 0: lane 15's second sample of the previous register): one shuffle
+    // instead of a 4-byte load that collides with the other half-warp's (frames start 0 mod 32 banks apart)
+    float2 xall[NLOAD];
+#pragma unroll
+    for (int n2 = 0; n2 < NLOAD; ++n2) xall[n2] = *reinterpret_cast<const float2*>(xf + 32 * n2);
+#endif
 #pragma unroll
     for (int n2 = 0; n2 < NLOAD; ++n2) {
         const int j = 2 * (l + 16 * n2);
+#if B200FE_XP_SHFL
+        float2 xr = xall[n2];
+        // lane l (> 0) takes lane l-1's y of this register; lane 0 takes lane 15's y of the previous register
+        const float snd = (n2 > 0 && l == 15) ? xall[n2 - 1].y : xall[n2].y;
+        const float got = __shfl_sync(0xffffffffu, snd, (l + 15) & 15, 16);
+        float xp = (n2 == 0 && l == 0) ? xall[0].x : got;
+#else
         float2 xr = *reinterpret_cast<const float2*>(xf + 32 * n2);
         float xp = (n2 == 0) ? xf[l == 0 ? 0 : -1] : xf[32 * n2 - 1];   // replicate pad at the frame start (TA:195)
+#endif
         if (kPeak) {
             xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale;
             xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
