@@ -76,6 +76,11 @@ int b200fe_plan_info(const b200fe_plan* plan, int what);
  * with at least one valid frame, in utterance order; returns the number of tiles (table may be NULL
  * to query the size), or a negative status. */
 int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host, int batch, int* table_host, int capacity);
+/* The same list plus PADDING tiles: an entry (utterance, -(row0 + 1)) makes the fused launch zero the rows
+ * [row0, row0 + 256) of that utterance (clipped at max_frames), so the zero padding of the reference's collate
+ * (lasr/data/dataset.py:18) is written by the same persistent CTAs, interleaved with the frame tiles, instead of by a
+ * separate streaming kernel.  Pass the result with b200fe_fbank_args.tile_table_pads != 0. */
+int b200fe_build_tile_table_padded(const b200fe_plan* plan, const long long* nsamp_host, int batch, int max_frames, int* table_host, int capacity);
 
 /* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
  * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
@@ -153,6 +158,9 @@ typedef struct b200fe_fbank_args {
      * [sum of frames][num_mel_bins] with no padding rows (utterance u occupies rows [d_out_offsets[u],
      * d_out_offsets[u] + frames[u])).  NULL = the reference's zero-padded [batch][max_frames][num_mel_bins] layout. */
     const long long* d_out_offsets;
+    /* Non-zero: d_tile_table also holds the padding tiles of b200fe_build_tile_table_padded; the separate zero-fill
+     * kernel is then skipped. */
+    int tile_table_pads;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

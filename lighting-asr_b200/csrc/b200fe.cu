@@ -348,6 +348,22 @@ extern "C" long long b200fe_num_frames(const b200fe_plan* p, long long n)
     return n < p->win ? 0 : 1 + (n - p->win) / p->shift;   // TA:63-67
 }
 
+extern "C" int b200fe_build_tile_table_padded(const b200fe_plan* p, const long long* nsamp, int batch, int max_frames, int* table, int capacity)
+{
+    if (!p || !nsamp || batch < 0 || max_frames <= 0) return fail(B200FE_EINVAL, "build_tile_table_padded: bad argument");
+    if (p->use_ws) return fail(B200FE_EINVAL, "build_tile_table_padded: not available with the experimental warp-specialised kernel");
+    long long n = 0;
+    for (int u = 0; u < batch; ++u) {
+        const long long T = std::min<long long>(b200fe_num_frames(p, nsamp[u]), max_frames);
+        for (long long f0 = 0; f0 < T; f0 += plan_tile_frames(p), ++n)
+            if (table && n < capacity) { table[2 * n] = u; table[2 * n + 1] = (int)f0; }
+        for (long long r0 = T; r0 < max_frames; r0 += kPadTileRows, ++n)      // padding tiles follow the utterance's frames
+            if (table && n < capacity) { table[2 * n] = u; table[2 * n + 1] = (int)(-r0 - 1); }
+    }
+    if (n > 0x7fffffffLL) return fail(B200FE_EINVAL, "build_tile_table_padded: too many tiles");
+    return (int)n;
+}
+
 extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* nsamp, int batch, int* table, int capacity)
 {
     if (!p || !nsamp || batch < 0) return fail(B200FE_EINVAL, "build_tile_table: bad argument");
@@ -523,8 +539,9 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (compact) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
+    if (compact && g->tile_table_pads && ws) return fail(B200FE_EINVAL, "fbank_fused: padding tiles are not available with the experimental kernel");
     if (compact || ws) {
-        if (g->d_out && !g->d_out_offsets) {                      // packed output has no padding rows
+        if (g->d_out && !g->d_out_offsets && !(compact && g->tile_table_pads)) {   // packed output has no padding rows; padding tiles zero them in the fused launch
             const long long per_utt = (long long)g->max_frames * p->nmel;
             dim3 zg((unsigned)((per_utt + 8191) / 8192), (unsigned)g->batch);
             zero_pad_kernel<<<zg, 256, 0, st>>>(g->d_out, g->d_nsamp, g->max_frames, p->nmel, p->win, p->shift);

@@ -60,6 +60,7 @@ constexpr int kMaxMel = 128;
 constexpr int kMaxTimeMasks = 4;
 constexpr int kMaxFreqMasks = 4;
 constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
+constexpr int kPadTileRows = 256;   // rows zeroed by one padding tile of the compact work list (table entry with first frame < 0)
 constexpr int kStages = 1;         // one tile buffer: the next tile's TMA is issued right after the phase-A barrier
 
 struct FbankArgs {
@@ -497,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             }
             if (dyn) { const int2 e = __ldg(a.tile_table + id); d.utt = e.x; d.f0 = e.y; }
             else { d.utt = (int)((unsigned)id / (unsigned)a.tiles_per_utt); d.f0 = (id - d.utt * a.tiles_per_utt) * kFT; }
+            if (d.f0 < 0) return d;                                     // padding tile: rows [-f0 - 1, +kPadTileRows) are zeroed
             const unsigned n = (unsigned)__ldg(a.nsamp + d.utt);       // < 2^31 samples per utterance
             d.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
         }
@@ -505,6 +507,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     auto geom = [&](const Desc& d) -> TileGeom {
         TileGeom g;
         g.utt = d.utt; g.f0 = d.f0; g.T = d.T;
+        if (d.f0 < 0) {          // padding tile of the compact list: no frames, rows [row0, row0 + kPadTileRows) clipped at Tmax
+            g.f0 = -d.f0 - 1;
+            g.nvalid = 0;
+            g.nrows = max(min(a.Tmax - g.f0, kPadTileRows), 0);
+            return g;
+        }
         g.nvalid = min(max(d.T - d.f0, 0), kFT);
         g.nrows = (dyn || a.out_offsets != nullptr) ? g.nvalid : min(a.Tmax - d.f0, kFT);
         return g;

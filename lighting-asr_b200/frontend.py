@@ -21,6 +21,28 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_PAD_ROWS = 256       # rows zeroed by one padding tile (kPadTileRows in fbank_kernel.cuh)
+
+
+def _tile_table(T, ft, Tmax=None):
+    """Compact work list of the fused launch (same order as b200fe_build_tile_table[_padded]): for every utterance its frame
+    tiles (utterance, first frame) and, when ``Tmax`` is given, its padding tiles (utterance, -(row0 + 1)) right after them, so
+    the zero fill of the padded rows is interleaved with the frame tiles."""
+    T = np.asarray(T, dtype=np.int64)
+    B = len(T)
+    nt = (T + ft - 1) // ft
+    npad = (np.maximum(Tmax - T, 0) + _PAD_ROWS - 1) // _PAD_ROWS if Tmax is not None else np.zeros(B, dtype=np.int64)
+    per = nt + npad
+    tot = int(per.sum())
+    tab = np.empty((tot, 2), dtype=np.int32)
+    utt = np.repeat(np.arange(B, dtype=np.int64), per)
+    k = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(per) - per, per)          # index of the tile inside its utterance
+    ntu, Tu = nt[utt], T[utt]
+    tab[:, 0] = utt
+    tab[:, 1] = np.where(k < ntu, k * ft, -(Tu + (k - ntu) * _PAD_ROWS) - 1)
+    return tab
+
+
 def _h2d(arr, dev):
     """Small host -> device upload (length vectors, tile tables, mask descriptors).  Pageable on purpose: the driver
     stages < 64 kB copies inline in the compute stream's command buffer, whereas a pinned source goes through the H2D
@@ -112,6 +134,7 @@ class FbankPlan:
         self.window_size = self.lib.b200fe_window_size(h)
         self.window_shift = self.lib.b200fe_window_shift(h)
         self.tile_frames = self.lib.b200fe_plan_info(h, 5)
+        self.uses_ws = bool(self.lib.b200fe_plan_info(h, 6))
         self.sample_frequency = sample_frequency
 
     def num_frames(self, n):
@@ -182,6 +205,7 @@ class GpuFbankFrontend(torch.nn.Module):
         self.compact_tiles = compact_tiles
         # extract_host: one copy kernel per group over pinned host memory instead of one DMA per utterance
         self.kernel_h2d = True
+        self.pad_tiles = True           # padded rows are zeroed by padding tiles inside the fused launch (False: separate zero-fill kernel)
         self.overlap_calls = True       # extract_host: the H2D copies of the next call may start before this call's D2H tail ends
         self.kernel_d2h = True
         self._plans = {}
@@ -395,16 +419,14 @@ class GpuFbankFrontend(torch.nn.Module):
                 # ragged batch: enumerate only tiles with valid frames (host lengths are known), dynamic scheduling
                 T_g = T_host[b0:b0 + nb]
                 ft = plan.tile_frames
-                nt = (T_g + ft - 1) // ft
-                tot = int(nt.sum())
-                tab = np.empty((tot, 2), dtype=np.int32)
-                tab[:, 0] = np.repeat(np.arange(nb, dtype=np.int32), nt)
-                starts = np.cumsum(nt) - nt
-                tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(starts, nt)).astype(np.int32) * ft
+                pads = self.pad_tiles and not packed_out and not plan.uses_ws
+                tab = _tile_table(T_g, ft, Tmax if pads else None)
+                tot = tab.shape[0]
                 tab_dev = _h2d(tab, dev)
                 counter = torch.empty((1,), dtype=torch.int32, device=dev)
                 a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
-                self.launch_count += 2          # counter memset + zero-pad kernel
+                a.tile_table_pads = 1 if pads else 0
+                self.launch_count += 1 if pads else 2      # counter memset (+ zero-pad kernel)
             if need_post:
                 a.d_stats = off(stats, b0, (n_cls + 1) * D * 8)
                 a.stats_stride = (n_cls + 1) * D
@@ -691,12 +713,8 @@ class GpuFbankFrontend(torch.nn.Module):
         a.max_frames = int(T_host.max())
         a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 2 * D, 1
         if self.compact_tiles:
-            ft = plan.tile_frames
-            nt = (T_host + ft - 1) // ft
-            tot = int(nt.sum())
-            tab = np.empty((tot, 2), dtype=np.int32)
-            tab[:, 0] = np.repeat(np.arange(B, dtype=np.int32), nt)
-            tab[:, 1] = (np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(nt) - nt, nt)).astype(np.int32) * ft
+            tab = _tile_table(T_host, plan.tile_frames)
+            tot = tab.shape[0]
             tab_dev = _h2d(tab, dev)
             counter = torch.empty((1,), dtype=torch.int32, device=dev)
             a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)

@@ -492,3 +492,42 @@ def test_signal_zoo_against_live_torchaudio(lasr_b200):
             assert m_gpu <= 2 * m_ta + 1e-3, (k, report[k])
     for k, v in report.items():
         print(k, v)
+
+
+def test_padding_tiles_zero_the_padded_rows(lasr_b200):
+    """The padded rows of the (B, Tmax, 80) batch (pad_audio = 0, dataset.py:18) are written by padding tiles inside the fused
+    launch: a NaN-prefilled output buffer comes back with exact zeros past every utterance's last frame, identical to the
+    separate zero-fill kernel; the Python work list equals the C ABI's."""
+    import ctypes as C
+    import importlib
+    rng = np.random.default_rng(41)
+    n = np.round(rng.uniform(0.05, 6.0, 17) * 16000).astype(np.int64)
+    n[0] = 400; n[3] = 400 + 160 * 255; n[4] = 400 + 160 * 256; n[5] = int(n.max())
+    wavs = [rng.uniform(-0.5, 0.5, k).astype(np.float32) for k in n]
+    wav, n = _pad_batch(wavs, "cuda:0")
+    for kw in ({}, {"cmvn": "utt_meanvar"}):
+        outs = []
+        for pads in (True, False):
+            fe = lasr_b200.GpuFbankFrontend(**kw)
+            fe.pad_tiles = pads
+            T, _ = fe.frame_counts(n)
+            out = torch.full((len(n), int(T.max()) + 300, 80), float("nan"), device="cuda:0")       # max_frames beyond the longest utterance
+            feats, flen = fe(wav, n, max_frames=out.shape[1], out=out)
+            torch.cuda.synchronize()
+            g = feats.cpu().numpy()
+            assert np.isfinite(g).all()
+            for b in range(len(n)):
+                assert np.all(g[b, T[b]:] == 0)
+            outs.append(g)
+        assert np.array_equal(outs[0], outs[1])
+    fe = lasr_b200.GpuFbankFrontend()
+    plan = fe.plan(torch.device("cuda:0"))
+    T, _ = fe.frame_counts(n)
+    Tmax = int(T.max()) + 300
+    front = importlib.import_module("lighting-asr_b200.frontend")
+    want = front._tile_table(T, plan.tile_frames, Tmax)
+    cnt = plan.lib.b200fe_build_tile_table_padded(plan.handle, n.ctypes.data_as(C.c_void_p), len(n), Tmax, None, 0)
+    assert cnt == want.shape[0]
+    got = np.zeros((cnt, 2), dtype=np.int32)
+    assert plan.lib.b200fe_build_tile_table_padded(plan.handle, n.ctypes.data_as(C.c_void_p), len(n), Tmax, got.ctypes.data_as(C.c_void_p), cnt) == cnt
+    assert np.array_equal(got, want)
