@@ -178,6 +178,19 @@ int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_
 int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                       float* h_feats, void* stream);
 
+/* Host-only SpecAugment planner (no device work): the rectangles of the reference's `freq_mask` / `time_mask` and the
+ * (center, warped) pair of `time_warp` for a whole batch, utterances in order, drawn exactly as the reference draws them
+ * (lasr/utils/specaugment.py:20-24,61-64,90-95): CPython `random.randrange` (MT19937, `_randbelow_with_getrandbits`) and
+ * numpy's legacy `numpy.random.randint` (MT19937, masked rejection), each on the caller's generator state -- `py_key` /
+ * `np_key` are the 624 key words of `random.getstate()` / `numpy.random.get_state()`, `*py_pos` / `*np_pos` their positions;
+ * all four are advanced in place, so putting them back leaves both global generators where the reference would leave them.
+ * frames[u] = number of feature frames.  masks [batch][n_freq_mask + n_time_mask][2] (start, stop; (0,0) = skipped),
+ * row_bounds [batch][2 n_time_mask] sorted (row classes of the statistics), warps [batch][2] or NULL ((-1,-1) = not warped;
+ * drawn only when draw_time_warp != 0). */
+int b200fe_specaug_plan(unsigned int* py_key, int* py_pos, unsigned int* np_key, int* np_pos, const long long* frames, int batch,
+                        int num_mel, int max_freq_width, int n_freq_mask, int max_time_width, int n_time_mask,
+                        int draw_time_warp, int max_time_warp, int* masks, int* row_bounds, int* warps);
+
 /* Encoder source mask without a host round trip.  The reference builds it on the CPU from `xlen.tolist()`
  * (lasr/model/e2e_ctc_att/e2e_base.py:19-20 -> make_pad_mask, lasr/utils/mask.py:5-45, then `~mask`, unsqueeze(-2)):
  *   subsample == 1:  d_mask [batch][1][max_frames]          = (t < frames[b])          -- the mask the encoder receives

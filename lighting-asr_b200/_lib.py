@@ -53,7 +53,7 @@ class WarpArgs(C.Structure):
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table", "b200fe_build_tile_table_padded",
-    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
+    "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_specaug_plan", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
 ]
 
 _lib = None
@@ -113,6 +113,8 @@ def load(build_if_missing=True):
     lib.b200fe_copy_ragged.restype = C.c_int
     lib.b200fe_src_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200fe_src_mask.restype = C.c_int
+    lib.b200fe_specaug_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 7 + [C.c_void_p] * 3
+    lib.b200fe_specaug_plan.restype = C.c_int
     lib.b200fe_postpass.argtypes = [C.c_void_p, C.POINTER(PostArgs), C.c_void_p]
     lib.b200fe_postpass.restype = C.c_int
     lib.b200fe_time_warp.argtypes = [C.c_void_p, C.POINTER(WarpArgs), C.c_void_p]

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -414,6 +415,112 @@ extern "C" int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const lo
                                  static_cast<const char*>(h_wav) + (long long)u * h_stride * elem_bytes,
                                  (size_t)elem_bytes * (size_t)h_nsamp[u], cudaMemcpyHostToDevice, st));
     }
+    return B200FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-only SpecAugment planner: replays the reference's draws on caller-held MT19937 states.
+//   * CPython `random.randrange(a, a + n)` (lasr/utils/specaugment.py:23-24,64,95): _randbelow_with_getrandbits,
+//     k = n.bit_length(), r = genrand_uint32() >> (32 - k) until r < n;
+//   * numpy legacy `numpy.random.randint(0, high, size)` (specaugment.py:61,90): masked rejection on 32-bit draws,
+//     val = next_uint32() & mask until val <= high - 1 (numpy/random/src/distributions: buffered_bounded_masked_uint32).
+// Both generators are MT19937 with the standard tempering; their states are what random.getstate() / numpy.random.get_state()
+// return (624 key words + position) and are advanced in place.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct Mt19937 {
+    unsigned int* key;
+    int pos;
+    unsigned int next32()
+    {
+        if (pos >= 624) {
+            for (int kk = 0; kk < 624; ++kk) {
+                const unsigned int y = (key[kk] & 0x80000000u) | (key[(kk + 1) % 624] & 0x7fffffffu);
+                key[kk] = key[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        unsigned int y = key[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    int py_randbelow(int n)                  // random.randrange(0, n), n > 0
+    {
+        int k = 0;
+        while ((n >> k) != 0) ++k;
+        unsigned int r;
+        do { r = next32() >> (32 - k); } while (r >= (unsigned int)n);
+        return (int)r;
+    }
+    int np_randint(int high)                 // numpy.random.randint(0, high), high > 0
+    {
+        const unsigned int rng = (unsigned int)high - 1u;
+        if (rng == 0) return 0;
+        unsigned int mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        unsigned int v;
+        while ((v = (next32() & mask)) > rng) {}
+        return (int)v;
+    }
+};
+}  // namespace
+
+extern "C" int b200fe_specaug_plan(unsigned int* py_key, int* py_pos, unsigned int* np_key, int* np_pos, const long long* frames, int batch,
+                                   int num_mel, int max_freq_width, int n_freq_mask, int max_time_width, int n_time_mask,
+                                   int draw_time_warp, int max_time_warp, int* masks, int* row_bounds, int* warps)
+{
+    if (!py_key || !py_pos || !np_key || !np_pos || (!frames && batch > 0) || batch < 0 || !masks || !row_bounds)
+        return fail(B200FE_EINVAL, "specaug_plan: bad argument");
+    if (*py_pos < 0 || *py_pos > 624 || *np_pos < 0 || *np_pos > 624) return fail(B200FE_EINVAL, "specaug_plan: bad generator position");
+    if (n_freq_mask < 0 || n_freq_mask > B200FE_MAX_FREQ_MASKS || n_time_mask < 0 || n_time_mask > B200FE_MAX_TIME_MASKS)
+        return fail(B200FE_EINVAL, "specaug_plan: too many masks");
+    if (max_freq_width <= 0 || max_time_width <= 0 || num_mel < max_freq_width || max_time_warp < 0)
+        return fail(B200FE_EINVAL, "specaug_plan: bad mask widths");
+    Mt19937 py{py_key, *py_pos}, np_{np_key, *np_pos};
+    const int nm = n_freq_mask + n_time_mask, W = max_time_warp;
+    for (int u = 0; u < batch; ++u) {
+        const long long T = frames[u];
+        int* mk = masks + (long long)u * nm * 2;
+        int* rb = row_bounds + (long long)u * 2 * n_time_mask;
+        // time warp first (specaugment.py:20-24): no draw when T - W <= W
+        int center = -1, warped = -1;
+        if (draw_time_warp && T - W > W) {
+            center = W + py.py_randbelow((int)(T - 2 * W));
+            warped = center - W + py.py_randbelow(2 * W) + 1;
+        }
+        if (warps) { warps[2 * u] = center; warps[2 * u + 1] = warped; }
+        // frequency masks (specaugment.py:61-74): one numpy call for the (n, 2) table, then a start per row
+        int fs[2 * B200FE_MAX_FREQ_MASKS];
+        for (int i = 0; i < 2 * n_freq_mask; ++i) fs[i] = np_.np_randint(max_freq_width);
+        for (int i = 0; i < n_freq_mask; ++i) {
+            const int f = fs[2 * i], w = fs[2 * i + 1];
+            const int f0 = py.py_randbelow(num_mel - f);                // drawn before the skip test (:64)
+            int lo = 0, hi = 0;
+            if (f != 0) { lo = std::min(f0, num_mel); hi = std::min(f0 + w, num_mel); if (hi <= lo) lo = hi = 0; }
+            mk[2 * i] = lo; mk[2 * i + 1] = hi;
+        }
+        // time masks (specaugment.py:90-105)
+        int ts[2 * B200FE_MAX_TIME_MASKS];
+        for (int i = 0; i < 2 * n_time_mask; ++i) ts[i] = np_.np_randint(max_time_width);
+        for (int i = 0; i < n_time_mask; ++i) {
+            const int t = ts[2 * i], w = ts[2 * i + 1];
+            int lo = 0, hi = 0;
+            if (T - t > 0) {                                            // else: skipped without drawing (:93-94)
+                const long long t0 = py.py_randbelow((int)(T - t));
+                if (t != 0) {
+                    lo = (int)std::min<long long>(t0, T); hi = (int)std::min<long long>(t0 + w, T);
+                    if (hi <= lo) lo = hi = 0;
+                }
+            }
+            mk[2 * (n_freq_mask + i)] = lo; mk[2 * (n_freq_mask + i) + 1] = hi;
+            rb[2 * i] = lo; rb[2 * i + 1] = hi;
+        }
+        std::sort(rb, rb + 2 * n_time_mask);
+    }
+    *py_pos = py.pos; *np_pos = np_.pos;
     return B200FE_OK;
 }
 

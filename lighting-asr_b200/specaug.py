@@ -7,9 +7,13 @@ CPython's ``random`` -- in a fixed interleaved order, per utterance, in batch or
 code here calls the very same global functions in the same order; only the *application* of the
 rectangles (and the running mean fills) happens on the GPU.
 """
+import array
+import contextlib
 import random
 
 import numpy as np
+
+_NO_LOCK = contextlib.nullcontext()
 
 MAX_FREQ_MASKS = 4
 MAX_TIME_MASKS = 4
@@ -58,13 +62,60 @@ def plan_utterance(num_frames, num_mel, max_freq_width=27, n_freq_mask=2, max_ti
 
 def plan_batch(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2,
                consume_time_warp_draws=False, max_time_warp=5, return_warp=False):
-    """Rectangles for a batch, utterances visited in order (dataset.py:190).
-
-    Same draws, in the same order, as calling ``plan_utterance`` per utterance (tested), written as a
-    tight loop because the RNG replay is the only per-utterance host work left on the path.
+    """Rectangles for a batch, utterances visited in order (dataset.py:190): the same draws, in the same order, from the same
+    two global generators as the reference's per-utterance calls -- replayed by ONE call into the C library
+    (b200fe_specaug_plan: CPython's ``random.randrange`` and numpy's legacy ``randint`` on their MT19937 states, which are read
+    with ``getstate`` / ``get_state`` and written back advanced).  Tested bit for bit, generator positions included, against
+    ``plan_batch_reference_loop`` (the same plan drawn with the real Python calls) and against the reference's own functions.
     Returns (masks [B, n_f + n_t, 2] int32, row_bounds [B, 2 n_t] int32 sorted); with ``return_warp`` also
     warps [B, 2] int32 = (center, warped) of the time warp that precedes the masks (specaugment.py:20-24),
     (-1, -1) where the utterance is too short to be warped."""
+    import ctypes as C
+    from . import _lib
+    n_f, n_t = n_freq_mask, n_time_mask
+    if n_f > MAX_FREQ_MASKS or n_t > MAX_TIME_MASKS:
+        raise ValueError("at most %d frequency and %d time masks are supported" % (MAX_FREQ_MASKS, MAX_TIME_MASKS))
+    T = np.ascontiguousarray(np.asarray(frame_lens, dtype=np.int64).reshape(-1))
+    B = len(T)
+    masks = np.zeros((B, n_f + n_t, 2), dtype=np.int32)
+    bounds = np.zeros((B, 2 * n_t), dtype=np.int32)
+    warps = np.full((B, 2), -1, dtype=np.int32)
+    if B == 0:
+        return (masks, bounds, warps) if return_warp else (masks, bounds)
+    # CPython's generator: state out as an array('I') (624 key words + position), back in as a tuple
+    version, internal, gauss = random.getstate()
+    py_state = array.array("I", internal)
+    py_addr = py_state.buffer_info()[0]
+    # numpy's legacy global generator: its MT19937 state struct {uint32 key[624]; int pos;} is advanced in place
+    np_state = np_keep = None
+    try:
+        bitgen = np.random.mtrand._rand._bit_generator
+        if type(bitgen).__name__ != "MT19937":
+            raise AttributeError
+        np_addr = int(bitgen.ctypes.state_address)
+        lock = bitgen.lock
+    except AttributeError:                                     # no raw access: copy the state out and back
+        np_state = np.random.get_state()
+        np_keep = np.concatenate([np.array(np_state[1], dtype=np.uint32), np.array([np_state[2]], dtype=np.uint32)])
+        np_addr = np_keep.ctypes.data
+        lock = _NO_LOCK
+    lib = _lib.load()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    with lock:
+        _lib.check(lib.b200fe_specaug_plan(C.c_void_p(py_addr), C.c_void_p(py_addr + 624 * 4), C.c_void_p(np_addr), C.c_void_p(np_addr + 624 * 4),
+                                           vp(T), B, int(num_mel), int(max_freq_width), n_f, int(max_time_width), n_t,
+                                           int(bool(consume_time_warp_draws)), int(max_time_warp), vp(masks), vp(bounds), vp(warps)),
+                   "b200fe_specaug_plan")
+    random.setstate((version, tuple(py_state), gauss))
+    if np_state is not None:
+        np.random.set_state((np_state[0], np_keep[:624], int(np_keep[624])) + tuple(np_state[3:]))
+    return (masks, bounds, warps) if return_warp else (masks, bounds)
+
+
+def plan_batch_reference_loop(frame_lens, num_mel, max_freq_width=27, n_freq_mask=2, max_time_width=40, n_time_mask=2,
+                              consume_time_warp_draws=False, max_time_warp=5, return_warp=False):
+    """The same plan with one Python call per draw on the real generators (what plan_batch replays in C): kept as the
+    executable specification the fast planner is tested against."""
     n_f, n_t = n_freq_mask, n_time_mask
     if n_f > MAX_FREQ_MASKS or n_t > MAX_TIME_MASKS:
         raise ValueError("at most %d frequency and %d time masks are supported" % (MAX_FREQ_MASKS, MAX_TIME_MASKS))

@@ -185,3 +185,41 @@ def test_plugin_points_with_the_real_reference(lasr_b200, capsys):
         BaseConfig("lasr_b200.lasr_plugin:B200BatchAudioDataSet", dict(kwargs, not_a_parameter=1))
     # the front-end class itself is config-loadable too (model-side wrappers construct it from YAML)
     BaseConfig("lasr_b200:GpuFbankFrontend", dict(num_mel_bins=80, cmvn="global", cmvn_stats=[[0.0] * 80, [1.0] * 80], specaug=True))
+
+
+def test_c_planner_replays_both_generators_exactly(lasr_b200):
+    """b200fe_specaug_plan (one C call per batch) against the same plan drawn with the real ``random.randrange`` /
+    ``numpy.random.randint`` calls: identical rectangles, row bounds and warp points, and both global generators end at the
+    same position (next uniform and next Gaussian draws agree), from mid-block positions and for non-default mask counts."""
+    sa = lasr_b200.specaug
+    for seed in range(25):
+        for consume in (False, True):
+            for kw in ({}, {"max_freq_width": 15, "n_freq_mask": 3, "max_time_width": 70, "n_time_mask": 4}, {"n_freq_mask": 0, "n_time_mask": 1}):
+                rng = np.random.default_rng(seed)
+                T = rng.integers(1, 400, 48)
+                T[:6] = [1, 5, 10, 11, 12, 39]
+                random.seed(seed)
+                np.random.seed(seed)
+                for _ in range(seed % 3):
+                    random.random()
+                    np.random.rand()
+                st0 = (random.getstate(), np.random.get_state())
+                a = sa.plan_batch(T, 80, consume_time_warp_draws=consume, return_warp=True, **kw)
+                after_a = (random.random(), np.random.rand(), random.gauss(0, 1), np.random.randn())
+                random.setstate(st0[0])
+                np.random.set_state(st0[1])
+                b = sa.plan_batch_reference_loop(T, 80, consume_time_warp_draws=consume, return_warp=True, **kw)
+                after_b = (random.random(), np.random.rand(), random.gauss(0, 1), np.random.randn())
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), (seed, consume, kw)
+                assert after_a == after_b, (seed, consume, kw)
+    # 624-word block boundaries: enough draws to regenerate both generators' states several times
+    random.seed(7)
+    np.random.seed(7)
+    T = np.full(700, 998)
+    st0 = (random.getstate(), np.random.get_state())
+    a = sa.plan_batch(T, 80, consume_time_warp_draws=True, return_warp=True)
+    after_a = (random.random(), np.random.rand())
+    random.setstate(st0[0])
+    np.random.set_state(st0[1])
+    b = sa.plan_batch_reference_loop(T, 80, consume_time_warp_draws=True, return_warp=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and after_a == (random.random(), np.random.rand())
