@@ -81,6 +81,13 @@ int b200fe_build_tile_table(const b200fe_plan* plan, const long long* nsamp_host
  * (lasr/data/dataset.py:18) is written by the same persistent CTAs, interleaved with the frame tiles, instead of by a
  * separate streaming kernel.  Pass the result with b200fe_fbank_args.tile_table_pads != 0. */
 int b200fe_build_tile_table_padded(const b200fe_plan* plan, const long long* nsamp_host, int batch, int max_frames, int* table_host, int capacity);
+/* The same work list built ON THE DEVICE from d_nsamp (one small kernel): no host-side table, no table upload.  d_table has room
+ * for `capacity` entries (b200fe_tile_table_capacity gives a sufficient bound), *d_n_tiles receives the number of entries and
+ * *d_work_counter is reset.  Pass d_table, n_tiles = capacity, d_n_tiles and d_work_counter to b200fe_fbank_fused (with
+ * tile_table_pads = with_pads). */
+int b200fe_tile_table_capacity(const b200fe_plan* plan, int batch, int max_frames, int with_pads);
+int b200fe_build_tile_table_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads,
+                                   int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, void* stream);
 
 /* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
  * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
@@ -161,6 +168,9 @@ typedef struct b200fe_fbank_args {
     /* Non-zero: d_tile_table also holds the padding tiles of b200fe_build_tile_table_padded; the separate zero-fill
      * kernel is then skipped. */
     int tile_table_pads;
+    /* Optional: the number of valid entries of d_tile_table lives in device memory (b200fe_build_tile_table_device); n_tiles
+     * is then only an upper bound used to size the grid, and the work counter is NOT reset by this call. */
+    const int* d_n_tiles;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

@@ -127,6 +127,56 @@ __global__ void __launch_bounds__(256) src_mask_kernel(const long long* __restri
     }
 }
 
+// Work list of the fused launch built on the device from the sample counts (same order and entries as
+// b200fe_build_tile_table[_padded]): per utterance its frame tiles (utt, first frame) and, with pads, its padding tiles
+// (utt, -(row0 + 1)).  One CTA: block-wide exclusive scan of the per-utterance entry counts, then every thread writes the
+// entries of its utterances.  Also publishes the tile count and resets the work counter of the dynamic scheduler, so a call
+// needs no host-side table, no table upload and no memset node.
+__global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long* __restrict__ nsamp, int B, int win, int shift, int ft,
+                                                                int Tmax, int pads, int pad_rows, int2* __restrict__ table, int capacity,
+                                                                int* __restrict__ ntiles_out, int* __restrict__ counter)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_base = 0; if (counter) *counter = 0; }
+    __syncthreads();
+    for (int u0 = 0; u0 < B; u0 += 1024) {
+        const int u = u0 + tid;
+        int T = 0, nt = 0, np_ = 0;
+        if (u < B) {
+            const long long n = nsamp[u];
+            long long Tl = n >= win ? 1 + (n - win) / shift : 0;
+            if (Tl > Tmax) Tl = Tmax;
+            T = (int)Tl;
+            nt = (T + ft - 1) / ft;
+            np_ = pads ? (max(Tmax - T, 0) + pad_rows - 1) / pad_rows : 0;
+        }
+        const int cnt = nt + np_;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            warp_sums[lane] = w;                     // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int base = s_base + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - cnt;
+        for (int k = 0; k < cnt; ++k) {
+            const int idx = base + k;
+            if (idx < capacity) table[idx] = k < nt ? make_int2(u, k * ft) : make_int2(u, -(T + (k - nt) * pad_rows) - 1);
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = base + cnt;        // total so far (the last thread holds the inclusive end)
+        __syncthreads();
+    }
+    if (tid == 0) *ntiles_out = min(s_base, capacity);
+}
+
 // int16 PCM abs-max: peak = max |s16| / 2^15 (what max |x| is after soundfile's conversion)
 __global__ void __launch_bounds__(256) absmax_i16_kernel(const short* __restrict__ wav, long long stride, const long long* __restrict__ offsets,
                                                          const long long* __restrict__ nsamp, float* __restrict__ peak)

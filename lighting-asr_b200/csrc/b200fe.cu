@@ -365,6 +365,27 @@ extern "C" int b200fe_build_tile_table_padded(const b200fe_plan* p, const long l
     return (int)n;
 }
 
+extern "C" int b200fe_tile_table_capacity(const b200fe_plan* p, int batch, int max_frames, int with_pads)
+{
+    if (!p || batch < 0 || max_frames <= 0) return fail(B200FE_EINVAL, "tile_table_capacity: bad argument");
+    const long long per = (max_frames + plan_tile_frames(p) - 1) / plan_tile_frames(p) + (with_pads ? (max_frames + kPadTileRows - 1) / kPadTileRows : 0);
+    const long long n = per * batch;
+    if (n > 0x7fffffffLL) return fail(B200FE_EINVAL, "tile_table_capacity: too many tiles");
+    return (int)std::max<long long>(n, 1);
+}
+
+extern "C" int b200fe_build_tile_table_device(const b200fe_plan* p, const long long* d_nsamp, int batch, int max_frames, int with_pads,
+                                              int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, void* stream)
+{
+    if (!p || !d_nsamp || !d_table || !d_n_tiles || batch <= 0 || max_frames <= 0 || capacity <= 0)
+        return fail(B200FE_EINVAL, "build_tile_table_device: bad argument");
+    if (p->use_ws && with_pads) return fail(B200FE_EINVAL, "build_tile_table_device: padding tiles are not available with the experimental kernel");
+    build_tile_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
+                                                                  kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_build_tile_table(const b200fe_plan* p, const long long* nsamp, int batch, int* table, int capacity)
 {
     if (!p || !nsamp || batch < 0) return fail(B200FE_EINVAL, "build_tile_table: bad argument");
@@ -618,6 +639,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.tiles_per_utt = (g->max_frames + tile_ft - 1) / tile_ft;
     const bool compact = g->d_tile_table != nullptr;
     if (compact && (!g->d_work_counter || g->n_tiles < 0)) return fail(B200FE_EINVAL, "fbank_fused: a tile table needs n_tiles and d_work_counter");
+    if (g->d_n_tiles && (!compact || ws)) return fail(B200FE_EINVAL, "fbank_fused: d_n_tiles needs a tile table (and the default kernel)");
     const long long ntiles = compact ? (long long)g->n_tiles : (long long)a.tiles_per_utt * g->batch;
     if (ntiles > 0x7fffffffLL) return fail(B200FE_EINVAL, "fbank_fused: too many tiles");
     a.ntiles = (int)ntiles;
@@ -631,6 +653,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
 
     a.tile_table = reinterpret_cast<const int2*>(g->d_tile_table);
     a.work_counter = g->d_work_counter;
+    a.ntiles_ptr = g->d_n_tiles;          // table built on the device: n_tiles is only the capacity bound for the grid size
     // Lock-step streaming (every utterance yields exactly max_frames frames): tiles take several utterances, so a 4-frame
     // push fills a 32-frame tile with 8 streams instead of occupying one tile per stream.
     if (g->uniform_frames && plan_has_multi(p) && !i16 && !compact && !ws && !g->d_out_offsets && g->max_frames <= kFT / 2 && !g->d_peak && !g->d_stats && !a.masks &&
@@ -645,7 +668,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (compact) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));
+    if (compact && !g->d_n_tiles) CUDA_TRY(cudaMemsetAsync(g->d_work_counter, 0, sizeof(int), st));   // the device builder resets it itself
     if (compact && g->tile_table_pads && ws) return fail(B200FE_EINVAL, "fbank_fused: padding tiles are not available with the experimental kernel");
     if (compact || ws) {
         if (g->d_out && !g->d_out_offsets && !(compact && g->tile_table_pads)) {   // packed output has no padding rows; padding tiles zero them in the fused launch

@@ -112,6 +112,7 @@ struct FbankArgs {
     // (dynamic scheduling; padded rows are then zeroed by zero_pad_kernel)
     const int2* tile_table;
     int* work_counter;
+    const int* ntiles_ptr;        // optional: the number of tiles lives in device memory (work list built on the device)
     int use_tma;
     int tile_floats;             // floats reserved per tile stage
     // multi-utterance tiles (lock-step streaming: every utterance yields exactly Tmax = multi_fpu frames): a tile takes
@@ -321,17 +322,19 @@ __device__ __forceinline__ void load_frame_single_i16(float2 (&v)[16], const sho
 }
 
 // 256-point family: two consecutive real frames a (at xa) and b (at xb) -> z[n] = ya[n] + j yb[n].
+// b_ok = false: frame b lies past the utterance's last frame; it is replaced by silence so that whatever the tile buffer holds
+// there (stale samples, possibly NaN bit patterns) cannot leak into frame a through the shared FFT's rounding.
 template <int NLOAD, bool kPeak, bool kDither>
 __device__ __forceinline__ void load_frame_dual(float2 (&v)[16], const float* __restrict__ xa, const float* __restrict__ xb,
-                                                const float* __restrict__ wls, const FrameCtx& c, int l)
+                                                const float* __restrict__ wls, const FrameCtx& c, int l, bool b_ok)
 {
     float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int n2 = 0; n2 < NLOAD; ++n2) {
         const int j = l + 16 * n2;
         const int po = (n2 == 0 && l == 0) ? 0 : 16 * n2 - 1;            // replicate pad at the frame start
-        float2 xr = make_float2(xa[16 * n2], xb[16 * n2]);
-        float2 xp = make_float2(xa[po], xb[po]);
+        float2 xr = make_float2(xa[16 * n2], b_ok ? xb[16 * n2] : 0.f);
+        float2 xp = make_float2(xa[po], b_ok ? xb[po] : 0.f);
         if (kPeak) {
             xr.x = peak_div(xr.x, c.pmax, c.prcp) * c.pscale; xr.y = peak_div(xr.y, c.pmax, c.prcp) * c.pscale;
             xp.x = peak_div(xp.x, c.pmax, c.prcp) * c.pscale; xp.y = peak_div(xp.y, c.pmax, c.prcp) * c.pscale;
@@ -486,11 +489,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     // tile table -> sample count) never sit on any warp's critical path.
     struct Desc { int id, utt, f0, T; };
     const bool dyn = a.tile_table != nullptr;
+    const int ntiles = a.ntiles_ptr != nullptr ? __ldg(a.ntiles_ptr) : a.ntiles;
     constexpr bool multi = kMulti;
     int4* s_desc = reinterpret_cast<int4*>(bars + 2);          // 16-byte aligned: two 8-byte slots are reserved for mbarriers
     auto resolve = [&](int id) -> Desc {               // thread 0 only
         Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
-        if (id < a.ntiles) {
+        if (id < ntiles) {
             if (multi) {                                    // the tile's utterances form one run of consecutive output rows
                 d.utt = id * a.multi_upt;
                 d.T = a.multi_fpu * min(a.multi_upt, a.B - d.utt);
@@ -551,24 +555,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     Desc cur, nxt;
     { const int4 v0 = s_desc[0], v1 = s_desc[1]; cur = Desc{v0.x, v0.y, v0.z, v0.w}; nxt = Desc{v1.x, v1.y, v1.z, v1.w}; }
     TileGeom g = geom(cur);
-    if (a.use_tma && tid == 0 && cur.id < a.ntiles) issue_load(g, 0);
+    if (a.use_tma && tid == 0 && cur.id < ntiles) issue_load(g, 0);
 
-    for (; cur.id < a.ntiles; ++it) {
+    for (; cur.id < ntiles; ++it) {
         const int utt = g.utt, f0 = g.f0, nvalid = g.nvalid, nrows = g.nrows;
         float* xs = reinterpret_cast<float*>(smem + L.tile_off[0]);
         const TileGeom gn = geom(nxt);
-        Desc fut; fut.id = a.ntiles; fut.utt = 0; fut.f0 = 0; fut.T = 0;
-        int4 nxt_desc = make_int4(a.ntiles, 0, 0, 0);
+        Desc fut; fut.id = ntiles; fut.utt = 0; fut.f0 = 0; fut.T = 0;
+        int4 nxt_desc = make_int4(ntiles, 0, 0, 0);
         if (tid == 0) {
             // descriptor of the tile after next: its loads complete while this tile is being computed
             const int id2 = dyn ? atomicAdd(a.work_counter, 1) : nxt.id + (int)gridDim.x;
-            fut = resolve(nxt.id < a.ntiles ? id2 : a.ntiles);
+            fut = resolve(nxt.id < ntiles ? id2 : ntiles);
         }
 
         if (a.use_tma) {
             // the tile buffer has been free since the last phase-A barrier: when the current tile carries no
             // frames (padded grid) the next tile's load can go out right away, otherwise after this tile's phase A
-            if (nvalid <= 0 && tid == 0 && nxt.id < a.ntiles) issue_load(gn, 0);
+            if (nvalid <= 0 && tid == 0 && nxt.id < ntiles) issue_load(gn, 0);
             // the mbarrier phase advances only for tiles that actually carried a load
             if (nvalid > 0) { mbar_wait(&bars[0], phase_bits & 1u); phase_bits ^= 1u; }
         } else if (nvalid > 0) {
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     // sample offset of the frame inside the tile buffer (multi-utterance tiles: slot -> (utterance, frame))
                     int foff = fl * a.shift;
                     if (multi) { const int uj = fl / a.multi_fpu; foff = uj * a.multi_span + (fl - uj * a.multi_fpu) * a.shift; }
-                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + foff + l, xs + foff + a.shift + l, wls, fc, l);
+                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + foff + l, xs + foff + a.shift + l, wls, fc, l, fl + 1 < nvalid);
                     else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + foff + 2 * l, wl, fc, l);
                     else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + foff + 2 * l, wl, fc, l);
                     if (kEarlyTma && last_pass && a.use_tma) {
@@ -682,13 +686,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             if (kEarlyTma && a.use_tma) {
                 if (tid == 0) {
                     mbar_wait(&bars[kStages], consumed_phase);
-                    if (nxt.id < a.ntiles) issue_load(gn, 0);
+                    if (nxt.id < ntiles) issue_load(gn, 0);
                 }
                 consumed_phase ^= 1u;
             }
             __syncthreads();   // B1: PT complete; every warp has finished phase C of the previous tile
             if (tid == 0) {
-                if (!kEarlyTma && a.use_tma && nxt.id < a.ntiles) issue_load(gn, 0);
+                if (!kEarlyTma && a.use_tma && nxt.id < ntiles) issue_load(gn, 0);
                 s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
             }
             // per-tile epilogue tables for phase C (written here: no warp is still reading the previous tile's)

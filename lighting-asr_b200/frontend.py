@@ -43,6 +43,30 @@ def _tile_table(T, ft, Tmax=None):
     return tab
 
 
+_TORCH_OF = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+             np.dtype(np.float64): torch.float64, np.dtype(np.uint8): torch.uint8}
+
+
+def _h2d_many(arrs, dev):
+    """ONE upload for several small host arrays (each pageable transfer costs ~80 us of host time): returns device tensors
+    that are 16-byte aligned views of a single buffer, in the order given (None entries pass through)."""
+    live = [(i, np.ascontiguousarray(a)) for i, a in enumerate(arrs) if a is not None]
+    out = [None] * len(arrs)
+    if not live:
+        return out
+    offs, total = [], 0
+    for _, a in live:
+        offs.append(total)
+        total += (a.nbytes + 15) // 16 * 16
+    host = np.empty(max(total, 16), dtype=np.uint8)
+    for (_, a), o in zip(live, offs):
+        host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+    d = torch.from_numpy(host).to(dev, non_blocking=True)
+    for (i, a), o in zip(live, offs):
+        out[i] = d[o:o + a.nbytes].view(_TORCH_OF[a.dtype]).reshape(a.shape) if a.nbytes else torch.empty(a.shape, dtype=_TORCH_OF[a.dtype], device=dev)
+    return out
+
+
 def _h2d(arr, dev):
     """Small host -> device upload (length vectors, tile tables, mask descriptors).  Pageable on purpose: the driver
     stages < 64 kB copies inline in the compute stream's command buffer, whereas a pinned source goes through the H2D
@@ -277,11 +301,10 @@ class GpuFbankFrontend(torch.nn.Module):
             off_host = np.ascontiguousarray(wav_offsets, dtype=np.int64)
             if (off_host % (16 // esz) != 0).any():
                 raise ValueError("wav_offsets must be multiples of 16 bytes")
-            off_dev = _h2d(off_host, dev)
             row_stride = int(wav.numel())
             row_elems = int(wav.numel())
         else:
-            off_dev = None
+            off_host = None
             row_stride = wav.stride(0)
             row_elems = wav.shape[1]
         plan = self.plan(dev)
@@ -291,7 +314,7 @@ class GpuFbankFrontend(torch.nn.Module):
             len_dev = wav_len.to(torch.int64).contiguous()
         else:
             len_host = np.asarray(wav_len, dtype=np.int64).reshape(-1)
-            len_dev = _h2d(len_host, dev)
+            len_dev = None                       # uploaded below together with the other small tables
         if len_host is not None:
             T_host, win = self.frame_counts(len_host)
             if (len_host < win).any():
@@ -310,7 +333,6 @@ class GpuFbankFrontend(torch.nn.Module):
                 raise ValueError("packed_out needs host lengths (the row offsets are their prefix sums)")
             ooff_host = np.zeros(B, dtype=np.int64)
             np.cumsum(T_host[:-1], out=ooff_host[1:])
-            ooff_dev = _h2d(ooff_host, dev)
             oshape = (int(T_host.sum()), D)
         else:
             oshape = (B, Tmax, D)
@@ -324,16 +346,7 @@ class GpuFbankFrontend(torch.nn.Module):
         cur_stream = torch.cuda.current_stream(dev)
         stream = C.c_void_p(cur_stream.cuda_stream)
 
-        peak = None
-        if self.peak_norm:
-            peak = torch.empty((B,), dtype=torch.float32, device=dev)
-            absmax = lib.b200fe_peak_absmax_i16 if i16 else lib.b200fe_peak_absmax
-            _lib.check(absmax(plan.handle, _ptr(wav), row_stride if not packed else int(len_host.max()) if len_host is not None else row_stride,
-                              _ptr(off_dev), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
-            self.launch_count += 2          # memset + abs-max kernel
-
         n_f = n_t = 0
-        masks_dev = bounds_dev = None
         if self.specaug:
             warp_np = None
             if masks is None:
@@ -346,8 +359,8 @@ class GpuFbankFrontend(torch.nn.Module):
                 n_f_, n_t_ = self.sa["n_freq_mask"], self.sa["n_time_mask"]
                 b_np = np.sort(m_np[:, n_f_:].reshape(B, -1), axis=1).astype(np.int32)
             n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
-            masks_dev = _h2d(m_np, dev)
-            bounds_dev = _h2d(b_np, dev)
+        else:
+            m_np = b_np = None
         mean_fill = self.specaug and not self.replace_with_zero
         utt_cmvn = self.cmvn in ("utt_mean", "utt_meanvar")
         need_post = mean_fill or utt_cmvn
@@ -366,6 +379,26 @@ class GpuFbankFrontend(torch.nn.Module):
             group = max(1, min(B, self.l2_chunk_bytes // max(per_utt, 1)))
         else:
             group = B
+        # ONE host -> device transfer per call for the small tables; the work list of the fused launch is built on the
+        # device from the sample counts (b200fe_build_tile_table_device), the experimental kernel keeps the host-built list
+        tab0 = None
+        pads = self.pad_tiles and not packed_out and not plan.uses_ws
+        dev_tables = self.compact_tiles and not plan.uses_ws
+        if self.compact_tiles and plan.uses_ws and len_host is not None and group >= B:
+            tab0 = _tile_table(T_host, plan.tile_frames, None)
+        up = _h2d_many([off_host, len_host if len_dev is None else None, m_np, b_np, ooff_host, tab0], dev)
+        off_dev, masks_dev, bounds_dev, ooff_dev, tab0_dev = up[0], up[2], up[3], up[4], up[5]
+        if len_dev is None:
+            len_dev = up[1]
+
+        peak = None
+        if self.peak_norm:
+            peak = torch.empty((B,), dtype=torch.float32, device=dev)
+            absmax = lib.b200fe_peak_absmax_i16 if i16 else lib.b200fe_peak_absmax
+            _lib.check(absmax(plan.handle, _ptr(wav), row_stride if not packed else int(len_host.max()) if len_host is not None else row_stride,
+                              _ptr(off_dev), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
+            self.launch_count += 2          # memset + abs-max kernel
+
         stats = cm = ci = fills = None
         if need_post:
             stats = torch.zeros((B, n_cls + 1, D), dtype=torch.float64, device=dev)
@@ -415,18 +448,28 @@ class GpuFbankFrontend(torch.nn.Module):
                 a.d_masks = off(masks_dev, b0, (n_f + n_t) * 2 * 4)
                 a.n_freq_masks, a.n_time_masks = n_f, n_t
                 a.mask_zero = int(self.replace_with_zero)
-            if self.compact_tiles and len_host is not None:
-                # ragged batch: enumerate only tiles with valid frames (host lengths are known), dynamic scheduling
-                T_g = T_host[b0:b0 + nb]
-                ft = plan.tile_frames
-                pads = self.pad_tiles and not packed_out and not plan.uses_ws
-                tab = _tile_table(T_g, ft, Tmax if pads else None)
-                tot = tab.shape[0]
-                tab_dev = _h2d(tab, dev)
+            if dev_tables:
+                # ragged batch: only tiles with valid frames (+ padding tiles), consumed through an atomic counter; the list,
+                # its length and the counter reset come from one small kernel on the device-resident sample counts
+                cap = lib.b200fe_tile_table_capacity(plan.handle, nb, Tmax, 1 if pads else 0)
+                work = torch.empty((2 * cap + 2,), dtype=torch.int32, device=dev)          # table | n_tiles | counter
+                _lib.check(lib.b200fe_build_tile_table_device(plan.handle, a.d_nsamp, nb, Tmax, 1 if pads else 0, _ptr(work), cap,
+                                                              C.c_void_p(work.data_ptr() + 8 * cap), C.c_void_p(work.data_ptr() + 8 * cap + 4), stream),
+                           "b200fe_build_tile_table_device")
+                a.d_tile_table, a.n_tiles = _ptr(work), cap
+                a.d_n_tiles, a.d_work_counter = C.c_void_p(work.data_ptr() + 8 * cap), C.c_void_p(work.data_ptr() + 8 * cap + 4)
+                a.tile_table_pads = 1 if pads else 0
+                self.launch_count += 1 if pads else 2      # table kernel (+ zero-pad kernel)
+            elif self.compact_tiles and len_host is not None:
+                if tab0_dev is not None:
+                    tab_dev, tot = tab0_dev, tab0.shape[0]
+                else:
+                    tab = _tile_table(T_host[b0:b0 + nb], plan.tile_frames, None)
+                    tot = tab.shape[0]
+                    tab_dev = _h2d(tab, dev)
                 counter = torch.empty((1,), dtype=torch.int32, device=dev)
                 a.d_tile_table, a.n_tiles, a.d_work_counter = _ptr(tab_dev), tot, _ptr(counter)
-                a.tile_table_pads = 1 if pads else 0
-                self.launch_count += 1 if pads else 2      # counter memset (+ zero-pad kernel)
+                self.launch_count += 2                     # counter memset + zero-pad kernel
             if need_post:
                 a.d_stats = off(stats, b0, (n_cls + 1) * D * 8)
                 a.stats_stride = (n_cls + 1) * D
@@ -712,7 +755,15 @@ class GpuFbankFrontend(torch.nn.Module):
         a.d_peak = _ptr(peak)
         a.max_frames = int(T_host.max())
         a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 2 * D, 1
-        if self.compact_tiles:
+        if self.compact_tiles and not plan.uses_ws:
+            cap = plan.lib.b200fe_tile_table_capacity(plan.handle, B, a.max_frames, 0)
+            work = torch.empty((2 * cap + 2,), dtype=torch.int32, device=dev)              # table | n_tiles | counter
+            _lib.check(plan.lib.b200fe_build_tile_table_device(plan.handle, _ptr(len_dev), B, a.max_frames, 0, _ptr(work), cap,
+                                                               C.c_void_p(work.data_ptr() + 8 * cap), C.c_void_p(work.data_ptr() + 8 * cap + 4), stream),
+                       "b200fe_build_tile_table_device")
+            a.d_tile_table, a.n_tiles = _ptr(work), cap
+            a.d_n_tiles, a.d_work_counter = C.c_void_p(work.data_ptr() + 8 * cap), C.c_void_p(work.data_ptr() + 8 * cap + 4)
+        elif self.compact_tiles:
             tab = _tile_table(T_host, plan.tile_frames)
             tot = tab.shape[0]
             tab_dev = _h2d(tab, dev)

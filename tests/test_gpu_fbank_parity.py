@@ -531,3 +531,26 @@ def test_padding_tiles_zero_the_padded_rows(lasr_b200):
     got = np.zeros((cnt, 2), dtype=np.int32)
     assert plan.lib.b200fe_build_tile_table_padded(plan.handle, n.ctypes.data_as(C.c_void_p), len(n), Tmax, got.ctypes.data_as(C.c_void_p), cnt) == cnt
     assert np.array_equal(got, want)
+    # the same list built on the device from the device-resident sample counts (what forward() uses), with and without pads,
+    # and for a batch larger than one scan chunk (1024 utterances)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    big = np.round(np.random.default_rng(3).uniform(0.03, 1.2, 2500) * 16000).astype(np.int64)
+    for lens, tmax in ((n, Tmax), (big, 150)):
+        Tl, _ = fe.frame_counts(lens)
+        Tl = np.minimum(Tl, tmax)
+        for with_pads in (1, 0):
+            ref_tab = front._tile_table(Tl, plan.tile_frames, tmax if with_pads else None)
+            cap = plan.lib.b200fe_tile_table_capacity(plan.handle, len(lens), tmax, with_pads)
+            assert cap >= ref_tab.shape[0]
+            work = torch.full((2 * cap + 2,), -7, dtype=torch.int32, device="cuda:0")
+            d_len = torch.from_numpy(lens).cuda()
+            rc = plan.lib.b200fe_build_tile_table_device(plan.handle, C.c_void_p(d_len.data_ptr()), len(lens), tmax, with_pads, C.c_void_p(work.data_ptr()),
+                                                         cap, C.c_void_p(work.data_ptr() + 8 * cap), C.c_void_p(work.data_ptr() + 8 * cap + 4), st)
+            assert rc == 0
+            w = work.cpu().numpy()
+            assert w[2 * cap] == ref_tab.shape[0] and w[2 * cap + 1] == 0
+            assert np.array_equal(w[: 2 * ref_tab.shape[0]].reshape(-1, 2), ref_tab)
+    # lengths that live on the device only: no host synchronisation, same features
+    feats_h, _ = fe(wav, n, max_frames=Tmax)
+    feats_d, _ = fe(wav, torch.from_numpy(n).cuda(), max_frames=Tmax)
+    assert torch.equal(feats_h, feats_d)
