@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long*
                                                                 int* __restrict__ ntiles_out, int* __restrict__ counter)
 {
     __shared__ int warp_sums[32];
+    __shared__ int s_off[1025];          // exclusive offsets of the chunk's utterances inside the chunk (+ total)
+    __shared__ int s_nt[1024], s_T[1024];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) { s_base = 0; if (counter) *counter = 0; }
@@ -165,13 +167,21 @@ __global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long*
             warp_sums[lane] = w;                     // inclusive scan of the warp totals
         }
         __syncthreads();
-        const int base = s_base + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - cnt;
-        for (int k = 0; k < cnt; ++k) {
-            const int idx = base + k;
-            if (idx < capacity) table[idx] = k < nt ? make_int2(u, k * ft) : make_int2(u, -(T + (k - nt) * pad_rows) - 1);
+        const int excl = (wid > 0 ? warp_sums[wid - 1] : 0) + incl - cnt;
+        s_off[tid] = excl; s_nt[tid] = nt; s_T[tid] = T;
+        if (tid == 1023) s_off[1024] = excl + cnt;
+        __syncthreads();
+        // cooperative fill: consecutive threads write consecutive entries (utterance found by binary search over the offsets)
+        const int total = s_off[1024], base = s_base;
+        for (int e = tid; e < total; e += 1024) {
+            int lo = 0, hi = 1023;                   // last j with s_off[j] <= e
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid - 1; }
+            const int k = e - s_off[lo], ntj = s_nt[lo];
+            const int idx = base + e;
+            if (idx < capacity) table[idx] = k < ntj ? make_int2(u0 + lo, k * ft) : make_int2(u0 + lo, -(s_T[lo] + (k - ntj) * pad_rows) - 1);
         }
         __syncthreads();
-        if (tid == 1023) s_base = base + cnt;        // total so far (the last thread holds the inclusive end)
+        if (tid == 0) s_base = base + total;
         __syncthreads();
     }
     if (tid == 0) *ntiles_out = min(s_base, capacity);
