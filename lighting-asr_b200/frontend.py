@@ -554,7 +554,6 @@ class GpuFbankFrontend(torch.nn.Module):
         return feats, flen
 
     # -- host-to-host path: the drop-in for the reference's collate_fn (features back on the host) --
-    @torch.no_grad()
     @staticmethod
     def pack_host(wavs, dtype=torch.float32, pin=True, out=None):
         """Packs a list of 1-D utterances (what the reference's collate loop receives, dataset.py:190-206) into ONE

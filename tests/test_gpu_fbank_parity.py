@@ -341,7 +341,7 @@ def test_extract_host_layouts_and_copy_engines(lasr_b200):
             fe = lasr_b200.GpuFbankFrontend(**kw)
             ref, rlen = fe(dev_in, n)
             host = dev_in.cpu().pin_memory()
-            pk, lens, offs = lasr_b200.GpuFbankFrontend.pack_host(srcs, dtype=dtype)
+            pk, lens, offs = fe.pack_host(srcs, dtype=dtype)            # callable on the instance as well as on the class
             assert np.array_equal(lens, n) and (offs % (16 // pk.element_size()) == 0).all()
             for kh, kd, ov in ((True, True, True), (False, False, False), (True, False, True), (False, True, False)):
                 fe.kernel_h2d, fe.kernel_d2h, fe.overlap_calls = kh, kd, ov
