@@ -323,7 +323,7 @@ def main():
                        "l2": "inputs (%.0f MB/step/GPU) exceed the 126 MB L2; no flush needed" % (wav_np.nbytes / 1e6),
                        "parallelism": "global batch of %d utterances sharded per utterance (length-balanced) x%d, no data-path collective" % (256 * world, world)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "kernel": "fbank_fused_kernel<13,true,false,false> (every fused launch of one step, incl. the zero fill of the padded rows by its padding tiles)",
+                         "traffic": traffic, "kernel": "fbank_fused_kernel<13,true,false,false,false,false,true> = lean instantiation of the default option set (every fused launch of one step, incl. the zero fill of the padded rows by its padding tiles)",
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": fused_per_step_ms,
                          "kernel_share_of_step": fused_per_step_ms / step_ms, "peak_source": peak_src},
             "e2e": {"value": hours_all / (e2e_ms / args.steps * 1e-3), "unit": "audio-h/s",

@@ -81,8 +81,11 @@ static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : k
 
 static bool plan_has_multi(const b200fe_plan* p) { return p->nload == 13 && (p->static_mel || p->nfft == 256); }
 
-static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false)
+static bool plan_has_lean(const b200fe_plan* p) { return p->nload == 13 && p->static_mel && p->nfft == 512; }
+
+static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false, bool lean = false)
 {
+    if (lean) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, true>;
     if (multi) {   // multi-utterance tiles (lock-step streaming): the two default option sets, float32, no peak normalisation
         if (p->nfft == 256) return (const void*)fbank_fused_kernel<13, false, false, true, false, true>;
         return (const void*)fbank_fused_kernel<13, true, false, false, false, true>;
@@ -291,6 +294,8 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     const void* kfn = plan_kernel(p, false);
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    if (e == cudaSuccess && plan_has_lean(p))
+        e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess && plan_has_multi(p))
         e = cudaFuncSetAttribute(plan_kernel(p, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (p->nfft == 512) {
@@ -687,7 +692,9 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         return B200FE_OK;
     }
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0), dim3(grid), dim3(kThreads), kargs,
+    // the lean instantiation serves the default option set whenever the launch applies no CMVN, no masks and writes the padded layout
+    const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets;
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean), dim3(grid), dim3(kThreads), kargs,
                               (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
     return B200FE_OK;
 }
