@@ -69,7 +69,8 @@ int b200fe_padded_window_size(const b200fe_plan* plan);
 long long b200fe_num_frames(const b200fe_plan* plan, long long num_samples);
 /* Introspection for tests / benchmarks: what = 0 straight-line mel path in use, 1 registers
  * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count, 5 frames
- * per tile (the granularity of b200fe_build_tile_table). */
+ * per tile (the granularity of b200fe_build_tile_table), 6 experimental warp-specialised kernel in use, 7 in-launch utterance CMVN
+ * (apply tiles) available. */
 int b200fe_plan_info(const b200fe_plan* plan, int what);
 
 /* Host helper: fills table[2*i] = utterance, table[2*i+1] = first frame for every tile (b200fe_plan_info(plan, 5) frames)
@@ -88,6 +89,23 @@ int b200fe_build_tile_table_padded(const b200fe_plan* plan, const long long* nsa
 int b200fe_tile_table_capacity(const b200fe_plan* plan, int batch, int max_frames, int with_pads);
 int b200fe_build_tile_table_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads,
                                    int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, void* stream);
+/* The device-side builder with two options.  (1) d_zero / zero_bytes (optional, 16-byte aligned, multiple of 16): a buffer
+ * the same kernel clears -- the statistics accumulators of the call -- which saves the memset in front of the fused launch.
+ * (2) apply_lag > 0: CMVN-APPLY tiles (utterance CMVN inside the fused launch instead of b200fe_postpass, for the
+ * `_subtract_column_mean` semantics of TA:220-226,644 and its mean/variance extension): besides the frame and padding tiles of
+ * utterance u, slot u of the list carries the apply tiles of utterance u - apply_lag, entries (utterance | 0x40000000, row0) =
+ * normalise rows [row0, row0 + 240) of that utterance in place; the last apply_lag utterances' apply tiles close the list.  A
+ * persistent CTA that takes an apply tile waits until all frame tiles of that utterance have been signalled in
+ * d_utt_done[utterance] (int32 [batch + 1], zeroed by this call; element [batch] becomes non-zero if an apply tile ever gave up
+ * waiting -- never expected, checked by the tests), reads the utterance's column sums from d_stats and rewrites the rows while
+ * they are still L2-resident.  64 is a good lag: a CTA publishes the completions of eight tiles behind one fence and the
+ * persistent grid holds about 900 claimed tiles, so the frame tiles an apply tile depends on have normally been signalled when it
+ * is claimed.  Capacity with apply tiles: b200fe_tile_table_capacity(...) + batch * ceil(max_frames / 240).  Pass d_utt_done and
+ * apply_cmvn_mode to b200fe_fbank_fused.  Needs b200fe_plan_info(plan, 7) != 0.  Measured on B200 (BASELINE config 2): 0.409 ms
+ * per step against 0.415 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3. */
+int b200fe_build_work_list_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads, int apply_lag,
+                                  int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, int* d_utt_done,
+                                  void* d_zero, long long zero_bytes, void* stream);
 
 /* Peak normalisation statistics: d_peak[b] = max |wav[b][0..nsamp[b])|.
  * Replaces the abs-max half of VoiceNorm (R/lasr/data/datatrans.py:22-27); the division is
@@ -171,6 +189,15 @@ typedef struct b200fe_fbank_args {
     /* Optional: the number of valid entries of d_tile_table lives in device memory (b200fe_build_tile_table_device); n_tiles
      * is then only an upper bound used to size the grid, and the work counter is NOT reset by this call. */
     const int* d_n_tiles;
+    /* Utterance CMVN applied INSIDE the launch by the apply tiles of b200fe_build_work_list_device: 0 = off, 1 = subtract the
+     * utterance's column means (torchaudio's subtract_mean, TA:220-226), 2 = mean and variance ((x - mean) / std, variance
+     * floored at 1e-20: the definition of b200fe_postpass).  Needs d_stats with stats_stride > 0 (per-utterance sums, one row
+     * class), d_utt_done (int32 [batch + 1], zeroed by the list builder), the padded output layout and the default option set
+     * (b200fe_plan_info(plan, 7) != 0); d_utt_mean / d_utt_istd (optional, [batch][num_mel_bins]) receive the vectors used. */
+    int apply_cmvn_mode;
+    int* d_utt_done;
+    float* d_utt_mean;
+    float* d_utt_istd;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

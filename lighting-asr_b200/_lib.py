@@ -29,6 +29,7 @@ class FbankArgs(C.Structure):
         ("d_wav_offsets", C.c_void_p), ("offsets_aligned", C.c_int),
         ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p), ("wav_dtype", C.c_int), ("uniform_frames", C.c_int),
         ("d_out_offsets", C.c_void_p), ("tile_table_pads", C.c_int), ("d_n_tiles", C.c_void_p),
+        ("apply_cmvn_mode", C.c_int), ("d_utt_done", C.c_void_p), ("d_utt_mean", C.c_void_p), ("d_utt_istd", C.c_void_p),
     ]
 
 
@@ -52,7 +53,7 @@ class WarpArgs(C.Structure):
 
 EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
-    "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table", "b200fe_build_tile_table_padded", "b200fe_tile_table_capacity", "b200fe_build_tile_table_device",
+    "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table", "b200fe_build_tile_table_padded", "b200fe_tile_table_capacity", "b200fe_build_tile_table_device", "b200fe_build_work_list_device",
     "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_specaug_plan", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
 ]
 
@@ -103,6 +104,8 @@ def load(build_if_missing=True):
     lib.b200fe_tile_table_capacity.restype = C.c_int
     lib.b200fe_build_tile_table_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200fe_build_tile_table_device.restype = C.c_int
+    lib.b200fe_build_work_list_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_ll, C.c_void_p]
+    lib.b200fe_build_work_list_device.restype = C.c_int
     lib.b200fe_peak_absmax.argtypes = [C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.b200fe_peak_absmax.restype = C.c_int
     lib.b200fe_peak_absmax_i16.argtypes = lib.b200fe_peak_absmax.argtypes

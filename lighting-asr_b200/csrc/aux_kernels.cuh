@@ -131,30 +131,43 @@ __global__ void __launch_bounds__(256) src_mask_kernel(const long long* __restri
 // b200fe_build_tile_table[_padded]): per utterance its frame tiles (utt, first frame) and, with pads, its padding tiles
 // (utt, -(row0 + 1)).  One CTA: block-wide exclusive scan of the per-utterance entry counts, then every thread writes the
 // entries of its utterances.  Also publishes the tile count and resets the work counter of the dynamic scheduler, so a call
-// needs no host-side table, no table upload and no memset node.
+// needs no host-side table, no table upload and no memset node.  Launched with a few CTAs: every CTA repeats the (cheap) scan and
+// writes its share of the entries; the optional buffer `zero16` (the statistics accumulators of the same call) is cleared by all
+// of them, which saves the memset node in front of the fused launch.
+// apply_lag > 0 (b200fe_build_work_list_device): slot u additionally carries the CMVN-apply tiles (utt | apply_bit, row0) of
+// utterance u - apply_lag, apply_lag extra slots close the list, and the per-utterance completion counters are zeroed.
 __global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long* __restrict__ nsamp, int B, int win, int shift, int ft,
                                                                 int Tmax, int pads, int pad_rows, int2* __restrict__ table, int capacity,
-                                                                int* __restrict__ ntiles_out, int* __restrict__ counter)
+                                                                int* __restrict__ ntiles_out, int* __restrict__ counter,
+                                                                int apply_lag, int apply_bit, int apply_rows, int* __restrict__ utt_done,
+                                                                uint4* __restrict__ zero16, long long n_zero16)
 {
     __shared__ int warp_sums[32];
     __shared__ int s_off[1025];          // exclusive offsets of the chunk's utterances inside the chunk (+ total)
-    __shared__ int s_nt[1024], s_T[1024];
+    __shared__ int s_nt[1024], s_T[1024], s_np[1024];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_base = 0; if (counter) *counter = 0; }
+    if (tid == 0) { s_base = 0; if (counter && blockIdx.x == 0) *counter = 0; }
+    if (utt_done && blockIdx.x == 0) for (int u = tid; u <= B; u += 1024) utt_done[u] = 0;      // [B] = error flag of the apply tiles
+    for (long long i = (long long)blockIdx.x * 1024 + tid; i < n_zero16; i += 1024LL * gridDim.x) zero16[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int u0 = 0; u0 < B; u0 += 1024) {
+    auto frames_of = [&](int u) -> int {
+        const long long n = nsamp[u];
+        long long Tl = n >= win ? 1 + (n - win) / shift : 0;
+        if (Tl > Tmax) Tl = Tmax;
+        return (int)Tl;
+    };
+    const int nslots = B + (apply_lag > 0 ? apply_lag : 0);
+    for (int u0 = 0; u0 < nslots; u0 += 1024) {
         const int u = u0 + tid;
-        int T = 0, nt = 0, np_ = 0;
+        int T = 0, nt = 0, np_ = 0, na = 0;
         if (u < B) {
-            const long long n = nsamp[u];
-            long long Tl = n >= win ? 1 + (n - win) / shift : 0;
-            if (Tl > Tmax) Tl = Tmax;
-            T = (int)Tl;
+            T = frames_of(u);
             nt = (T + ft - 1) / ft;
             np_ = pads ? (max(Tmax - T, 0) + pad_rows - 1) / pad_rows : 0;
         }
-        const int cnt = nt + np_;
+        if (apply_lag > 0 && u >= apply_lag && u - apply_lag < B) na = (frames_of(u - apply_lag) + apply_rows - 1) / apply_rows;
+        const int cnt = nt + np_ + na;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -168,23 +181,26 @@ __global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long*
         }
         __syncthreads();
         const int excl = (wid > 0 ? warp_sums[wid - 1] : 0) + incl - cnt;
-        s_off[tid] = excl; s_nt[tid] = nt; s_T[tid] = T;
+        s_off[tid] = excl; s_nt[tid] = nt; s_T[tid] = T; s_np[tid] = np_;
         if (tid == 1023) s_off[1024] = excl + cnt;
         __syncthreads();
         // cooperative fill: consecutive threads write consecutive entries (utterance found by binary search over the offsets)
         const int total = s_off[1024], base = s_base;
-        for (int e = tid; e < total; e += 1024) {
+        for (int e = tid + 1024 * (int)blockIdx.x; e < total; e += 1024 * (int)gridDim.x) {
             int lo = 0, hi = 1023;                   // last j with s_off[j] <= e
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid - 1; }
-            const int k = e - s_off[lo], ntj = s_nt[lo];
+            const int k = e - s_off[lo], ntj = s_nt[lo], npj = s_np[lo];
             const int idx = base + e;
-            if (idx < capacity) table[idx] = k < ntj ? make_int2(u0 + lo, k * ft) : make_int2(u0 + lo, -(s_T[lo] + (k - ntj) * pad_rows) - 1);
+            if (idx < capacity)
+                table[idx] = k < ntj ? make_int2(u0 + lo, k * ft)
+                           : k < ntj + npj ? make_int2(u0 + lo, -(s_T[lo] + (k - ntj) * pad_rows) - 1)
+                                           : make_int2((u0 + lo - apply_lag) | apply_bit, (k - ntj - npj) * apply_rows);
         }
         __syncthreads();
         if (tid == 0) s_base = base + total;
         __syncthreads();
     }
-    if (tid == 0) *ntiles_out = min(s_base, capacity);
+    if (tid == 0 && blockIdx.x == 0) *ntiles_out = min(s_base, capacity);
 }
 
 // int16 PCM abs-max: peak = max |s16| / 2^15 (what max |x| is after soundfile's conversion)
@@ -227,6 +243,7 @@ struct PostArgs {
     int fill_zero;               // 1: replace_with_zero (fills are 0), 0: running mean fills
     int rows_per_cta;
     const long long* feat_offsets;   // optional [B] first row of every utterance (packed features)
+    int inline_finalize;             // utterance CMVN without masks: the post pass derives the vectors itself (no finalize launch)
 };
 
 // One CTA (128 threads, thread d = mel column d) per utterance.
@@ -469,11 +486,29 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
 // traffic, per-thread CMVN vectors and frequency-mask winners in registers.
 __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
 {
-    const int utt = blockIdx.y;
+    // CTAs are scheduled x-fastest, y ascending: walking utterances and row blocks BACKWARDS starts with the rows the fused launch
+    // wrote last, i.e. the ones most likely to be L2-resident still
+    const int utt = (int)(gridDim.y - 1 - blockIdx.y);
     const long long n = a.nsamp[utt];
     const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
-    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r0 = (int)(gridDim.x - 1 - blockIdx.x) * a.rows_per_cta;
     if (r0 >= T) return;
+    __shared__ __align__(16) float s_mu[1024], s_is[1024];
+    if (a.inline_finalize) {
+        // same fp64 -> fp32 vectors as finalize_kernel (one row class); the CTA of the utterance's first rows publishes them
+        const double* sb = a.stats + (long long)utt * a.stats_stride;
+        for (int d = threadIdx.x; d < a.nmel; d += 256) {
+            const double mean = sb[d] / T;
+            double istd = 1.0;
+            if (a.cmvn_mode == 2) {
+                const double var = sb[(long long)a.n_cls * a.nmel + d] / T - mean * mean;
+                istd = 1.0 / sqrt(var > 1e-20 ? var : 1e-20);
+            }
+            s_mu[d] = (float)mean; s_is[d] = (float)istd;
+            if (r0 == 0) { a.cm_mean[(long long)utt * a.nmel + d] = (float)mean; a.cm_istd[(long long)utt * a.nmel + d] = (float)istd; }
+        }
+        __syncthreads();
+    }
     const int r1 = min(r0 + a.rows_per_cta, T);
     const int nq = a.nmel >> 2;                    // float4 groups per row
     const int slots = 256 / nq;                    // rows processed concurrently
@@ -486,8 +521,8 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
     int tlo[kMaxTimeMasks], thi[kMaxTimeMasks];
     float tfill[kMaxTimeMasks];
     if (a.cmvn_mode != 0) {
-        const float4 m4 = *reinterpret_cast<const float4*>(a.cm_mean + (long long)utt * a.nmel + 4 * q);
-        const float4 s4 = *reinterpret_cast<const float4*>(a.cm_istd + (long long)utt * a.nmel + 4 * q);
+        const float4 m4 = a.inline_finalize ? *reinterpret_cast<const float4*>(s_mu + 4 * q) : *reinterpret_cast<const float4*>(a.cm_mean + (long long)utt * a.nmel + 4 * q);
+        const float4 s4 = a.inline_finalize ? *reinterpret_cast<const float4*>(s_is + 4 * q) : *reinterpret_cast<const float4*>(a.cm_istd + (long long)utt * a.nmel + 4 * q);
         mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
         is[0] = s4.x; is[1] = s4.y; is[2] = s4.z; is[3] = s4.w;
     }

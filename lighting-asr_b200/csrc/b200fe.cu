@@ -77,14 +77,16 @@ static const void* ws_kernel(bool peak, bool i16)
     if (i16) return peak ? (const void*)fbank_ws_kernel<true, true> : (const void*)fbank_ws_kernel<false, true>;
     return peak ? (const void*)fbank_ws_kernel<true, false> : (const void*)fbank_ws_kernel<false, false>;
 }
+constexpr int kBuilderCtas = 16;     // CTAs of the work-list builder (each repeats the scan, writes 1/16 of the entries)
 static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : kFT; }
 
 static bool plan_has_multi(const b200fe_plan* p) { return p->nload == 13 && (p->static_mel || p->nfft == 256); }
 
 static bool plan_has_lean(const b200fe_plan* p) { return p->nload == 13 && p->static_mel && p->nfft == 512; }
 
-static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false, bool lean = false)
+static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false, bool lean = false, bool apply = false)
 {
+    if (lean && apply) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, true, true>;
     if (lean) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, true>;
     if (multi) {   // multi-utterance tiles (lock-step streaming): the two default option sets, float32, no peak normalisation
         if (p->nfft == 256) return (const void*)fbank_fused_kernel<13, false, false, true, false, true>;
@@ -294,8 +296,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     const void* kfn = plan_kernel(p, false);
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
-    if (e == cudaSuccess && plan_has_lean(p))
+    if (e == cudaSuccess && plan_has_lean(p)) {
         e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    }
     if (e == cudaSuccess && plan_has_multi(p))
         e = cudaFuncSetAttribute(plan_kernel(p, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     if (p->nfft == 512) {
@@ -346,6 +350,7 @@ extern "C" int b200fe_plan_info(const b200fe_plan* p, int what)
         case 4: return p->num_sms;
         case 5: return plan_tile_frames(p);
         case 6: return p->use_ws;
+        case 7: return (plan_has_lean(p) && !p->use_ws) ? 1 : 0;
         default: return -1;
     }
 }
@@ -385,8 +390,28 @@ extern "C" int b200fe_build_tile_table_device(const b200fe_plan* p, const long l
     if (!p || !d_nsamp || !d_table || !d_n_tiles || batch <= 0 || max_frames <= 0 || capacity <= 0)
         return fail(B200FE_EINVAL, "build_tile_table_device: bad argument");
     if (p->use_ws && with_pads) return fail(B200FE_EINVAL, "build_tile_table_device: padding tiles are not available with the experimental kernel");
-    build_tile_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
-                                                                  kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter);
+    build_tile_table_kernel<<<kBuilderCtas, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
+                                                                             kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter,
+                                                                             0, kApplyBit, kApplyRows, nullptr, nullptr, 0);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_build_work_list_device(const b200fe_plan* p, const long long* d_nsamp, int batch, int max_frames, int with_pads, int apply_lag,
+                                             int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, int* d_utt_done,
+                                             void* d_zero, long long zero_bytes, void* stream)
+{
+    if (!p || !d_nsamp || !d_table || !d_n_tiles || !d_work_counter || batch <= 0 || max_frames <= 0 || capacity <= 0 || apply_lag < 0)
+        return fail(B200FE_EINVAL, "build_work_list_device: bad argument");
+    if (p->use_ws) return fail(B200FE_EINVAL, "build_work_list_device: not available with the experimental kernel");
+    if (apply_lag > 0 && !d_utt_done) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need d_utt_done");
+    if (apply_lag > 0 && !plan_has_lean(p)) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need the default option set (plan_info 7)");
+    if (zero_bytes < 0 || (zero_bytes > 0 && (!d_zero || (zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(d_zero) & 15) != 0)))
+        return fail(B200FE_EINVAL, "build_work_list_device: d_zero must be 16-byte aligned and zero_bytes a multiple of 16");
+    build_tile_table_kernel<<<kBuilderCtas, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
+                                                                             kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter,
+                                                                             apply_lag, kApplyBit, kApplyRows, apply_lag > 0 ? d_utt_done : nullptr,
+                                                                             reinterpret_cast<uint4*>(d_zero), zero_bytes / 16);
     CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }
@@ -659,6 +684,17 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.tile_table = reinterpret_cast<const int2*>(g->d_tile_table);
     a.work_counter = g->d_work_counter;
     a.ntiles_ptr = g->d_n_tiles;          // table built on the device: n_tiles is only the capacity bound for the grid size
+    if (g->apply_cmvn_mode != 0) {
+        // utterance CMVN inside the launch: apply tiles of b200fe_build_work_list_device, lean instantiation only
+        if (g->apply_cmvn_mode != 1 && g->apply_cmvn_mode != 2) return fail(B200FE_EINVAL, "fbank_fused: apply_cmvn_mode must be 0, 1 or 2");
+        if (!(plan_has_lean(p) && !p->use_ws) || g->d_peak || i16 || g->uniform_frames || g->d_cmvn_mean || a.masks || g->d_out_offsets || !g->d_out)
+            return fail(B200FE_EINVAL, "fbank_fused: in-launch utterance CMVN needs the default option set, float32 input and the padded output layout");
+        if (!g->d_utt_done || !g->d_n_tiles || !g->d_stats || g->stats_stride < 2LL * p->nmel || n_cls != 1)
+            return fail(B200FE_EINVAL, "fbank_fused: in-launch utterance CMVN needs d_utt_done, a device-built work list and per-utterance statistics");
+        if ((g->d_utt_mean == nullptr) != (g->d_utt_istd == nullptr)) return fail(B200FE_EINVAL, "fbank_fused: d_utt_mean and d_utt_istd go together");
+        if ((reinterpret_cast<uintptr_t>(g->d_out) & 15) != 0) return fail(B200FE_EINVAL, "fbank_fused: in-launch utterance CMVN needs a 16-byte aligned output");
+        a.apply_mode = g->apply_cmvn_mode; a.utt_done = g->d_utt_done; a.utt_mean = g->d_utt_mean; a.utt_istd = g->d_utt_istd;
+    }
     // Lock-step streaming (every utterance yields exactly max_frames frames): tiles take several utterances, so a 4-frame
     // push fills a 32-frame tile with 8 streams instead of occupying one tile per stream.
     if (g->uniform_frames && plan_has_multi(p) && !i16 && !compact && !ws && !g->d_out_offsets && g->max_frames <= kFT / 2 && !g->d_peak && !g->d_stats && !a.masks &&
@@ -694,7 +730,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
     // the lean instantiation serves the default option set whenever the launch applies no CMVN, no masks and writes the padded layout
     const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets;
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean), dim3(grid), dim3(kThreads), kargs,
+    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean, a.apply_mode != 0), dim3(grid), dim3(kThreads), kargs,
                               (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
     return B200FE_OK;
 }
@@ -724,10 +760,14 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     a.feat_offsets = g->d_feat_offsets;
     a.rows_per_cta = 64;
     cudaStream_t st = (cudaStream_t)stream;
-    finalize_kernel<<<g->batch, 128, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
     const bool vec = (p->nmel % 4 == 0) && p->nmel <= 256 * 4 && ((reinterpret_cast<uintptr_t>(g->d_feats) & 15) == 0) &&
                      (a.cmvn_mode == 0 || (((reinterpret_cast<uintptr_t>(g->d_cmvn_mean) | reinterpret_cast<uintptr_t>(g->d_cmvn_istd)) & 15) == 0));
+    // utterance CMVN without SpecAugment fills: the post pass derives the vectors itself, one launch instead of two
+    a.inline_finalize = (vec && !masks && a.cmvn_mode != 0 && a.n_cls == 1) ? 1 : 0;
+    if (!a.inline_finalize) {
+        finalize_kernel<<<g->batch, 128, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
     a.rows_per_cta = vec ? 96 : 64;
     dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
     if (vec) postpass_vec_kernel<<<grid, 256, 0, st>>>(a);

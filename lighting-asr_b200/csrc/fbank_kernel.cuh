@@ -63,6 +63,10 @@ constexpr int kMaxFreqMasks = 4;
 constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
 constexpr int kPadTileRows = 256;   // rows zeroed by one padding tile of the compact work list (table entry with first frame < 0)
 constexpr int kStages = 1;         // one tile buffer: the next tile's TMA is issued right after the phase-A barrier
+constexpr int kApplyBit = 0x40000000;   // work-list entry (utt | kApplyBit, row0): CMVN-apply tile, rows [row0, row0 + kApplyRows)
+constexpr int kApplyRows = 240;         // rows of one apply tile: 240 * 80 * 4 B = 76.8 kB fit the transposition + staging + PT buffers
+constexpr int kSigBatch = 8;            // completions a CTA collects before one fence publishes them
+constexpr int kReadyBit = 0x20000000;   // descriptor only: the utterance was already complete when the tile was claimed (no wait)
 
 struct FbankArgs {
     // input
@@ -119,6 +123,11 @@ struct FbankArgs {
     // multi-utterance tiles (lock-step streaming: every utterance yields exactly Tmax = multi_fpu frames): a tile takes
     // multi_upt consecutive utterances, multi_fpu frames each; utterance j's samples sit at j * multi_span in the tile buffer
     int multi_fpu, multi_upt, multi_span;
+    // utterance CMVN inside the launch (apply tiles of the work list; lean instantiation only)
+    int apply_mode;                 // 0 off, 1 mean, 2 mean + variance
+    int* utt_done;                  // [B] frame tiles of the utterance whose features and statistics are globally visible; [B] = error flag
+    float* utt_mean;                // optional [B][nmel]: the vectors the apply tiles used
+    float* utt_istd;
     // mel tables (warp-uniform, read through the constant bank) -- generic (non-static) phase B
     short seg_start[kMaxMel + 3];   // k where segment s begins, s = 0..nmel+1  (segment s feeds bin s (up) and s-1 (down))
     short grp_begin[9];             // mel bins handled by warp w: [grp_begin[w], grp_begin[w+1])
@@ -142,7 +151,7 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     else { o += xbytes; L.outs_off = o; o += obytes; }   // phase C of tile i overlaps phase A of tile i+1
     L.pt_off = o; o += 64 * kPTStride * 16;
     L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
-    L.bar_off = o; o += 16 + 32;            // mbarrier slots (16 B) + 2 tile descriptors (int4)
+    L.bar_off = o; o += 32 + 32 + 48;       // 4 mbarrier slots | 2 tile descriptors (int4) | pending completion signals (count + kSigBatch utterances)
     L.total = o;
     return L;
 }
@@ -166,6 +175,7 @@ __device__ __forceinline__ int row_class(const int* __restrict__ bounds, int nb,
 
 struct TileGeom {
     int utt, f0, nvalid, nrows, T;
+    bool apply, ready;
 };
 
 // Phase B only stores the raw mel energy of (frame, bin) into the staging tile; log / CMVN / masks are
@@ -416,15 +426,101 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 #undef MGROUP_END
 #undef B200FE_MEL_DEVICE_CODE
 
+// CMVN-apply tile (utterance CMVN inside the fused launch): rows [row0, row0 + kApplyRows) of utterance utt are normalised in
+// place, (x - mean) * istd with the same fp64 -> fp32 vectors finalize_kernel derives from the column sums.  The tile may start
+// once every frame tile of the utterance has been signalled (their stores and atomics are then visible at L2): normally thread 0
+// saw that when it claimed the tile (ready), otherwise it waits here.  The wait is bounded: the tiles it depends on precede this
+// one in the work list, so they are owned by resident CTAs that never wait on anything later in the list.  The rows make one round
+// trip: ONE bulk copy (TMA) brings them -- still L2-resident -- into the transposition / staging / PT buffers, which are idle
+// between two frame tiles, the column vectors are derived from the fp64 sums (ld.global.cg) while they fly, the rows are
+// normalised in shared memory and ONE bulk copy writes them back.  No registers are held across the latency.
+// Completion counters of the apply tiles.  Producer: ONE fence.acq_rel.gpu (orders the CTA's earlier feature stores and
+// statistics atomics -- cumulative over the preceding CTA barrier -- before the increments), then relaxed reductions; a fence
+// costs 0.5 - 1 us on the critical path of warp 0, hence the batching.  Consumer: relaxed polling, then ONE fence.acq_rel
+// before the dependent reads.
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p)
+{
+    int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v)
+{
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ bool apply_cmvn_tile(const FbankArgs& a, int utt, int row0, int Tu, bool ready, float* s_mean, float* s_istd,
+                                                unsigned char* s_rows, uint64_t* bar, uint32_t parity, int tid, int nmel)
+{
+    const int T = min(Tu, a.Tmax);
+    const int nr = max(min(T - row0, kApplyRows), 0);
+    const uint32_t bytes = (uint32_t)nr * (uint32_t)nmel * 4u;   // nmel % 4 == 0: a multiple of 16
+    float* grows = a.out + ((long long)utt * a.Tmax + row0) * nmel;
+    if (tid == 0) {
+        if (!ready) {
+            const int need = (T + kFT - 1) / kFT;
+            int spins = 0;
+            while (ld_relaxed_gpu(a.utt_done + utt) < need) {
+                __nanosleep(128);
+                if (++spins > (1 << 22)) { atomicExch(a.utt_done + a.B, 1 + utt); break; }
+            }
+        }
+        // acquire side of the completion counter (the count may have been observed two tiles ago, when the tile was claimed);
+        // the rows were written through the generic proxy by other SMs, the bulk copy reads them through the async proxy
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (bytes > 0) { mbar_expect_tx(bar, bytes); tma_load_1d(s_rows, grows, bytes, bar); }
+    }
+    __syncthreads();          // orders thread 0's acquire before everybody's reads of the column sums
+    // the column vectors are derived while the rows fly
+    if (tid < nmel) {
+        const double* sb = a.stats + (long long)utt * a.stats_stride;
+        double mean = 0.0, istd = 1.0;
+        if (Tu > 0) {
+            mean = __ldcg(sb + tid) / Tu;
+            if (a.apply_mode == 2) {
+                const double var = __ldcg(sb + (long long)a.n_cls * nmel + tid) / Tu - mean * mean;
+                istd = 1.0 / sqrt(var > 1e-20 ? var : 1e-20);
+            }
+        }
+        s_mean[tid] = (float)mean; s_istd[tid] = (float)istd;
+        if (row0 == 0 && a.utt_mean != nullptr) {
+            a.utt_mean[(long long)utt * nmel + tid] = (float)mean;
+            a.utt_istd[(long long)utt * nmel + tid] = (float)istd;
+        }
+    }
+    __syncthreads();
+    if (bytes == 0) return false;
+    mbar_wait(bar, parity);
+    const int nq = nmel >> 2, n4 = nr * nq;
+    float4* rows4 = reinterpret_cast<float4*>(s_rows);
+    const float4* m4 = reinterpret_cast<const float4*>(s_mean);
+    const float4* i4 = reinterpret_cast<const float4*>(s_istd);
+#pragma unroll 4
+    for (int e = tid; e < n4; e += kThreads) {
+        const int q = e % nq;
+        const float4 m = m4[q], sc = i4[q], v = rows4[e];
+        rows4[e] = make_float4((v.x - m.x) * sc.x, (v.y - m.y) * sc.y, (v.z - m.z) * sc.z, (v.w - m.w) * sc.w);
+    }
+    fence_proxy_async();      // the normalised rows (generic-proxy writes) become visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grows), "r"(smem_u32(s_rows)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the buffers belong to the next tile's phase A afterwards
+    }
+    return true;
+}
+
 // kDual: padded window of 256 samples (8 kHz family).  Two consecutive real frames a, b are packed as
 // z[n] = ya[n] + j yb[n]; after the same 256-point complex FFT, 2 Xa[k] = Z[k] + conj Z[256-k] and
 // 2j Xb[k] = Z[k] - conj Z[256-k], so the conjugate-pair exchange yields both power spectra without any
 // split twiddle (k = 0..127; the Nyquist bin has zero mel weight, TA:627).
 // kI16: the waveform is int16 PCM (2 bytes per sample over PCIe / HBM); 512-point family only.
 // kMulti: multi-utterance tiles for lock-step streaming (instantiated for the two default option sets only).
+// kApply: the lean kernel plus the CMVN-apply tiles of b200fe_build_work_list_device (utterance CMVN inside the launch).
 // kLean: no CMVN / zero masks / packed output inside the launch -- the plain and the statistics (utterance CMVN by post pass)
 // modes of the default option set; the same arithmetic with those runtime switches compiled out (-2 % time, A/B measured).
-template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false, bool kMulti = false, bool kLean = false>
+template <int NLOAD, bool kStaticMel, bool kPeak, bool kDual, bool kI16 = false, bool kMulti = false, bool kLean = false, bool kApply = false>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const __grid_constant__ FbankArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -438,6 +534,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     float2* s_stw = reinterpret_cast<float2*>(s_cmask + 8);
     float2* s_win = s_stw + 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    int4* s_desc = reinterpret_cast<int4*>(bars + 4);          // 16-byte aligned: four 8-byte slots are reserved for mbarriers
+    int* s_sig = reinterpret_cast<int*>(bars + 8);             // [0] count, [1..kSigBatch] utterances whose tile completed (thread 0 only)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -464,6 +562,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
         mbar_init(&bars[kStages], kWarps);        // "tile consumed": every warp has its last frames in registers
+        mbar_init(&bars[2], 1);                   // apply tiles: bulk load of the rows
+        s_sig[0] = 0;
         fence_mbar_init();
     }
     // global CMVN vectors (or the identity) are staged once; per-utterance vectors per tile
@@ -494,7 +594,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     const bool dyn = a.tile_table != nullptr;
     const int ntiles = a.ntiles_ptr != nullptr ? __ldg(a.ntiles_ptr) : a.ntiles;
     constexpr bool multi = kMulti;
-    int4* s_desc = reinterpret_cast<int4*>(bars + 2);          // 16-byte aligned: two 8-byte slots are reserved for mbarriers
     auto resolve = [&](int id) -> Desc {               // thread 0 only
         Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
         if (id < ntiles) {
@@ -506,14 +605,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             if (dyn) { const int2 e = __ldg(a.tile_table + id); d.utt = e.x; d.f0 = e.y; }
             else { d.utt = (int)((unsigned)id / (unsigned)a.tiles_per_utt); d.f0 = (id - d.utt * a.tiles_per_utt) * kFT; }
             if (d.f0 < 0) return d;                                     // padding tile: rows [-f0 - 1, +kPadTileRows) are zeroed
-            const unsigned n = (unsigned)__ldg(a.nsamp + d.utt);       // < 2^31 samples per utterance
+            const unsigned n = (unsigned)__ldg(a.nsamp + (kApply ? (d.utt & ~kApplyBit) : d.utt));       // < 2^31 samples per utterance
             d.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
+            if (kApply && (d.utt & kApplyBit)) {
+                // claimed two tiles ahead: normally every frame tile of the utterance has been signalled by now, and the
+                // apply tile will start without a round trip to the counter
+                const int need = (min(d.T, a.Tmax) + kFT - 1) / kFT;
+                if (ld_relaxed_gpu(a.utt_done + (d.utt & ~kApplyBit)) >= need) d.utt |= kReadyBit;
+            }
         }
         return d;
     };
     auto geom = [&](const Desc& d) -> TileGeom {
         TileGeom g;
-        g.utt = d.utt; g.f0 = d.f0; g.T = d.T;
+        g.utt = d.utt; g.f0 = d.f0; g.T = d.T; g.apply = false; g.ready = false;
+        if (kApply && (d.utt & kApplyBit)) {   // CMVN-apply tile: no frames, no padding rows; handled after the phase-C block
+            g.utt = d.utt & ~(kApplyBit | kReadyBit); g.nvalid = 0; g.nrows = 0; g.apply = true; g.ready = (d.utt & kReadyBit) != 0;
+            return g;
+        }
         if (d.f0 < 0) {          // padding tile of the compact list: no frames, rows [row0, row0 + kPadTileRows) clipped at Tmax
             g.f0 = -d.f0 - 1;
             g.nvalid = 0;
@@ -547,6 +656,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 
     int it = 0;
     uint32_t phase_bits = 0, consumed_phase = 0;
+    // in-launch utterance CMVN: thread 0 collects the utterances of completed frame tiles (a tile is complete at the next CTA-wide
+    // barrier, when every warp's feature stores and statistics atomics have been issued) and publishes kSigBatch of them behind
+    // ONE fence -- a fence per tile sits on warp 0's critical path and was measured at 5.6 % of the step.
+    int pending = -1;
+    auto flush_signals = [&]() {          // thread 0
+        const int n = s_sig[0];
+        if (n > 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (int i = 1; i <= n; ++i) red_relaxed_gpu_add(a.utt_done + s_sig[i], 1);
+            s_sig[0] = 0;
+        }
+    };
+    auto signal_pending = [&](bool force) {          // thread 0, after a CTA barrier that follows the tile's phase C
+        if (pending >= 0) { const int n = s_sig[0] + 1; s_sig[n] = pending; s_sig[0] = n; }
+        if (force || s_sig[0] >= kSigBatch) flush_signals();
+    };
+
     if (tid == 0) {
         const int id0 = dyn ? atomicAdd(a.work_counter, 1) : (int)blockIdx.x;
         const int id1 = dyn ? atomicAdd(a.work_counter, 1) : (int)(blockIdx.x + gridDim.x);
@@ -697,7 +823,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             if (tid == 0) {
                 if (!kEarlyTma && a.use_tma && nxt.id < ntiles) issue_load(gn, 0);
                 s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
+                if (kApply) signal_pending(false);        // after the TMA issue: the fence must not delay the next tile's load
             }
+            if (kApply) pending = utt;
             // per-tile epilogue tables for phase C (written here: no warp is still reading the previous tile's)
             if (cm_per_utt && tid < nmel) {
                 s_mean[tid] = __ldg(a.cm_mean + (long long)utt * a.cm_stride + tid);
@@ -959,6 +1087,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             if (tid == 0) s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
             __syncthreads();
             nxt_desc = s_desc[it & 1];
+            if (kApply) {
+                // an apply tile may depend on completions this CTA still holds back: publish them before waiting
+                if (tid == 0) signal_pending(g.apply);
+                pending = -1;
+                if (g.apply) {
+                    static_assert(kAliasStaging || kHalfWarps * 16 * kXRow * 8 + ((kFT * (B200FE_STATIC_NMEL + 1) * 4 + 15) & ~15) + 64 * kPTStride * 16 >=
+                                  kApplyRows * B200FE_STATIC_NMEL * 4, "an apply tile must fit the transposition + staging + PT buffers");
+                    if (apply_cmvn_tile(a, g.utt, g.f0, g.T, g.ready, s_mean, s_istd, smem + L.xbuf_off, &bars[2], (phase_bits >> 1) & 1u, tid, nmel))
+                        phase_bits ^= 2u;
+                }
+            }
             __syncthreads();
         } else if (kAliasStaging) {
             __syncthreads();      // the staging tile aliases the transposition buffers of the next phase A
@@ -966,6 +1105,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         cur = nxt;
         g = gn;
         nxt = Desc{nxt_desc.x, nxt_desc.y, nxt_desc.z, nxt_desc.w};
+    }
+    if (kApply) {
+        __syncthreads();
+        if (tid == 0) signal_pending(true);
     }
 }
 

@@ -15,6 +15,7 @@ def timeit(fn, K=30):
     return e0.elapsed_time(e1) / K
 fe = lasr_b200.GpuFbankFrontend()
 fe2 = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+fe2.inlaunch_cmvn = False          # finalize + post-pass launches
 if os.environ.get("PAD_TILES") == "0":
     fe.pad_tiles = fe2.pad_tiles = False
 B2, N2 = 256, 16000 * 18
@@ -32,4 +33,37 @@ out3 = torch.empty((256, int(T3.max()), 80), device=dev)
 r.append(timeit(lambda: fe(wav3, n3, out=out3)))
 r.append(timeit(lambda: fe2(wav3, n3, out=out3)))
 r.append(timeit(lambda: fe.accumulate_stats(wav3, n3)))
+fe2.profile_events = []
+t_post = timeit(lambda: fe2(wav3, n3, out=out3))
+torch.cuda.synchronize()
+ev = fe2.profile_events[-30:]
+print("%-8s C2 utt_meanvar post-pass path %.4f ms, of which the fused launch (statistics + features) %.4f ms" % (tag, t_post, sum(a.elapsed_time(b) for a, b in ev) / len(ev)), flush=True)
+fe2.profile_events = None
+for lag in (int(x) for x in os.environ.get("APPLY_LAGS", "16").split(",")):
+    fe3 = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+    fe3.inlaunch_cmvn = True
+    fe3.apply_lag = lag
+    fe3.pad_tiles = fe.pad_tiles
+    fe3.profile_events = []
+    t = timeit(lambda: fe3(wav3, n3, out=out3))
+    torch.cuda.synchronize()
+    ev = fe3.profile_events[-30:]
+    print("%-8s   fused launch with apply tiles alone %.4f ms" % (tag, sum(a.elapsed_time(b) for a, b in ev) / len(ev)), flush=True)
+    work, idx = fe3.last["apply_flags"]
+    print("%-8s C2 utt_meanvar in-launch (apply tiles, lag %d) %.4f ms  error flag %d" % (tag, lag, t, int(work[idx].item())), flush=True)
 print("%-8s uniform plain %.4f | C2 plain %.4f | C2 utt_meanvar %.4f | C2 stats only %.4f  (ms)" % (tag, *r), flush=True)
+
+# the work-list builders alone
+import ctypes as C
+plan = fe.plan(torch.device(dev)); lib = plan.lib
+nd = torch.from_numpy(n3).to(dev)
+Tm = int(T3.max())
+cap = lib.b200fe_tile_table_capacity(plan.handle, 256, Tm, 1) + 256 * ((Tm + 239) // 240)
+work = torch.empty((2 * cap + 2 + 257,), dtype=torch.int32, device=dev)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+p0 = work.data_ptr()
+t_old = timeit(lambda: lib.b200fe_build_tile_table_device(plan.handle, nd.data_ptr(), 256, Tm, 1, p0, cap, p0 + 8 * cap, p0 + 8 * cap + 4, st))
+z = torch.empty((256, 2, 80), dtype=torch.float64, device=dev)
+t_new = timeit(lambda: lib.b200fe_build_work_list_device(plan.handle, nd.data_ptr(), 256, Tm, 1, 0, p0, cap, p0 + 8 * cap, p0 + 8 * cap + 4, None, z.data_ptr(), z.numel() * 8, st))
+t_z = timeit(lambda: torch.zeros((256, 2, 80), dtype=torch.float64, device=dev))
+print("%-8s builders alone: frame+padding list %.4f ms, the same + statistics zero fill %.4f ms; torch.zeros of the statistics %.4f ms" % (tag, t_old, t_new, t_z), flush=True)
