@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(1024) build_tile_table_kernel(const long long*
     __shared__ int s_nt[1024], s_T[1024], s_np[1024];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();      // the fused launch may stage its plan constants while the list is being built
+    pdl_wait();                   // the buffers written below may still be read by the previous call's post pass
     if (tid == 0) { s_base = 0; if (counter && blockIdx.x == 0) *counter = 0; }
     if (utt_done && blockIdx.x == 0) for (int u = tid; u <= B; u += 1024) utt_done[u] = 0;      // [B] = error flag of the apply tiles
     for (long long i = (long long)blockIdx.x * 1024 + tid; i < n_zero16; i += 1024LL * gridDim.x) zero16[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -488,6 +490,8 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
 {
     // CTAs are scheduled x-fastest, y ascending: walking utterances and row blocks BACKWARDS starts with the rows the fused launch
     // wrote last, i.e. the ones most likely to be L2-resident still
+    pdl_launch_dependents();
+    pdl_wait();
     const int utt = (int)(gridDim.y - 1 - blockIdx.y);
     const long long n = a.nsamp[utt];
     const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;

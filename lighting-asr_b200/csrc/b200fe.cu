@@ -77,6 +77,21 @@ static const void* ws_kernel(bool peak, bool i16)
     if (i16) return peak ? (const void*)fbank_ws_kernel<true, true> : (const void*)fbank_ws_kernel<false, true>;
     return peak ? (const void*)fbank_ws_kernel<true, false> : (const void*)fbank_ws_kernel<false, false>;
 }
+// Launch with programmatic stream serialisation (see pdl_wait in b200fe_common.cuh): the kernel may start while the preceding
+// kernel of the stream drains; it synchronises with it through griddepcontrol.wait.
+static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    memset(&attr, 0, sizeof attr);
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 constexpr int kBuilderCtas = 16;     // CTAs of the work-list builder (each repeats the scan, writes 1/16 of the entries)
 static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : kFT; }
 
@@ -238,12 +253,12 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         for (int j = 0; j < p->nmel; ++j) { cost[j] = (p->seg_start[j + 2] - p->seg_start[j]) * 0.5 + 6.0; tot += cost[j]; }
         int j = 0; double acc = 0;
         p->grp_begin[0] = 0;
-        for (int w = 1; w < kWarps; ++w) {
-            const double target = tot * w / (double)kWarps;
+        for (int w = 1; w < kMelGroups; ++w) {
+            const double target = tot * w / (double)kMelGroups;
             while (j < p->nmel && acc + cost[j] * 0.5 < target) { acc += cost[j]; ++j; }
             p->grp_begin[w] = (short)j;
         }
-        for (int w = kWarps; w <= 8; ++w) p->grp_begin[w] = (short)p->nmel;
+        for (int w = kMelGroups; w <= 8; ++w) p->grp_begin[w] = (short)p->nmel;
     }
     // ---- FFT twiddles (double precision, rounded once) ----
     std::vector<float2> twd(256), stw(256);
@@ -384,16 +399,26 @@ extern "C" int b200fe_tile_table_capacity(const b200fe_plan* p, int batch, int m
     return (int)std::max<long long>(n, 1);
 }
 
+static cudaError_t launch_builder(const b200fe_plan* p, const long long* d_nsamp, int batch, int max_frames, int with_pads, int* d_table, int capacity,
+                                  int* d_n_tiles, int* d_work_counter, int apply_lag, int* d_utt_done, void* d_zero, long long zero_bytes, void* stream)
+{
+    int win = p->win, shift = p->shift, ft = plan_tile_frames(p), pads = with_pads ? 1 : 0, pad_rows = kPadTileRows, apply_bit = kApplyBit, apply_rows = kApplyRows;
+    int2* table = reinterpret_cast<int2*>(d_table);
+    uint4* zero16 = reinterpret_cast<uint4*>(d_zero);
+    long long n_zero16 = zero_bytes / 16;
+    void* args[] = {(void*)&d_nsamp, (void*)&batch, (void*)&win, (void*)&shift, (void*)&ft, (void*)&max_frames, (void*)&pads, (void*)&pad_rows, (void*)&table,
+                    (void*)&capacity, (void*)&d_n_tiles, (void*)&d_work_counter, (void*)&apply_lag, (void*)&apply_bit, (void*)&apply_rows, (void*)&d_utt_done,
+                    (void*)&zero16, (void*)&n_zero16};
+    return launch_pdl((const void*)build_tile_table_kernel, dim3(kBuilderCtas), dim3(1024), args, 0, (cudaStream_t)stream);
+}
+
 extern "C" int b200fe_build_tile_table_device(const b200fe_plan* p, const long long* d_nsamp, int batch, int max_frames, int with_pads,
                                               int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, void* stream)
 {
     if (!p || !d_nsamp || !d_table || !d_n_tiles || batch <= 0 || max_frames <= 0 || capacity <= 0)
         return fail(B200FE_EINVAL, "build_tile_table_device: bad argument");
     if (p->use_ws && with_pads) return fail(B200FE_EINVAL, "build_tile_table_device: padding tiles are not available with the experimental kernel");
-    build_tile_table_kernel<<<kBuilderCtas, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
-                                                                             kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter,
-                                                                             0, kApplyBit, kApplyRows, nullptr, nullptr, 0);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_builder(p, d_nsamp, batch, max_frames, with_pads, d_table, capacity, d_n_tiles, d_work_counter, 0, nullptr, nullptr, 0, stream));
     return B200FE_OK;
 }
 
@@ -408,11 +433,8 @@ extern "C" int b200fe_build_work_list_device(const b200fe_plan* p, const long lo
     if (apply_lag > 0 && !plan_has_lean(p)) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need the default option set (plan_info 7)");
     if (zero_bytes < 0 || (zero_bytes > 0 && (!d_zero || (zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(d_zero) & 15) != 0)))
         return fail(B200FE_EINVAL, "build_work_list_device: d_zero must be 16-byte aligned and zero_bytes a multiple of 16");
-    build_tile_table_kernel<<<kBuilderCtas, 1024, 0, (cudaStream_t)stream>>>(d_nsamp, batch, p->win, p->shift, plan_tile_frames(p), max_frames, with_pads ? 1 : 0,
-                                                                             kPadTileRows, reinterpret_cast<int2*>(d_table), capacity, d_n_tiles, d_work_counter,
-                                                                             apply_lag, kApplyBit, kApplyRows, apply_lag > 0 ? d_utt_done : nullptr,
-                                                                             reinterpret_cast<uint4*>(d_zero), zero_bytes / 16);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_builder(p, d_nsamp, batch, max_frames, with_pads, d_table, capacity, d_n_tiles, d_work_counter, apply_lag,
+                            apply_lag > 0 ? d_utt_done : nullptr, d_zero, zero_bytes, stream));
     return B200FE_OK;
 }
 
@@ -730,8 +752,8 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
     // the lean instantiation serves the default option set whenever the launch applies no CMVN, no masks and writes the padded layout
     const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets;
-    CUDA_TRY(cudaLaunchKernel(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean, a.apply_mode != 0), dim3(grid), dim3(kThreads), kargs,
-                              (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
+    CUDA_TRY(launch_pdl(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean, a.apply_mode != 0), dim3(grid), dim3(kThreads), kargs,
+                        (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
     return B200FE_OK;
 }
 
@@ -770,9 +792,13 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     }
     a.rows_per_cta = vec ? 96 : 64;
     dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
-    if (vec) postpass_vec_kernel<<<grid, 256, 0, st>>>(a);
-    else postpass_kernel<<<grid, 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    if (vec) {
+        void* pargs[] = {(void*)&a};
+        CUDA_TRY(launch_pdl((const void*)postpass_vec_kernel, grid, dim3(256), pargs, 0, st));
+    } else {
+        postpass_kernel<<<grid, 256, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
     return B200FE_OK;
 }
 

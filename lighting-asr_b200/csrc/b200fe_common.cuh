@@ -101,6 +101,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): the builder -> fused -> post-pass chain of a call is launched with programmatic stream
+// serialisation, so a kernel's CTAs may become resident, and run the part of their prologue that touches only plan constants, while
+// the preceding kernel drains.  pdl_wait() returns when the preceding kernel has completed and its writes are visible: every read of
+// caller data and every write comes after it.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float fast_log(float x)
 {
     // lg2.approx: max rel err 2^-22 on the mantissa path; |abs err| <= ~4e-7 near 1, <= 3 ulp elsewhere.

@@ -32,7 +32,7 @@
 namespace b200fe {
 
 #ifndef B200FE_WARPS
-#define B200FE_WARPS 8              // warps per CTA: 8 (2 CTAs/SM, 32-frame tiles) or 6 (3 CTAs/SM, 24-frame tiles)
+#define B200FE_WARPS 8              // warps per CTA: 8 (2 CTAs/SM, 32-frame tiles), 6 (3 CTAs/SM, 24-frame tiles) or 4 (4 CTAs/SM, 16-frame tiles)
 #endif
 // Two scheduling variants kept behind macros because they were measured SLOWER on B200 (A/B on one box, C2 plain launch:
 // 0.3285 ms baseline): issuing the next tile's TMA as soon as every warp holds its last frames in registers instead of
@@ -53,8 +53,9 @@ constexpr int kWarps = B200FE_WARPS;
 constexpr int kFT = 4 * kWarps;             // frames per tile: every half-warp transforms two frames
 constexpr int kThreads = 32 * kWarps;
 constexpr int kHalfWarps = 2 * kWarps;
-constexpr int kCtasPerSm = kWarps == 8 ? 2 : 3;
-constexpr bool kAliasStaging = kWarps != 8;   // 3 CTAs/SM only fit with the staging tile aliased onto the transposition buffers
+constexpr int kCtasPerSm = kWarps == 8 ? 2 : kWarps == 4 ? 4 : 3;
+constexpr bool kAliasStaging = kWarps == 6;
+constexpr int kMelGroups = kWarps == 4 ? 8 : kWarps;   // bin groups of phase B (16-frame tiles: one per half-warp)   // 3 CTAs/SM only fit with the staging tile aliased onto the transposition buffers
 constexpr int kXRow = 17;           // padded row length (float2) of the transposition buffer
 constexpr int kPTStride = kFT + 1;   // PT4[k/4][frame] float4 groups; a row of kFT frames is padded by one group (4*(kFT+1) = 4 mod 32 words)
 constexpr int kMaxMel = 128;
@@ -64,7 +65,7 @@ constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
 constexpr int kPadTileRows = 256;   // rows zeroed by one padding tile of the compact work list (table entry with first frame < 0)
 constexpr int kStages = 1;         // one tile buffer: the next tile's TMA is issued right after the phase-A barrier
 constexpr int kApplyBit = 0x40000000;   // work-list entry (utt | kApplyBit, row0): CMVN-apply tile, rows [row0, row0 + kApplyRows)
-constexpr int kApplyRows = 240;         // rows of one apply tile: 240 * 80 * 4 B = 76.8 kB fit the transposition + staging + PT buffers
+constexpr int kApplyRows = kWarps == 8 ? 240 : 96;         // rows of one apply tile: 240 * 80 * 4 B = 76.8 kB fit the transposition + staging + PT buffers
 constexpr int kSigBatch = 8;            // completions a CTA collects before one fence publishes them
 constexpr int kReadyBit = 0x20000000;   // descriptor only: the utterance was already complete when the tile was claimed (no wait)
 
@@ -566,6 +567,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         s_sig[0] = 0;
         fence_mbar_init();
     }
+    // everything above reads plan constants only; the work list, the counters and all caller data come after the preceding kernel
+    pdl_launch_dependents();
+    pdl_wait();
     // global CMVN vectors (or the identity) are staged once; per-utterance vectors per tile
     const bool cm_per_utt = kLean ? false : (a.cm_mean != nullptr && a.cm_stride != 0);
     if (tid < nmel) {
@@ -851,19 +855,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 
             // ================= phase B: warp = mel-bin group, lane = frame =================
             {
-                const int fl = lane;
+                // 16-frame tiles (4 warps): the half-warps of a warp take two different bin groups
+                const int fl = kWarps == 4 ? (lane & 15) : lane;
+                const int grp = kWarps == 4 ? 2 * warp + (lane >> 4) : warp;
                 float* orow = outs + fl * ostride;
                 const float4* pcol = reinterpret_cast<const float4*>(pt) + fl;
                 if (fl >= kFT) {
                     // 24-frame tiles leave lanes 24..31 idle in this phase
                 } else if (kStaticMel) {
-                    switch (warp) {
+                    switch (grp) {
                         case 0: mel_static_group0(pcol, orow); break;
                         case 1: mel_static_group1(pcol, orow); break;
                         case 2: mel_static_group2(pcol, orow); break;
                         case 3: mel_static_group3(pcol, orow); break;
                         case 4: mel_static_group4(pcol, orow); break;
-#if B200FE_WARPS == 8
+#if B200FE_WARPS == 8 || B200FE_WARPS == 4
                         case 5: mel_static_group5(pcol, orow); break;
                         case 6: mel_static_group6(pcol, orow); break;
                         default: mel_static_group7(pcol, orow); break;
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 #endif
                     }
                 } else {
-                    const int jb = a.grp_begin[warp], je = a.grp_begin[warp + 1];
+                    const int jb = a.grp_begin[grp], je = a.grp_begin[grp + 1];
                     if (jb < je) {
                         const float* pf = pt + fl * 4;
                         float up_prev = 0.f;
