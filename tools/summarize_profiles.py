@@ -7,14 +7,13 @@ import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
-skip = len(rows) % 5 if len(rows) % 5 else 0
 agg = {}
-for r in rows[-40:]:                       # the last 8 steps (5 launches each): warm
+for r in rows[-39:]:                       # the last 13 steps (3 launches each: list builder, fused, post pass): warm
     k = r[4]
     agg.setdefault(k, []).append(float(r[-1]) / 1e3)
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(ROOT, "profiles", "%s_launches_c2_step.csv" % tag), "w") as f:
-    f.write("# ncu launch list of `python bench.py --profile-only --steps 2 --warmup 3` (C2 workload, device-resident loop), last 40 launches\n")
+    f.write("# ncu launch list of `python bench.py --profile-only --steps 2 --warmup 3` (C2 workload, device-resident loop), last 39 launches = 13 steps\n")
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none ; times are cold-cache and serialised: compare SHARES\n")
     f.write("kernel,launches,total_us,share_pct,avg_us\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
