@@ -586,9 +586,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     const bool zmask = kLean ? false : (a.mask_zero && a.masks != nullptr);
     const int nmask = a.n_fmask + a.n_tmask;
     // statistics without SpecAugment row classes are reduced inside phase C (no staging write-back, no extra barrier)
-    const bool stats_fused = a.stats != nullptr && !zmask && (a.row_bounds == nullptr || a.n_cls <= 1) && nmel <= kThreads;
+    // (with SpecAugment row classes: for every tile that lies inside ONE class, which is all but a handful per utterance)
+    const bool stats_cap = a.stats != nullptr && !zmask && nmel <= kThreads;
+    const bool has_cls = !kLean && a.row_bounds != nullptr && a.n_cls > 1;
     // the same thread <-> (row part, column) mapping serves the plain copy-out: constant strides, no index arithmetic
-    const bool rowpart_c = !zmask && nmel <= kThreads && (stats_fused || (B200FE_ROWPART_PLAIN != 0 && a.stats == nullptr));
+    // ... and the CMVN / zero-mask epilogue of the training front end (BASELINE config 3): the thread's column fixes its CMVN pair and
+    // its frequency-mask bit, its rows are rg + k * parts, so the per-element row / column arithmetic of the generic loop disappears
+    const bool epi_rowpart = !kLean && a.stats == nullptr && a.out != nullptr && (a.cm_mean != nullptr || zmask) && nmel <= kThreads;
+    const bool rowpart_nostats = (!zmask && nmel <= kThreads && B200FE_ROWPART_PLAIN != 0 && a.stats == nullptr) || epi_rowpart;
 
     // ---- tile scheduler ------------------------------------------------------------------------
     // Thread 0 resolves tile descriptors (id, utterance, first frame, frame count of the utterance) TWO tiles
@@ -905,6 +910,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 
         // ================= phase C: epilogue + copy-out, zero padding, statistics =================
         // element e = row * nmel + col of the tile (contiguous in global memory) <-> staging row*(nmel+1)+col
+        bool stats_fused = stats_cap;          // this tile's statistics are reduced inside the copy-out
+        int tcls = 0;                          // ... into this row class
+        if (has_cls && stats_cap && nvalid > 0) {
+            const int* bounds = a.row_bounds + (long long)utt * (a.n_cls - 1);
+            tcls = row_class(bounds, a.n_cls - 1, f0);
+            stats_fused = tcls == row_class(bounds, a.n_cls - 1, f0 + nvalid - 1);
+        }
+        const bool rowpart_c = stats_fused || rowpart_nostats;
         {
             const long long orow0 = (!kLean && a.out_offsets != nullptr) ? __ldg(a.out_offsets + utt) : (long long)utt * a.Tmax;
             float* obase = a.out != nullptr ? a.out + (orow0 + f0) * nmel : nullptr;
@@ -922,6 +935,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     const int rg = tid / nmel, col = tid - rg * nmel;
                     const float* sp = outs + tid + rg;                  // staging index of e = tid: e + row
                     const float cm = affine ? s_mean[col] : 0.f, ci = affine ? s_istd[col] : 1.f;
+                    // zero masks (replace_with_zero): the column bit is fixed per thread, row k of the thread is rg + k * parts
+                    const bool colz = !kLean && zmask && ((s_cmask[col >> 5] >> (col & 31)) & 1u);
+                    const unsigned rowz = (!kLean && zmask) ? (colz ? 0xffffffffu : s_cmask[4]) >> rg : 0u;
                     float pivot = 0.f, s1 = 0.f, s2 = 0.f;
                     int cnt = 0;
                     if (kStaticMel && nvalid == kFT) {
@@ -934,6 +950,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                         for (int k = 0; k < kIt; ++k) {
                             if (lg) x[k] = fast_log(fmaxf(x[k], lf));
                             if (affine) x[k] = (x[k] - cm) * ci;
+                            if (!kLean && ((rowz >> (k * parts)) & 1u)) x[k] = 0.f;
                         }
                         pivot = x[0];
                         if (stats_fused) {
@@ -955,6 +972,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             float x = sp[k * (P + parts)];
                             if (lg) x = fast_log(fmaxf(x, lf));
                             if (affine) x = (x - cm) * ci;
+                            if (!kLean && ((rowz >> (k * parts)) & 1u)) x = 0.f;
                             if (obase) obase[e] = x;
                             if (cnt == 0) pivot = x;
                             const float dd = x - pivot;
@@ -964,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     if (stats_fused && cnt > 0) {
                         double* sb = a.stats + (long long)utt * a.stats_stride;
                         const double dp = (double)pivot, d1 = (double)s1;
-                        atomicAdd(sb + col, d1 + cnt * dp);
+                        atomicAdd(sb + (long long)tcls * nmel + col, d1 + cnt * dp);
                         atomicAdd(sb + (long long)a.n_cls * nmel + col, (double)s2 + 2.0 * dp * d1 + cnt * dp * dp);
                     }
                 }
