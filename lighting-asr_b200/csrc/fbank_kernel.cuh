@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
                 if (lane == 0) s_cmask[warp] = bal;
             }
-            if (zmask && warp == 4) {
+            if (zmask && warp == (kWarps > 4 ? 4 : 0)) {       // a warp without column work when there is one (128 columns = 4 warps)
                 const int* mk = a.masks + (long long)utt * nmask * 2 + 2 * a.n_fmask;
                 bool m = false;
 #pragma unroll 1
