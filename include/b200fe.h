@@ -101,8 +101,8 @@ int b200fe_build_tile_table_device(const b200fe_plan* plan, const long long* d_n
  * they are still L2-resident.  64 is a good lag: a CTA publishes the completions of eight tiles behind one fence and the
  * persistent grid holds about 900 claimed tiles, so the frame tiles an apply tile depends on have normally been signalled when it
  * is claimed.  Capacity with apply tiles: b200fe_tile_table_capacity(...) + batch * ceil(max_frames / 240).  Pass d_utt_done and
- * apply_cmvn_mode to b200fe_fbank_fused.  Needs b200fe_plan_info(plan, 7) != 0.  Measured on B200 (BASELINE config 2): 0.409 ms
- * per step against 0.415 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3. */
+ * apply_cmvn_mode to b200fe_fbank_fused.  Needs b200fe_plan_info(plan, 7) != 0.  Measured on B200 (BASELINE config 2): 0.380 ms
+ * per step against 0.382 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3. */
 int b200fe_build_work_list_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads, int apply_lag,
                                   int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, int* d_utt_done,
                                   void* d_zero, long long zero_bytes, void* stream);

@@ -233,8 +233,8 @@ class GpuFbankFrontend(torch.nn.Module):
         self.kernel_h2d = True
         self.pad_tiles = True           # padded rows are zeroed by padding tiles inside the fused launch (False: separate zero-fill kernel)
         # Utterance CMVN applied inside the fused launch by CMVN-apply tiles instead of the post-pass launch; the tiles of an utterance
-        # are queued `apply_lag` utterances after its frame tiles.  Opt-in: measured on B200 (C2) at 0.409 ms per step against
-        # 0.415 ms for the post pass -- an apply tile costs its CTA about 5 us without FFT work.
+        # are queued `apply_lag` utterances after its frame tiles.  Opt-in: measured on B200 (C2) at 0.380 ms per step against
+        # 0.382 ms for the post pass -- an apply tile costs its CTA about 5 us without FFT work.
         self.inlaunch_cmvn = False
         self.apply_lag = 64
         self.overlap_calls = True       # extract_host: the H2D copies of the next call may start before this call's D2H tail ends
