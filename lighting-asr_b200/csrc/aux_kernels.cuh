@@ -547,6 +547,21 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
     }
     const bool need_read = a.cmvn_mode != 0;
     float4* base = reinterpret_cast<float4*>(a.feats + (a.feat_offsets != nullptr ? a.feat_offsets[utt] : (long long)utt * a.Tmax) * a.nmel);
+    if (need_read && a.masks == nullptr) {
+        // plain utterance CMVN: four rows' loads are in flight before the first store (the in-place loop below gives the compiler
+        // no licence to hoist a load above the previous row's store)
+        for (int rb = r0 + slot; rb < r1; rb += 4 * slots) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int r = rb + u * slots; if (r < r1) v[u] = base[(long long)r * nq + q]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * slots;
+                if (r < r1) base[(long long)r * nq + q] = make_float4((v[u].x - mu[0]) * is[0], (v[u].y - mu[1]) * is[1], (v[u].z - mu[2]) * is[2], (v[u].w - mu[3]) * is[3]);
+            }
+        }
+        return;
+    }
     for (int r = r0 + slot; r < r1; r += slots) {
         int thit = -1; float tf = 0.f;
 #pragma unroll
