@@ -215,6 +215,27 @@ int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const long long* h_
 int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                       float* h_feats, void* stream);
 
+/* ---- Host staging (no device work): the reference's collate loop receives a LIST of 1-D host arrays, one per utterance
+ * (R/lasr/data/dataset.py:190-206; float64 from soundfile.read, R/lasr/data/reader.py:24).  A persistent thread pool packs
+ * them back to back into ONE (pinned) staging buffer -- the layout b200fe_fbank_fused reads through d_wav_offsets -- converting
+ * float64 -> float32 on the way (the `.float()` of WavToKaldiFbank, R/lasr/data/datatrans.py:73), and zero-fills the padding
+ * rows of the host feature batch (pad_audio = 0, dataset.py:18) while the GPU works.  Jobs are asynchronous: *_begin returns a
+ * positive ticket, b200fe_host_wait blocks until that job is done (the waiting thread helps).  Tickets complete in FIFO order
+ * of submission per pool. */
+typedef struct b200fe_host_pool b200fe_host_pool;
+int b200fe_host_pool_create(int n_threads /* <= 0: one per hardware thread */, b200fe_host_pool** pool);
+void b200fe_host_pool_destroy(b200fe_host_pool* pool);
+int b200fe_host_pool_threads(const b200fe_host_pool* pool);
+/* Utterance u: nsamp[u] elements from h_src[u] go to h_dst + dst_offsets[u] (elements of the DESTINATION type; starts must be
+ * 16-byte aligned); the gap up to the next 16-byte boundary is cleared.  src_dtype: 0 float32 -> float32, 1 int16 -> int16
+ * (PCM as the file holds it), 2 float64 -> float32.  dst_capacity = elements h_dst can hold. */
+long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                 void* h_dst, const long long* dst_offsets, long long dst_capacity);
+/* Clears rows [valid_rows[u], utt_rows) of every utterance of a host [batch][utt_rows][row_elems] float32 tensor. */
+long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, int batch, long long utt_rows, long long row_elems,
+                                      const long long* valid_rows, int elem_bytes /* 4 float32, 2 bfloat16 */);
+int b200fe_host_wait(b200fe_host_pool* pool, long long ticket);
+
 /* Host-only SpecAugment planner (no device work): the rectangles of the reference's `freq_mask` / `time_mask` and the
  * (center, warped) pair of `time_warp` for a whole batch, utterances in order, drawn exactly as the reference draws them
  * (lasr/utils/specaugment.py:20-24,61-64,90-95): CPython `random.randrange` (MT19937, `_randbelow_with_getrandbits`) and

@@ -13,9 +13,18 @@
 #include <string>
 #include <vector>
 
+#include "host_pool.h"
 #include "aux_kernels.cuh"
-#include "fbank_ws_kernel.cuh"
 #include "fbank_kernel.cuh"
+#include "fbank_instances.h"
+#ifdef B200FE_WITH_WS          // the warp-specialised experiment (measured 30 % slower) is not part of the default build
+#include "fbank_ws_kernel.cuh"
+#endif
+
+// the instantiations of the fused kernel live in fbank_inst.cu (one translation unit per group, built in parallel)
+#define B200FE_X(g, n, s, p, d, i, m, l, a) extern template __global__ void b200fe::fbank_fused_kernel<n, s, p, d, i, m, l, a>(const __grid_constant__ b200fe::FbankArgs);
+B200FE_FBANK_INSTANCES(B200FE_X)
+#undef B200FE_X
 
 #define B200FE_MEL_HOST_TABLES
 #include "mel_static_default.inc"
@@ -72,11 +81,13 @@ struct b200fe_plan {
     int ws_smem_bytes;
 };
 
+#ifdef B200FE_WITH_WS
 static const void* ws_kernel(bool peak, bool i16)
 {
     if (i16) return peak ? (const void*)fbank_ws_kernel<true, true> : (const void*)fbank_ws_kernel<false, true>;
     return peak ? (const void*)fbank_ws_kernel<true, false> : (const void*)fbank_ws_kernel<false, false>;
 }
+#endif
 // Launch with programmatic stream serialisation (see pdl_wait in b200fe_common.cuh): the kernel may start while the preceding
 // kernel of the stream drains; it synchronises with it through griddepcontrol.wait.
 static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t st)
@@ -93,7 +104,11 @@ static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, void** args
 }
 
 constexpr int kBuilderCtas = 16;     // CTAs of the work-list builder (each repeats the scan, writes 1/16 of the entries)
+#ifdef B200FE_WITH_WS
 static int plan_tile_frames(const b200fe_plan* p) { return p->use_ws ? kWsFT : kFT; }
+#else
+static int plan_tile_frames(const b200fe_plan*) { return kFT; }
+#endif
 
 static bool plan_has_multi(const b200fe_plan* p) { return p->nload == 13 && (p->static_mel || p->nfft == 256); }
 
@@ -330,6 +345,8 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     // Bit-identical output, but measured 25-30 % SLOWER than the phase-ordered kernel on B200, so it is
     // opt-in and kept for A/B runs only.
     p->use_ws = 0;
+    p->ws_smem_bytes = 0;
+#ifdef B200FE_WITH_WS
     p->ws_smem_bytes = ws_layout(p->shift, p->win).total;
     const char* want_ws = getenv("B200FE_WS");
     if (p->static_mel && want_ws && want_ws[0] == '1' && (size_t)p->ws_smem_bytes <= prop.sharedMemPerBlockOptin) {
@@ -338,6 +355,7 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
         if (e != cudaSuccess) { b200fe_plan_destroy(p); return fail(B200FE_ECUDA, "cudaFuncSetAttribute (ws): %s", cudaGetErrorString(e)); }
         p->use_ws = 1;
     }
+#endif
     *out = p;
     return B200FE_OK;
 }
@@ -488,6 +506,76 @@ extern "C" int b200fe_h2d_ragged(const void* h_wav, long long h_stride, const lo
                                  static_cast<const char*>(h_wav) + (long long)u * h_stride * elem_bytes,
                                  (size_t)elem_bytes * (size_t)h_nsamp[u], cudaMemcpyHostToDevice, st));
     }
+    return B200FE_OK;
+}
+
+// ---- host staging (include/b200fe.h): thread pool that packs / converts utterance lists and zero-fills padding rows ----
+extern "C" int b200fe_host_pool_create(int n_threads, b200fe_host_pool** pool)
+{
+    if (!pool) return fail(B200FE_EINVAL, "host_pool_create: null argument");
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    n_threads = std::max(1, std::min(n_threads, 256));
+    try { *pool = new b200fe_host_pool(n_threads); }
+    catch (const std::exception& e) { return fail(B200FE_EINVAL, "host_pool_create: %s", e.what()); }
+    return B200FE_OK;
+}
+extern "C" void b200fe_host_pool_destroy(b200fe_host_pool* pool) { delete pool; }
+extern "C" int b200fe_host_pool_threads(const b200fe_host_pool* pool) { return pool ? (int)pool->threads.size() : 0; }
+
+extern "C" long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                            void* h_dst, const long long* dst_offsets, long long dst_capacity)
+{
+    if (!pool || !h_src || !nsamp || !h_dst || !dst_offsets || batch < 0) return fail(B200FE_EINVAL, "host_pack: bad argument");
+    if (src_dtype < 0 || src_dtype > 2) return fail(B200FE_EINVAL, "host_pack: src_dtype must be 0 (float32), 1 (int16) or 2 (float64)");
+    if ((reinterpret_cast<uintptr_t>(h_dst) & 15) != 0) return fail(B200FE_EINVAL, "host_pack: the staging buffer must be 16-byte aligned");
+    const long long dsz = src_dtype == 1 ? 2 : 4, ssz = src_dtype == 1 ? 2 : src_dtype == 2 ? 8 : 4, al = 16 / dsz;
+    const long long chunk = (256LL << 10) / dsz;                  // elements per task: 256 kB of destination
+    std::vector<b200fe_host::Task> tasks;
+    for (int u = 0; u < batch; ++u) {
+        const long long n = nsamp[u], o = dst_offsets[u];
+        if (n < 0 || o < 0 || (o % al) != 0 || !h_src[u]) return fail(B200FE_EINVAL, "host_pack: utterance %d: bad length, offset or pointer", u);
+        const long long padded = (n + al - 1) / al * al;
+        if (o + padded > dst_capacity) return fail(B200FE_EINVAL, "host_pack: utterance %d does not fit the staging buffer", u);
+        for (long long c = 0; c < n || c == 0; c += chunk) {
+            const long long m = std::min(chunk, n - c);
+            b200fe_host::Task t;
+            t.kind = src_dtype == 2 ? 1 : 0;
+            t.src = static_cast<const char*>(h_src[u]) + c * ssz;
+            t.dst = static_cast<char*>(h_dst) + (o + c) * dsz;
+            t.n = src_dtype == 2 ? m : m * dsz;
+            t.tail_zero = (c + m >= n) ? (padded - n) * dsz : 0;
+            tasks.push_back(t);
+            if (n == 0) break;
+        }
+    }
+    if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_dst; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
+    return pool->submit(tasks);
+}
+
+extern "C" long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, int batch, long long utt_rows, long long row_elems,
+                                                 const long long* valid_rows, int elem_bytes)
+{
+    if (!pool || !h_feats || !valid_rows || batch < 0 || utt_rows < 0 || row_elems <= 0 || (elem_bytes != 2 && elem_bytes != 4))
+        return fail(B200FE_EINVAL, "host_zero_rows: bad argument");
+    std::vector<b200fe_host::Task> tasks;
+    const long long row_bytes = row_elems * elem_bytes, chunk = 1LL << 20;
+    for (int u = 0; u < batch; ++u) {
+        const long long v = std::max(0LL, std::min(valid_rows[u], utt_rows));
+        char* base = reinterpret_cast<char*>(h_feats) + ((long long)u * utt_rows + v) * row_bytes;
+        const long long nb = (utt_rows - v) * row_bytes;
+        for (long long c = 0; c < nb; c += chunk) {
+            b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = base + c; t.n = std::min(chunk, nb - c); t.tail_zero = 0;
+            tasks.push_back(t);
+        }
+    }
+    if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_feats; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
+    return pool->submit(tasks);
+}
+
+extern "C" int b200fe_host_wait(b200fe_host_pool* pool, long long ticket)
+{
+    if (!pool || ticket <= 0) return fail(B200FE_EINVAL, "host_wait: bad argument");
+    if (pool->wait(ticket) != 0) return fail(B200FE_EINVAL, "host_wait: unknown ticket %lld", ticket);
     return B200FE_OK;
 }
 
@@ -743,12 +831,14 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         if (ntiles == 0) return B200FE_OK;
     }
     void* kargs[] = {(void*)&a};
+#ifdef B200FE_WITH_WS
     if (ws) {
         // persistent, one CTA per SM: FFT warps / epilogue warps / producer warp hand tiles over through mbarrier rings
         const int wgrid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)p->num_sms));
         CUDA_TRY(cudaLaunchKernel(ws_kernel(g->d_peak != nullptr, i16), dim3(wgrid), dim3(kWsThreads), kargs, (size_t)p->ws_smem_bytes, st));
         return B200FE_OK;
     }
+#endif
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
     // the lean instantiation serves the default option set whenever the launch applies no CMVN, no masks and writes the padded layout
     const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets;

@@ -1,0 +1,146 @@
+// Host-side staging helpers of the C ABI (include/b200fe.h, "host staging"): a small persistent thread pool that
+//   * packs a LIST of utterances (what the reference's collate loop receives one by one, R/lasr/data/dataset.py:190-206;
+//     float64 from soundfile.read, R/lasr/data/reader.py:24) into one pinned staging buffer, converting float64 -> float32
+//     on the way (the `.float()` of WavToKaldiFbank, R/lasr/data/datatrans.py:73) with non-temporal stores, and
+//   * zero-fills the padding rows of the host feature batch (pad_audio = 0, R/lasr/data/dataset.py:18)
+// while the GPU works.  Plain C++11 threads; no CUDA calls in here.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+namespace b200fe_host {
+
+struct Job {
+    std::atomic<long long> remaining{0};
+    std::mutex m;
+    std::condition_variable cv;
+};
+
+struct Task {
+    int kind;                 // 0 memcpy, 1 float64 -> float32, 2 zero fill
+    const void* src;
+    void* dst;
+    long long n;              // bytes (kinds 0, 2) or elements (kind 1)
+    long long tail_zero;      // bytes to clear right after the destination range (alignment gap of the packed layout)
+    std::shared_ptr<Job> job;
+};
+
+inline void cvt_f64_f32(const double* __restrict__ s, float* __restrict__ d, long long n)
+{
+    long long i = 0;
+#if defined(__SSE2__)
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        for (; i + 8 <= n; i += 8) {
+            const __m128 a = _mm_cvtpd_ps(_mm_loadu_pd(s + i)), b = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 2));
+            const __m128 c = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 4)), e = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 6));
+            _mm_stream_ps(d + i, _mm_movelh_ps(a, b));          // the staging buffer is read next by the DMA engine, not by a core
+            _mm_stream_ps(d + i + 4, _mm_movelh_ps(c, e));
+        }
+        _mm_sfence();
+    }
+#endif
+    for (; i < n; ++i) d[i] = (float)s[i];
+}
+
+inline void run_task(const Task& t)
+{
+    switch (t.kind) {
+        case 0: memcpy(t.dst, t.src, (size_t)t.n); if (t.tail_zero > 0) memset(static_cast<char*>(t.dst) + t.n, 0, (size_t)t.tail_zero); break;
+        case 1:
+            cvt_f64_f32(static_cast<const double*>(t.src), static_cast<float*>(t.dst), t.n);
+            if (t.tail_zero > 0) memset(static_cast<float*>(t.dst) + t.n, 0, (size_t)t.tail_zero);
+            break;
+        default: memset(t.dst, 0, (size_t)t.n); break;
+    }
+}
+
+}  // namespace b200fe_host
+
+struct b200fe_host_pool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<b200fe_host::Task> q;
+    bool stop = false;
+    long long next_ticket = 1;
+    std::map<long long, std::shared_ptr<b200fe_host::Job>> jobs;
+
+    explicit b200fe_host_pool(int n)
+    {
+        for (int i = 0; i < n; ++i) threads.emplace_back([this] { worker(); });
+    }
+    ~b200fe_host_pool()
+    {
+        { std::lock_guard<std::mutex> g(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    static void finish(const b200fe_host::Task& t)
+    {
+        if (t.job->remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(t.job->m); t.job->cv.notify_all(); }
+    }
+    void worker()
+    {
+        for (;;) {
+            b200fe_host::Task t;
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [this] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                t = q.front(); q.pop_front();
+            }
+            b200fe_host::run_task(t);
+            finish(t);
+        }
+    }
+    long long submit(std::vector<b200fe_host::Task>& tasks)
+    {
+        auto job = std::make_shared<b200fe_host::Job>();
+        job->remaining = (long long)tasks.size();
+        for (auto& t : tasks) t.job = job;
+        long long ticket;
+        {
+            std::lock_guard<std::mutex> g(m);
+            ticket = next_ticket++;
+            jobs[ticket] = job;
+            for (auto& t : tasks) q.push_back(t);
+        }
+        cv.notify_all();
+        return ticket;
+    }
+    // The waiting thread helps: it drains queued tasks (of any job, FIFO) until its own job is complete.
+    int wait(long long ticket)
+    {
+        std::shared_ptr<b200fe_host::Job> job;
+        {
+            std::lock_guard<std::mutex> g(m);
+            auto it = jobs.find(ticket);
+            if (it == jobs.end()) return -1;
+            job = it->second;
+            jobs.erase(it);
+        }
+        while (job->remaining.load() > 0) {
+            b200fe_host::Task t;
+            bool have = false;
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (!q.empty()) { t = q.front(); q.pop_front(); have = true; }
+            }
+            if (have) { b200fe_host::run_task(t); finish(t); continue; }
+            std::unique_lock<std::mutex> g(job->m);
+            job->cv.wait(g, [&] { return job->remaining.load() <= 0; });
+        }
+        return 0;
+    }
+};

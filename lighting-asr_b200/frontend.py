@@ -372,6 +372,10 @@ class GpuFbankFrontend(torch.nn.Module):
         mean_fill = self.specaug and not self.replace_with_zero
         utt_cmvn = self.cmvn in ("utt_mean", "utt_meanvar")
         need_post = mean_fill or utt_cmvn
+        # replace_with_zero together with utterance CMVN: the statistics must see the unmasked features and the zeros go in
+        # after normalisation (CMVN first, masks second -- the order of the mean-fill and time-warp paths), so the post
+        # pass writes them (fill_zero) instead of the fused launch
+        zero_in_post = self.specaug and self.replace_with_zero and utt_cmvn
         n_cls = (2 * n_t + 1) if mean_fill else 1
 
         gm = gi = None
@@ -418,7 +422,7 @@ class GpuFbankFrontend(torch.nn.Module):
             if utt_cmvn:
                 cm = torch.empty((B, D), dtype=torch.float32, device=dev)
                 ci = torch.empty((B, D), dtype=torch.float32, device=dev)
-            if mean_fill:
+            if mean_fill or zero_in_post:
                 fills = torch.empty((B, n_f + n_t), dtype=torch.float32, device=dev)
 
         def off(t, b0, per):
@@ -457,7 +461,7 @@ class GpuFbankFrontend(torch.nn.Module):
                 a.dither_seed = self.dither_seed
             if gm is not None:
                 a.d_cmvn_mean, a.d_cmvn_istd, a.cmvn_stride = _ptr(gm), _ptr(gi), 0
-            if self.specaug:
+            if self.specaug and not zero_in_post:
                 a.d_masks = off(masks_dev, b0, (n_f + n_t) * 2 * 4)
                 a.n_freq_masks, a.n_time_masks = n_f, n_t
                 a.mask_zero = int(self.replace_with_zero)
@@ -523,12 +527,13 @@ class GpuFbankFrontend(torch.nn.Module):
                 q.cmvn_mode = {"utt_mean": 1, "utt_meanvar": 2}.get(self.cmvn, 0)
                 q.d_cmvn_mean = off(cm, b0, D * 4)
                 q.d_cmvn_istd = off(ci, b0, D * 4)
-                if mean_fill:
-                    q.d_masks = a.d_masks
+                if mean_fill or zero_in_post:
+                    q.d_masks = off(masks_dev, b0, (n_f + n_t) * 2 * 4)
                     q.n_freq_masks, q.n_time_masks = n_f, n_t
                     q.d_fills = off(fills, b0, (n_f + n_t) * 4)
+                    q.fill_zero = int(zero_in_post)
                 _lib.check(lib.b200fe_postpass(plan.handle, C.byref(q), stream), "b200fe_postpass")
-                self.launch_count += 2 if mean_fill else 1      # (finalize +) in-place post pass
+                self.launch_count += 2 if (mean_fill or zero_in_post) else 1      # (finalize +) in-place post pass
         self.last = dict(stats=stats, fills=fills, masks=masks_dev, utt_mean=cm, utt_istd=ci, peak=peak, feat_offsets=ooff_host,
                          apply_flags=self._apply_flags if apply_tiles else None)
         return feats, feat_len
@@ -647,6 +652,11 @@ class GpuFbankFrontend(torch.nn.Module):
         key = (B, Nmax, Tmax, total, dev.index or 0, wav_host.dtype, packed_in, packed_out, rows_total if packed_out else 0)
         c = self._host_cache.get(key)
         if c is None:
+            # new geometry: the old staging buffers may still be read by queued kernels / copies of the previous call, and the
+            # allocator can hand their memory straight back -- drain the device before dropping them (HostPipeline, the
+            # path behind B200Collate, keeps grow-only capacity buffers instead and never gets here)
+            if self._host_cache:
+                torch.cuda.synchronize(dev)
             self._host_cache.clear()
             # two staging buffers: the H2D copies of call k+1 overlap the compute / D2H tail of call k
             c = dict(wavs=[torch.zeros((total + 64,), dtype=wav_host.dtype, device=dev) for _ in range(2)],
@@ -683,6 +693,8 @@ class GpuFbankFrontend(torch.nn.Module):
             s_in.wait_stream(main)
         elif c["wav_free"][slot] is not None:
             s_in.wait_event(c["wav_free"][slot])          # the call that last read this staging buffer has finished computing
+        else:
+            s_in.wait_stream(main)                        # fresh buffers: their zero fill was queued on the main stream
         s_out.wait_stream(main)
         if kh2d:
             s_in.wait_event(ev_tab)
@@ -756,11 +768,21 @@ class GpuFbankFrontend(torch.nn.Module):
     @torch.no_grad()
     def accumulate_stats(self, wav, wav_len, stats=None):
         """Adds this batch's [sum | count ; sumsq | 0] to ``stats`` (float64 CUDA [2, D+1])."""
+        if not wav.is_cuda or wav.dim() != 2 or wav.dtype not in (torch.float32, torch.int16):
+            raise ValueError("accumulate_stats: wav must be a float32 or int16 CUDA tensor (B, Nmax)")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
         dev = wav.device
         plan = self.plan(dev)
         B, D = wav.shape[0], self.num_mel_bins
         len_host = np.asarray(wav_len.cpu() if torch.is_tensor(wav_len) else wav_len, dtype=np.int64).reshape(-1)
         T_host, win = self.frame_counts(len_host)
+        if len(len_host) != B:
+            raise ValueError("accumulate_stats: one length per utterance")
+        if (len_host < win).any():
+            raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(len_host.min())))
+        if (len_host > wav.shape[1]).any():
+            raise ValueError("wav_len exceeds the padded width")
         len_dev = _h2d(len_host, dev)
         if stats is None:
             stats = torch.zeros((2, D + 1), dtype=torch.float64, device=dev)
@@ -768,8 +790,8 @@ class GpuFbankFrontend(torch.nn.Module):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         if self.peak_norm:
             peak = torch.empty((B,), dtype=torch.float32, device=dev)
-            _lib.check(plan.lib.b200fe_peak_absmax(plan.handle, _ptr(wav), wav.stride(0), C.c_void_p(0), _ptr(len_dev), B, _ptr(peak), stream),
-                       "b200fe_peak_absmax")
+            absmax = plan.lib.b200fe_peak_absmax_i16 if wav.dtype == torch.int16 else plan.lib.b200fe_peak_absmax
+            _lib.check(absmax(plan.handle, _ptr(wav), wav.stride(0), C.c_void_p(0), _ptr(len_dev), B, _ptr(peak), stream), "b200fe_peak_absmax")
         # per-utterance accumulators (no atomic contention on one 2 x D block), compact tile list, then one
         # fp64 reduction over the batch
         dev_list = self.compact_tiles and not plan.uses_ws        # the list builder clears the accumulators as well
@@ -780,6 +802,9 @@ class GpuFbankFrontend(torch.nn.Module):
         a.d_peak = _ptr(peak)
         a.max_frames = int(T_host.max())
         a.d_stats, a.stats_stride, a.n_row_classes = _ptr(acc), 2 * D, 1
+        if self.dither != 0.0:
+            self.dither_seed += 1
+            a.dither_seed = self.dither_seed
         if self.compact_tiles and not plan.uses_ws:
             cap = plan.lib.b200fe_tile_table_capacity(plan.handle, B, a.max_frames, 0)
             work = torch.empty((2 * cap + 2,), dtype=torch.int32, device=dev)              # table | n_tiles | counter

@@ -1,0 +1,219 @@
+"""Host-to-host pipeline behind ``B200Collate``: a LIST of 1-D host waveforms in, the reference's batch tensors out.
+
+The reference's collate loop receives the utterances one by one as float64 ndarrays from ``soundfile.read``
+(lasr/data/reader.py:24, lasr/data/dataset.py:190-206), runs the transform chain per utterance and pads with
+``batch_list`` (dataset.py:8-22).  Here one call moves the whole batch:
+
+    list of ndarrays --(C thread pool: pack + float64->float32, non-temporal stores)--> pinned staging ring
+      --(one DMA per ~32 MB utterance group, stream s_in)--> packed device buffer
+      --(fused fbank / CMVN / SpecAugment launches, current stream)--> (B, Tmax, D) device features
+      --(one copy kernel per group writing mapped pinned memory, stream s_out)--> pinned (B, Tmax, D) host batch
+    padding rows of the host batch are zero-filled by the thread pool meanwhile.
+
+All staging is capacity based and grow-only (pinned host rings, device buffers, streams are created once): batches of
+different shapes reuse it, nothing is keyed on the batch geometry.  Returned host tensors are slots of a ring: a batch
+stays valid until ``ring`` further calls (the trainer consumes batch k before it asks for batch k + ring).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_SRC_CODE = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.float64): 2}
+_DST_TORCH = {0: torch.float32, 1: torch.int16, 2: torch.float32}
+
+
+def default_threads():
+    """Host threads for packing: the process's share of the cores (torchrun starts one process per GPU)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(32, n // max(local, 1)))
+
+
+class _Grow:
+    """Grow-only flat buffer (pinned host or device); growing synchronises the device first so that no stream still
+    touches the buffer that is dropped."""
+
+    def __init__(self, dtype, device=None):
+        self.dtype, self.device, self.buf = dtype, device, None
+
+    def get(self, numel):
+        if self.buf is None or self.buf.numel() < numel:
+            if self.buf is not None:
+                torch.cuda.synchronize()
+            cap = int(numel * 1.25) + 1024
+            if self.device is None:
+                self.buf = torch.empty((cap,), dtype=self.dtype, pin_memory=True)
+            else:
+                self.buf = torch.empty((cap,), dtype=self.dtype, device=self.device)
+        return self.buf
+
+
+class HostPipeline:
+    def __init__(self, frontend, device="cuda:0", ring=3, threads=None, group_bytes=32 << 20):
+        self.fe = frontend
+        self.dev = torch.device(device)
+        self.lib = _lib.load()
+        self.ring = max(2, int(ring))
+        self.group_bytes = int(group_bytes)
+        h = C.c_void_p()
+        _lib.check(self.lib.b200fe_host_pool_create(int(threads or default_threads()), C.byref(h)), "b200fe_host_pool_create")
+        self.pool = h
+        self.threads = self.lib.b200fe_host_pool_threads(h)
+        self._in = {}          # dst dtype -> [(_Grow pinned, _Grow device)] * 2
+        self._hout = [_Grow(torch.uint8) for _ in range(self.ring)]
+        self._dout = [_Grow(torch.uint8, self.dev) for _ in range(self.ring)]
+        self._hlen = [torch.empty((0,), dtype=torch.int64)] * self.ring
+        self._dlen = [None] * self.ring
+        self._in_free = [None, None]        # H2D of the call that last used the pinned / device input slot has completed
+        self._comp_done = [None, None]      # ... and its kernels no longer read the device staging buffer
+        self._out_done = [None] * self.ring
+        self._turn = 0
+        self._streams = None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "pool", None):
+                self.lib.b200fe_host_pool_destroy(self.pool)
+                self.pool = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def submit(self, wavs, to_host=True):
+        """Starts one batch; returns a handle for ``result``.  Packing (host threads) is complete when this returns,
+        the copies and kernels are queued on the device."""
+        fe, lib, dev = self.fe, self.lib, self.dev
+        B = len(wavs)
+        if B == 0:
+            raise ValueError("empty batch")
+        arrs = [np.asarray(w) for w in wavs]
+        dt = arrs[0].dtype
+        if dt not in _SRC_CODE or any(a.dtype != dt for a in arrs):
+            dt = np.dtype(np.float64) if dt not in _SRC_CODE else dt
+            arrs = [np.ascontiguousarray(a, dtype=dt) for a in arrs]
+        if any(a.ndim != 1 for a in arrs):
+            raise ValueError("expected mono 1-D waveforms (run 'avgchannel' first, datatrans.py:10-14)")
+        arrs = [a if a.flags.c_contiguous else np.ascontiguousarray(a) for a in arrs]
+        code = _SRC_CODE[dt]
+        ddt = _DST_TORCH[code]
+        esz = 2 if code == 1 else 4
+        al = 16 // esz
+        lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=B)
+        T_host, win = fe.frame_counts(lens)
+        if (lens < win).any():
+            # torchaudio asserts (TA:142); LASR filters min_duration upstream (dataset.py:243,272)
+            raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(lens.min())))
+        offs = np.zeros(B, dtype=np.int64)
+        np.cumsum((lens[:-1] + al - 1) // al * al, out=offs[1:])
+        total = int(offs[-1] + (lens[-1] + al - 1) // al * al)
+        Tmax, D = int(T_host.max()), fe.num_mel_bins
+        turn = self._turn
+        self._turn += 1
+        si, so = turn & 1, turn % self.ring
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._streams
+        main = torch.cuda.current_stream(dev)
+        if ddt not in self._in:
+            self._in[ddt] = [(_Grow(ddt), _Grow(ddt, dev)) for _ in range(2)]
+        if self._in_free[si] is not None:
+            self._in_free[si].synchronize()            # the DMA that last read this pinned slot (two calls ago) is done
+        hin = self._in[ddt][si][0].get(total + 64)
+        dwav = self._in[ddt][si][1].get(total + 64)
+        # ---- utterance groups of ~group_bytes of audio; one pack job per group, queued in order ----
+        bounds, acc = [0], 0
+        for b in range(B):
+            acc += int(lens[b]) * esz
+            if acc >= self.group_bytes:
+                bounds.append(b + 1)
+                acc = 0
+        if bounds[-1] != B:
+            bounds.append(B)
+        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+        tickets = []
+        for b0, b1 in zip(bounds[:-1], bounds[1:]):
+            tk = lib.b200fe_host_pack_begin(self.pool, C.c_void_p(C.addressof(ptrs) + 8 * b0), C.c_void_p(lens.ctypes.data + 8 * b0), b1 - b0, code,
+                                            C.c_void_p(hin.data_ptr()), C.c_void_p(offs.ctypes.data + 8 * b0), hin.numel())
+            if tk <= 0:
+                _lib.check(int(tk), "b200fe_host_pack_begin")
+            tickets.append(tk)
+        # ---- output slot ----
+        obytes = B * Tmax * D * 4
+        dfeats = self._dout[so].get(obytes)[:obytes].view(torch.float32).view(B, Tmax, D)
+        if self._dlen[so] is None or self._dlen[so].numel() < B:
+            self._dlen[so] = torch.empty((max(B, 256),), dtype=torch.int64, device=dev)
+        dlen = self._dlen[so][:B]
+        zero_ticket = None
+        hfeats = hlen = None
+        if to_host:
+            hfeats = self._hout[so].get(obytes)[:obytes].view(torch.float32).view(B, Tmax, D)
+            if self._hlen[so].numel() < B:
+                self._hlen[so] = torch.empty((max(B, 256),), dtype=torch.int64, pin_memory=True)
+            hlen = self._hlen[so][:B]
+            zero_ticket = lib.b200fe_host_zero_rows_begin(self.pool, C.c_void_p(hfeats.data_ptr()), B, Tmax, D, C.c_void_p(T_host.ctypes.data), 4)
+            if zero_ticket <= 0:
+                _lib.check(int(zero_ticket), "b200fe_host_zero_rows_begin")
+            # device-readable (offset, bytes) of every utterance's valid rows, same offsets on both sides (padded layout)
+            tab = np.stack([np.arange(B, dtype=np.int64) * (Tmax * D * 4), T_host.astype(np.int64) * (D * 4)])
+            tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
+            ev_tab = torch.cuda.Event()
+            ev_tab.record(main)
+            s_out.wait_event(ev_tab)
+        if self._comp_done[si] is not None:
+            s_in.wait_event(self._comp_done[si])       # kernels of the call that last read this device staging buffer
+        if self._out_done[so] is not None:
+            main.wait_event(self._out_done[so])        # D2H of the call that last used this device feature slot
+        self.h2d_bytes = self.d2h_bytes = 0
+        for (b0, b1), tk in zip(zip(bounds[:-1], bounds[1:]), tickets):
+            _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")
+            o0 = int(offs[b0])
+            o1 = int(offs[b1]) if b1 < B else total
+            with torch.cuda.stream(s_in):
+                dwav[o0:o1].copy_(hin[o0:o1], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+            self.h2d_bytes += (o1 - o0) * esz
+            main.wait_event(ev_in)
+            fe.forward(dwav, lens[b0:b1], max_frames=Tmax, out=dfeats[b0:b1], out_len=dlen[b0:b1], wav_offsets=offs[b0:b1])
+            if to_host:
+                ev_c = torch.cuda.Event()
+                ev_c.record(main)
+                s_out.wait_event(ev_c)
+                _lib.check(lib.b200fe_copy_ragged(C.c_void_p(dfeats.data_ptr()), C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(hfeats.data_ptr()),
+                                                  C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(tab_dev.data_ptr() + 8 * (B + b0)), b1 - b0,
+                                                  int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
+                fe.launch_count += 1
+                self.d2h_bytes += int(T_host[b0:b1].sum()) * D * 4
+        self._in_free[si] = torch.cuda.Event()
+        self._in_free[si].record(s_in)
+        self._comp_done[si] = torch.cuda.Event()
+        self._comp_done[si].record(main)
+        done = None
+        if to_host:
+            with torch.cuda.stream(s_out):
+                hlen.copy_(dlen, non_blocking=True)
+            self.d2h_bytes += B * 8
+            done = torch.cuda.Event()
+            done.record(s_out)
+            self._out_done[so] = done
+            tab_dev.record_stream(s_out)
+        return dict(to_host=to_host, done=done, zero=zero_ticket, hfeats=hfeats, hlen=hlen, dfeats=dfeats, dlen=dlen, keep=arrs)
+
+    def result(self, h):
+        """Blocks until the batch of ``submit`` is complete on the host (``to_host``) and returns (feats, feat_len)."""
+        if not h["to_host"]:
+            return h["dfeats"], h["dlen"]
+        h["done"].synchronize()
+        if h["zero"]:
+            _lib.check(self.lib.b200fe_host_wait(self.pool, h["zero"]), "b200fe_host_wait")
+            h["zero"] = None
+        h["keep"] = None
+        return h["hfeats"], h["hlen"]
+
+    def run(self, wavs, to_host=True):
+        return self.result(self.submit(wavs, to_host))

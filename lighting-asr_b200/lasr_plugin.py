@@ -30,6 +30,8 @@ class GpuTransform:
         self.device = torch.device(device)
         self.return_tensor = return_tensor
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
+        self._pin = None                # grow-only pinned staging: the upload is then a true asynchronous DMA
+        self._pin_free = None
         # Register.register prints `value.__name__` when it overrides a key (lasr/utils/register.py:10-11)
         self.__name__ = "GpuTransform"
 
@@ -38,11 +40,22 @@ class GpuTransform:
         if w.ndim != 1:
             raise ValueError("expected a mono 1-D waveform (run 'avgchannel' first, datatrans.py:10-14)")
         n = w.shape[0]
-        pad = (-n) % 4
-        buf = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
-        if pad:
-            buf = torch.nn.functional.pad(buf, (0, pad))
-        feats, _ = self.frontend(buf.to(self.device, non_blocking=True).unsqueeze(0), np.array([n], dtype=np.int64))
+        i16 = w.dtype == np.int16
+        npad = (n + 7) // 8 * 8
+        tdt = torch.int16 if i16 else torch.float32
+        if self._pin is None or self._pin.dtype != tdt or self._pin.numel() < npad:
+            if self._pin_free is not None:
+                self._pin_free.synchronize()
+            self._pin = torch.empty((max(2 * npad, 1 << 16),), dtype=tdt, pin_memory=True)
+        elif self._pin_free is not None:
+            self._pin_free.synchronize()        # the previous call's DMA has read the staging buffer
+        view = self._pin.numpy()
+        view[:n] = w                            # float64 -> float32 here (the `.float()` of datatrans.py:73)
+        view[n:npad] = 0
+        dw = self._pin[:npad].to(self.device, non_blocking=True)
+        self._pin_free = torch.cuda.Event()
+        self._pin_free.record(torch.cuda.current_stream(self.device))
+        feats, _ = self.frontend(dw.unsqueeze(0), np.array([n], dtype=np.int64))
         feats = feats[0]
         return feats if self.return_tensor else feats.cpu().numpy()
 
@@ -70,26 +83,38 @@ class B200Collate:
     """Batched replacement of ``AudioDataSet.MergeBatch``'s transform loop (dataset.py:190-206).
 
     ``__call__(list_of_waveforms)`` -> dict(wav_array=(B,Tmax,80) float32, wav_len=(B,) int64),
-    the two entries ``LightModelFace.pack_data`` reads (bin/train_lighting.py:104-126).  Features
-    stay on the GPU unless ``to_host`` (Lightning's batch transfer is then a no-op)."""
+    the two entries ``LightModelFace.pack_data`` reads (bin/train_lighting.py:104-126).  The list holds
+    what the reference's loop receives: 1-D float64 ndarrays from ``soundfile.read`` (reader.py:24);
+    float32 arrays and int16 PCM (``soundfile.read(dtype="int16")``, half the PCIe bytes) are taken as
+    they are.  ``to_host=True`` returns pinned HOST tensors like the reference's collate (they are slots
+    of a ring: valid until ``ring`` further calls); otherwise the features stay on the GPU (Lightning's
+    batch transfer is then a no-op) and are ordered on the current stream.
 
-    def __init__(self, device="cuda:0", to_host=False, **frontend_kwargs):
+    ``prefetch(iterable)`` yields the batch of item k while item k + 1 is already being packed and
+    copied (what a DataLoader's prefetching does for the reference's CPU workers)."""
+
+    def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, **frontend_kwargs):
+        from .host_pipeline import HostPipeline
         self.device = torch.device(device)
         self.to_host = to_host
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
-        self._pinned = None             # packed pinned staging buffer, grown on demand and reused across batches
+        self.pipeline = HostPipeline(self.frontend, self.device, ring=ring, threads=threads)
 
     def __call__(self, wavs):
-        need = sum((len(w) + 3) // 4 * 4 for w in wavs)
-        if self._pinned is None or self._pinned.numel() < need:
-            self._pinned = torch.empty((int(need * 1.25) + 64,), dtype=torch.float32).pin_memory()
-        # utterances back to back in one pinned buffer: one DMA per group instead of a padded (B, Nmax) batch
-        host, n, offs = GpuFbankFrontend.pack_host(wavs, out=self._pinned)
-        feats, flen = self.frontend.extract_host(host, n, device=self.device, return_host=self.to_host, wav_offsets=offs)
-        if self.to_host:
-            return {"wav_array": feats.clone(), "wav_len": flen.clone()}
-        torch.cuda.current_stream(self.device).synchronize()
-        return {"wav_array": feats.clone(), "wav_len": flen.clone()}
+        feats, flen = self.pipeline.run(wavs, to_host=self.to_host)
+        return {"wav_array": feats, "wav_len": flen}
+
+    def prefetch(self, batches):
+        pending = None
+        for wavs in batches:
+            h = self.pipeline.submit(wavs, to_host=self.to_host)
+            if pending is not None:
+                feats, flen = self.pipeline.result(pending)
+                yield {"wav_array": feats, "wav_len": flen}
+            pending = h
+        if pending is not None:
+            feats, flen = self.pipeline.result(pending)
+            yield {"wav_array": feats, "wav_len": flen}
 
 
 def make_dataset_class():

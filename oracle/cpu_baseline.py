@@ -26,31 +26,50 @@ _WAVS = None     # set before the pool forks: workers inherit the waveforms (a D
                  # own audio from disk; pickling the inputs to the workers would penalise the baseline)
 
 
+_GLOBAL = None   # (mean, istd) of the global-CMVN chain, inherited by the forked workers like the waveforms
+_OPTS = {}       # extra fbank options (e.g. sample_frequency=8000.0) and peak_norm
+
+
 def _one(args):
     idx, cmvn, specaug = args
     wav = _WAVS[idx]
     from . import lasr_frontend
-    x = lasr_frontend.wav_to_kaldi_fbank(wav, use_torchaudio=True)
+    opts = dict(_OPTS)
+    if opts.pop("peak_norm", False):
+        wav = lasr_frontend.voice_norm(wav)                 # vectorised restatement of the reference's pure-Python loop
+    x = lasr_frontend.wav_to_kaldi_fbank(wav, use_torchaudio=True, **opts)
     if cmvn == "utt_meanvar":
         x = lasr_frontend.utterance_cmvn(x, True)
     elif cmvn == "utt_mean":
         x = lasr_frontend.utterance_cmvn(x, False)
-    if specaug:
+    elif cmvn == "global":
+        x = lasr_frontend.apply_cmvn(x, _GLOBAL[0], _GLOBAL[1])
+    if specaug == "full":
+        x = lasr_frontend.spec_augment_full(x)              # time warp (PIL BICUBIC) + masks: the registry transform `specaug`
+        x = x[0] if isinstance(x, tuple) else x
+    elif specaug:
         x, _ = lasr_frontend.spec_augment_masks(x)
     return x
 
 
-def run_chain(wavs, cmvn="utt_meanvar", specaug=False, workers=1, pool=None):
+def set_chain_options(global_cmvn=None, **opts):
+    """Call BEFORE make_pool: global CMVN vectors (mean, istd) and extra fbank options for the workers."""
+    global _GLOBAL, _OPTS
+    _GLOBAL, _OPTS = global_cmvn, dict(opts)
+
+
+def run_chain(wavs, cmvn="utt_meanvar", specaug=False, workers=1, pool=None, first=0):
     """fbank:80 (+ CMVN) (+ SpecAugment masks) for every utterance, then batch_list.  Returns the
-    padded (B, Tmax, 80) float32 batch and the frame counts, exactly what collate_fn builds."""
+    padded (B, Tmax, 80) float32 batch and the frame counts, exactly what collate_fn builds.
+    With a pool, ``wavs`` must be the slice ``[first : first + len(wavs)]`` of the list the pool was forked with."""
     from . import lasr_frontend
     global _WAVS
     if pool is None:
         _WAVS = wavs
         jobs = [(i, cmvn, specaug) for i in range(len(wavs))]
     else:
-        assert _WAVS is not None and len(wavs) <= len(_WAVS), "call make_pool(wavs, workers) first"
-        jobs = [(i, cmvn, specaug) for i in range(len(wavs))]
+        assert _WAVS is not None and first + len(wavs) <= len(_WAVS), "call make_pool(all_wavs, workers) first"
+        jobs = [(first + i, cmvn, specaug) for i in range(len(wavs))]
     if pool is not None:
         feats = pool.map(_one, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
     else:

@@ -1,0 +1,157 @@
+"""GPU: the host pipeline behind B200Collate (lists of host ndarrays in, the reference's batch tensors out) and the
+round-1 advisor findings: host synchronisation before host tensors are handed out, batches of CHANGING geometry,
+zero-fill masks together with utterance CMVN, int16 statistics with peak normalisation, sharded statistics."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kaldi_fbank, lasr_frontend
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(got, ref, rtol=1e-4, atol=1e-5):
+    return int((np.abs(got.astype(np.float64) - ref) > atol + rtol * np.abs(ref)).sum())
+
+
+def _batches(rng, shapes):
+    return [[np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens] for lens in shapes]
+
+
+def test_collate_to_host_needs_no_external_sync_and_handles_changing_geometry(lasr_b200):
+    """B200Collate(to_host=True) returns finished host tensors (no torch.cuda.synchronize by the caller) for batches whose B,
+    Nmax and Tmax all change from call to call; rows past an utterance's frames are zero (batch_list, dataset.py:8-22)."""
+    rng = np.random.default_rng(21)
+    shapes = [(16000, 4800, 32001), (48000, 400, 9999, 16000, 25000), (8000,), (160000, 16000), (4800, 32001, 16000)]
+    batches = _batches(rng, shapes)
+    col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, cmvn="utt_meanvar", ring=2)
+    direct = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+    for rep in range(2):
+        for wavs, lens in zip(batches, shapes):
+            out = col(wavs)
+            feats, flen = out["wav_array"], out["wav_len"]
+            assert not feats.is_cuda and feats.is_pinned() and feats.dtype == torch.float32 and feats.is_contiguous()
+            T = [kaldi_fbank.num_frames(n) for n in lens]
+            assert tuple(feats.shape) == (len(lens), max(T), 80) and flen.tolist() == T
+            g = feats.numpy().copy()                              # read immediately: no synchronize in between
+            nmax = (max(lens) + 3) // 4 * 4
+            buf = np.zeros((len(lens), nmax), dtype=np.float32)
+            for i, w in enumerate(wavs):
+                buf[i, : len(w)] = w
+            want = direct(torch.from_numpy(buf).to(DEV), np.array(lens, dtype=np.int64))[0].cpu().numpy()
+            assert np.allclose(g, want, rtol=1e-5, atol=1e-5)
+            for i, t in enumerate(T):
+                assert np.all(g[i, t:] == 0)
+                ref = lasr_frontend.utterance_cmvn(lasr_frontend.wav_to_kaldi_fbank(wavs[i], use_torchaudio=True))
+                assert _close(g[i, :t], ref.astype(np.float64), rtol=1e-4, atol=2e-5) <= max(1, ref.size // 100000)
+
+
+def test_collate_input_types_and_prefetch(lasr_b200):
+    rng = np.random.default_rng(22)
+    shapes = [(16000, 24000, 4321), (32000, 8000), (12345, 54321, 16000, 999)]
+    b64 = _batches(rng, shapes)
+    col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True)
+    want = [col(w)["wav_array"].clone() for w in b64]
+    got32 = [col([x.astype(np.float32) for x in w])["wav_array"].clone() for w in b64]
+    for a, b in zip(want, got32):
+        assert torch.equal(a, b)                                  # float64 -> float32 happens once, on the host, round to nearest
+    pcm = [[np.round(x * 32767).astype(np.int16) for x in w] for w in b64]
+    for w16, w in zip(pcm, b64):
+        a = col(w16)["wav_array"].clone()
+        b = col([x.astype(np.float32) / 32768.0 for x in w16])["wav_array"]
+        assert torch.equal(a, b)                                  # (float)s16 == float sample * 2^15 exactly
+    outs = [d["wav_array"].clone() for d in col.prefetch(b64)]
+    assert len(outs) == len(want) and all(torch.equal(a, b) for a, b in zip(outs, want))
+    dev_col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=False)
+    d = dev_col(b64[0])
+    assert d["wav_array"].is_cuda and torch.equal(d["wav_array"].cpu(), want[0]) and d["wav_len"].cpu().tolist() == [kaldi_fbank.num_frames(n) for n in shapes[0]]
+    with pytest.raises(AssertionError):
+        col([np.zeros(16000), np.zeros(399)])                     # torchaudio asserts on short input (TA:142)
+    with pytest.raises(ValueError):
+        col([np.zeros((100, 2))])
+
+
+def test_zero_masks_with_utterance_cmvn_are_applied_after_normalisation(lasr_b200):
+    """specaug + replace_with_zero + utterance CMVN: statistics over the UNMASKED features, zeros written after the
+    normalisation (CMVN first, masks second -- the order of the mean-fill and time-warp paths)."""
+    rng = np.random.default_rng(23)
+    lens = [48000, 160000, 7 * 16000 + 77, 6000]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    nmax = (max(lens) + 3) // 4 * 4
+    buf = np.zeros((len(lens), nmax), dtype=np.float32)
+    for i, w in enumerate(wavs):
+        buf[i, : len(w)] = w
+    wav, n = torch.from_numpy(buf).to(DEV), np.array(lens, dtype=np.int64)
+    raw = lasr_b200.GpuFbankFrontend()(wav, n)[0].cpu().numpy()
+    for mode, nv in (("utt_meanvar", True), ("utt_mean", False)):
+        fe = lasr_b200.GpuFbankFrontend(cmvn=mode, specaug=True, replace_with_zero=True)
+        random.seed(5)
+        np.random.seed(5)
+        g = fe(wav, n)[0].cpu().numpy()
+        random.seed(5)
+        np.random.seed(5)
+        for i, k in enumerate(lens):
+            T = kaldi_fbank.num_frames(k)
+            x = lasr_frontend.utterance_cmvn(raw[i, :T], nv)
+            y, rects = lasr_frontend.spec_augment_masks(x.copy(), replace_with_zero=True)
+            masked = y != x
+            assert np.all(g[i, :T][y == 0] == 0)
+            assert _close(g[i, :T], y.astype(np.float64), rtol=1e-4, atol=2e-5) == 0
+            assert masked.any() or not rects
+            assert np.all(g[i, T:] == 0)
+
+
+def test_accumulate_stats_int16_peak_norm_and_validation(lasr_b200):
+    rng = np.random.default_rng(24)
+    lens = [16000, 23456, 8000]
+    pcm = [np.round(np.clip(rng.normal(0, 0.2, n), -1, 1) * 32767).astype(np.int16) for n in lens]
+    nmax = (max(lens) + 7) // 8 * 8
+    b16 = np.zeros((3, nmax), dtype=np.int16)
+    for i, w in enumerate(pcm):
+        b16[i, : len(w)] = w
+    n = np.array(lens, dtype=np.int64)
+    fe = lasr_b200.GpuFbankFrontend(peak_norm=True)
+    st16 = fe.accumulate_stats(torch.from_numpy(b16).to(DEV), n).cpu().numpy()
+    st32 = fe.accumulate_stats(torch.from_numpy(b16.astype(np.float32) / 32768.0).to(DEV), n).cpu().numpy()
+    assert np.allclose(st16, st32, rtol=1e-9, atol=1e-6) and st16[0, 80] == sum(kaldi_fbank.num_frames(k) for k in lens)
+    feats = fe(torch.from_numpy(b16).to(DEV), n)[0].cpu().numpy()
+    ref = lasr_frontend.cmvn_stats([feats[i, : kaldi_fbank.num_frames(k)] for i, k in enumerate(lens)])
+    assert np.allclose(st16, ref, rtol=2e-7, atol=1e-4)
+    with pytest.raises(AssertionError):
+        fe.accumulate_stats(torch.zeros((1, 400), device=DEV), np.array([399]))
+    with pytest.raises(ValueError):
+        fe.accumulate_stats(torch.zeros((1, 400), device=DEV), np.array([401]))
+    with pytest.raises(ValueError):
+        fe.accumulate_stats(torch.zeros((1, 400)), np.array([400]))
+
+
+def test_sharded_statistics_sum_to_the_fp64_definition(lasr_b200):
+    """the product's accumulate_stats on two utterance shards (cmvn.shard_utterances), summed like the
+    all-reduce does, equals the fp64 definition (oracle cmvn_stats) on the whole batch's features."""
+    rng = np.random.default_rng(25)
+    lens = np.round(rng.uniform(0.5, 6.0, 24) * 16000).astype(np.int64)
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1).astype(np.float32) for n in lens]
+    fe = lasr_b200.GpuFbankFrontend()
+    total = torch.zeros((2, 81), dtype=torch.float64, device=DEV)
+    shards = lasr_b200.cmvn.shard_utterances(lens, 2)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(24))
+    feats_all = []
+    for idx in shards:
+        nmax = int((lens[idx].max() + 3) // 4 * 4)
+        buf = np.zeros((len(idx), nmax), dtype=np.float32)
+        for j, u in enumerate(idx):
+            buf[j, : lens[u]] = wavs[u]
+        w = torch.from_numpy(buf).to(DEV)
+        part = fe.accumulate_stats(w, lens[idx])
+        total += part                                             # what all_reduce(sum) computes over the ranks
+        f = fe(w, lens[idx])[0].cpu().numpy()
+        feats_all += [f[j, : kaldi_fbank.num_frames(int(lens[u]))] for j, u in enumerate(idx)]
+    ref = lasr_frontend.cmvn_stats(feats_all)
+    assert total[0, 80].item() == ref[0, 80]
+    assert np.allclose(total.cpu().numpy(), ref, rtol=2e-7, atol=1e-4)
+    mean, istd = lasr_b200.cmvn.mean_istd(total)
+    rm, ri = lasr_frontend.cmvn_from_stats(ref)
+    assert np.allclose(mean, rm, rtol=1e-6, atol=1e-6) and np.allclose(istd, ri, rtol=1e-6, atol=1e-6)

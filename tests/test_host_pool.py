@@ -1,0 +1,86 @@
+"""CPU: the host staging part of the C ABI (b200fe_host_*): packing / float64->float32 conversion of utterance
+lists into one staging buffer and the zero fill of padding rows -- no CUDA device needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def pool(lasr_b200):
+    lib = lasr_b200._lib.load()
+    h = C.c_void_p()
+    assert lib.b200fe_host_pool_create(3, C.byref(h)) == 0
+    assert lib.b200fe_host_pool_threads(h) == 3
+    yield lib, h
+    lib.b200fe_host_pool_destroy(h)
+
+
+def _aligned(n, dtype):
+    raw = np.empty(n * np.dtype(dtype).itemsize + 64, dtype=np.uint8)
+    o = (-raw.ctypes.data) % 16
+    return raw[o:o + n * np.dtype(dtype).itemsize].view(dtype)
+
+
+@pytest.mark.parametrize("src_dtype,code,dst_dtype", [(np.float64, 2, np.float32), (np.float32, 0, np.float32), (np.int16, 1, np.int16)])
+def test_pack_list_of_utterances(pool, src_dtype, code, dst_dtype):
+    lib, h = pool
+    rng = np.random.default_rng(7)
+    lens = np.array([1, 401, 70001, 0, 16000, 123457, 7], dtype=np.int64)           # ragged, one empty, one longer than a task chunk
+    if src_dtype == np.int16:
+        wavs = [rng.integers(-32768, 32767, n).astype(np.int16) for n in lens]
+    else:
+        wavs = [rng.normal(0, 0.3, n).astype(src_dtype) for n in lens]
+    al = 16 // np.dtype(dst_dtype).itemsize
+    offs = np.zeros(len(lens), dtype=np.int64)
+    np.cumsum((lens[:-1] + al - 1) // al * al, out=offs[1:])
+    total = int(offs[-1] + (lens[-1] + al - 1) // al * al)
+    dst = _aligned(total, dst_dtype)
+    dst[:] = 99
+    ptrs = (C.c_void_p * len(wavs))(*[max(w.ctypes.data, 1) for w in wavs])
+    tk = lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, len(wavs), code, dst.ctypes.data, offs.ctypes.data, total)
+    assert tk > 0, lib.b200fe_last_error()
+    assert lib.b200fe_host_wait(h, tk) == 0
+    for w, o, n in zip(wavs, offs, lens):
+        assert np.array_equal(dst[o:o + n], w.astype(dst_dtype))                      # float64 -> float32: round to nearest, like .astype
+        assert np.all(dst[o + n:o + (n + al - 1) // al * al] == 0)                     # alignment gap cleared
+    assert lib.b200fe_host_wait(h, tk) != 0                                            # a ticket can be waited for once
+
+
+def test_pack_argument_errors(pool):
+    lib, h = pool
+    w = np.zeros(10)
+    ptrs = (C.c_void_p * 1)(w.ctypes.data)
+    lens = np.array([10], dtype=np.int64)
+    dst = _aligned(16, np.float32)
+    off_bad = np.array([2], dtype=np.int64)                                             # not 16-byte aligned
+    assert lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, 1, 2, dst.ctypes.data, off_bad.ctypes.data, 16) < 0
+    off = np.array([8], dtype=np.int64)
+    assert lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, 1, 2, dst.ctypes.data, off.ctypes.data, 16) < 0      # does not fit
+    assert lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, 1, 5, dst.ctypes.data, off.ctypes.data, 64) < 0      # bad dtype code
+    assert b"host_pack" in lib.b200fe_last_error()
+
+
+def test_zero_padding_rows(pool):
+    lib, h = pool
+    B, T, D = 5, 300, 80
+    feats = np.full((B, T, D), 3.0, dtype=np.float32)
+    valid = np.array([300, 0, 17, 299, 1000], dtype=np.int64)                           # full, empty, partial, counts past T are clipped
+    tk = lib.b200fe_host_zero_rows_begin(h, feats.ctypes.data, B, T, D, valid.ctypes.data, 4)
+    assert tk > 0 and lib.b200fe_host_wait(h, tk) == 0
+    for b, v in enumerate(np.minimum(valid, T)):
+        assert np.all(feats[b, :v] == 3.0) and np.all(feats[b, v:] == 0.0)
+
+
+def test_jobs_complete_in_submission_order(pool):
+    lib, h = pool
+    big = np.random.default_rng(0).normal(size=2_000_000)
+    dst = _aligned(2_000_000, np.float32)
+    lens = np.array([big.size], dtype=np.int64)
+    off = np.zeros(1, dtype=np.int64)
+    ptrs = (C.c_void_p * 1)(big.ctypes.data)
+    tickets = [lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, 1, 2, dst.ctypes.data, off.ctypes.data, dst.size) for _ in range(4)]
+    assert tickets == sorted(tickets)
+    for tk in reversed(tickets):                                                        # waiting out of order is allowed
+        assert lib.b200fe_host_wait(h, tk) == 0
+    assert np.array_equal(dst, big.astype(np.float32))
