@@ -14,8 +14,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "obj")
 LIB = os.environ.get("B200FE_LIB") or os.path.join(HERE, "libb200fe.so")   # B200FE_LIB: A/B experiments with alternative builds
+OBJ = (LIB + ".obj") if os.environ.get("B200FE_LIB") else os.path.join(HERE, "obj")
 KERNEL_HDRS = ["fbank_kernel.cuh", "b200fe_common.cuh", "mel_static_default.inc", "fbank_instances.h"]
 MAIN_HDRS = KERNEL_HDRS + ["aux_kernels.cuh", "stream_kernels.cuh", "resample_kernels.cuh", "host_pool.h", "fbank_ws_kernel.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-pthread"]

@@ -44,3 +44,12 @@
 #define B200FE_X_7 B200FE_DEF
 #endif
 B200FE_FBANK_INSTANCES(B200FE_X)
+
+#if defined(B200FE_TIMELINE) && B200FE_INST_GROUP == 0
+extern "C" int b200fe_debug_timeline(void* host_dst, unsigned long long bytes, int clear)
+{
+    if (clear) { void* p = nullptr; cudaGetSymbolAddress(&p, b200fe::g_timeline); return (int)cudaMemset(p, 0, sizeof(b200fe::g_timeline)); }
+    if (bytes > sizeof(b200fe::g_timeline)) bytes = sizeof(b200fe::g_timeline);
+    return (int)cudaMemcpyFromSymbol(host_dst, b200fe::g_timeline, bytes);
+}
+#endif

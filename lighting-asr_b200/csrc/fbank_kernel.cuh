@@ -174,6 +174,15 @@ __device__ __forceinline__ int row_class(const int* __restrict__ bounds, int nb,
     return c;
 }
 
+#ifdef B200FE_TIMELINE
+// Debug build only (tools/timeline.py): per CTA, warp and tile the SM clock at the phase boundaries of the tile loop.
+constexpr int kTlTiles = 48, kTlStamps = 8;
+static __device__ long long g_timeline[296][8][kTlTiles][kTlStamps];   // one copy per translation unit; tools read group 0's
+#define TL_STAMP(k) do { if (lane == 0 && it < kTlTiles && blockIdx.x < 296) g_timeline[blockIdx.x][warp][it][k] = clock64(); } while (0)
+#else
+#define TL_STAMP(k) do { } while (0)
+#endif
+
 struct TileGeom {
     int utt, f0, nvalid, nrows, T;
     bool apply, ready;
@@ -707,6 +716,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             fut = resolve(nxt.id < ntiles ? id2 : ntiles);
         }
 
+        TL_STAMP(0);
         if (a.use_tma) {
             // the tile buffer has been free since the last phase-A barrier: when the current tile carries no
             // frames (padded grid) the next tile's load can go out right away, otherwise after this tile's phase A
@@ -732,6 +742,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             __syncthreads();
         }
 
+        TL_STAMP(1);
         if (nvalid > 0) {
             // ================= phase A: half-warp per frame (pair of frames in dual-256 mode) =================
             FrameCtx fc;
@@ -828,7 +839,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 }
                 consumed_phase ^= 1u;
             }
+            TL_STAMP(2);
             __syncthreads();   // B1: PT complete; every warp has finished phase C of the previous tile
+            TL_STAMP(3);
             if (tid == 0) {
                 if (!kEarlyTma && a.use_tma && nxt.id < ntiles) issue_load(gn, 0);
                 s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
@@ -904,7 +917,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     }
                 }
             }
+            TL_STAMP(4);
             __syncthreads();   // B2: staging complete; PT free for the next tile's phase A
+            TL_STAMP(5);
             nxt_desc = s_desc[it & 1];
         }
 
@@ -1104,6 +1119,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 }
             }
         }
+        TL_STAMP(6);
+#ifdef B200FE_TIMELINE
+        if (lane == 0 && it < kTlTiles && blockIdx.x < 296) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_timeline[blockIdx.x][warp][it][7] = ((long long)smid << 32) | (unsigned)nvalid; }
+#endif
         // the staging area aliases the transposition buffers that the next phase A overwrites
         // No closing barrier: a warp that finishes phase C goes straight to the next tile's phase A.  (A tile
         // without frames has no B1 / B2, so the descriptor exchange gets its own barrier.)
