@@ -234,6 +234,9 @@ long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_sr
 /* Clears rows [valid_rows[u], utt_rows) of every utterance of a host [batch][utt_rows][row_elems] float32 tensor. */
 long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, int batch, long long utt_rows, long long row_elems,
                                       const long long* valid_rows, int elem_bytes /* 4 float32, 2 bfloat16 */);
+/* Clears n byte ranges [offsets[i], offsets[i] + nbytes[i]) of a host buffer (non-temporal stores): the parts of a recycled
+ * batch buffer that still hold an earlier batch's rows and fall into this batch's padding. */
+long long b200fe_host_zero_ranges_begin(b200fe_host_pool* pool, void* h_base, const long long* offsets, const long long* nbytes, int n);
 int b200fe_host_wait(b200fe_host_pool* pool, long long ticket);
 
 /* Host-only SpecAugment planner (no device work): the rectangles of the reference's `freq_mask` / `time_mask` and the

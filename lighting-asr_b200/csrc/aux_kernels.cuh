@@ -395,6 +395,13 @@ __device__ __forceinline__ double pil_bicubic(double x)
 constexpr int kWarpRows = 32;    // output rows per CTA
 constexpr int kWarpTaps = 32;    // >= ceil(2 * scale) * 2 + 1 for |in - out| <= 5
 
+// Work split (second version; the first spent 218 thread-instructions per output cell, most of them in the coefficient
+// set-up that 32 of 256 threads ran alone): (1) 32 threads derive the tap window of their output row (one float64 division
+// per row); (2) ALL threads evaluate the raw bicubic coefficients, one (row, tap) pair each; (3) 32 threads add a row's
+// coefficients in Pillow's order (the sum's rounding depends on it), (4) all threads normalise, one division per pair;
+// (5) thread = (row, 4 columns): 128-bit loads of the source taps, float64 multiply and add per tap in source order, one
+// rounding to float32, 128-bit store; (6) statistics from the shared-memory copy of the tile: thread = (row third, column),
+// row classes looked up once per row.
 __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
 {
     const int utt = blockIdx.y;
@@ -403,15 +410,19 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
     const int r0 = blockIdx.x * kWarpRows;
     if (r0 >= a.Tmax) return;
     __shared__ double s_k[kWarpRows][kWarpTaps];
-    __shared__ int s_ymin[kWarpRows], s_n[kWarpRows];
+    __shared__ double s_c[kWarpRows], s_ss[kWarpRows], s_ww[kWarpRows];
+    __shared__ int s_ymin[kWarpRows], s_n[kWarpRows], s_xmin[kWarpRows], s_cls[kWarpRows];
     extern __shared__ float s_tile[];              // [kWarpRows][nmel + 1]
+    const int tid = threadIdx.x;
     const int center = a.warp[2 * utt], warped = a.warp[2 * utt + 1];
     const float* src = a.in + (long long)utt * a.Tmax * a.nmel;
     float* dst = a.out + (long long)utt * a.Tmax * a.nmel;
-    if (threadIdx.x < kWarpRows) {
-        const int row = r0 + threadIdx.x;
-        int ymin = row, cnt = 1;
-        s_k[threadIdx.x][0] = 1.0;
+    const int nb = a.n_cls - 1;
+    const int* bounds = (a.stats != nullptr && a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
+    if (tid < kWarpRows) {
+        const int row = r0 + tid;
+        int ymin = row, cnt = 1, xmin = 0;
+        double c = 0.0, ss = 0.0;
         if (row < T && center >= 0) {
             const bool left = row < warped;
             const int in_size = left ? center : T - center;
@@ -424,64 +435,97 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
                 const double scale = (double)in_size / (double)out_size;
                 const double filterscale = scale < 1.0 ? 1.0 : scale;
                 const double support = __dmul_rn(2.0, filterscale);
-                const double c = __dmul_rn((double)xx + 0.5, scale);
-                const double ss = 1.0 / filterscale;
-                int xmin = (int)__dadd_rn(__dsub_rn(c, support), 0.5);
+                c = __dmul_rn((double)xx + 0.5, scale);
+                ss = 1.0 / filterscale;
+                xmin = (int)__dadd_rn(__dsub_rn(c, support), 0.5);
                 if (xmin < 0) xmin = 0;
                 int xmax = (int)__dadd_rn(__dadd_rn(c, support), 0.5);
                 if (xmax > in_size) xmax = in_size;
-                cnt = min(xmax - xmin, kWarpTaps);
-                double ww = 0.0;
-                for (int x = 0; x < cnt; ++x) {
-                    const double w = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), c), 0.5), ss));
-                    s_k[threadIdx.x][x] = w;
-                    ww = __dadd_rn(ww, w);
-                }
-                if (ww != 0.0)
-                    for (int x = 0; x < cnt; ++x) s_k[threadIdx.x][x] = s_k[threadIdx.x][x] / ww;
+                cnt = -min(xmax - xmin, kWarpTaps);                   // negative: coefficients still to be evaluated
                 ymin = base + xmin;
             }
         }
-        s_ymin[threadIdx.x] = ymin;
-        s_n[threadIdx.x] = cnt;
+        s_ymin[tid] = ymin; s_n[tid] = cnt; s_xmin[tid] = xmin; s_c[tid] = c; s_ss[tid] = ss;
+        s_cls[tid] = bounds ? row_class(bounds, nb, row) : 0;
+        if (cnt > 0) s_k[tid][0] = 1.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < kWarpRows * kWarpTaps; i += 256) {
+        const int r = i / kWarpTaps, x = i - r * kWarpTaps;
+        if (x < -s_n[r]) s_k[r][x] = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + s_xmin[r]), s_c[r]), 0.5), s_ss[r]));
+    }
+    __syncthreads();
+    if (tid < kWarpRows && s_n[tid] < 0) {
+        double ww = 0.0;
+        for (int x = 0; x < -s_n[tid]; ++x) ww = __dadd_rn(ww, s_k[tid][x]);
+        s_ww[tid] = ww;
+    }
+    __syncthreads();
+    for (int i = tid; i < kWarpRows * kWarpTaps; i += 256) {
+        const int r = i / kWarpTaps, x = i - r * kWarpTaps;
+        if (x < -s_n[r] && s_ww[r] != 0.0) s_k[r][x] = s_k[r][x] / s_ww[r];
     }
     __syncthreads();
     const int ostride = a.nmel + 1;
-    for (int e = threadIdx.x; e < kWarpRows * a.nmel; e += 256) {
-        const int r = e / a.nmel, col = e - r * a.nmel, row = r0 + r;
-        if (row >= a.Tmax) break;
-        float v = 0.f;
-        if (row < T) {
-            const int ymin = s_ymin[r], cnt = s_n[r];
-            double acc = 0.0;
-            for (int y = 0; y < cnt; ++y) acc = __dadd_rn(acc, __dmul_rn((double)src[(long long)(ymin + y) * a.nmel + col], s_k[r][y]));
-            v = (float)acc;
+    const bool vec = (a.nmel & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    if (vec) {
+        const int nq = a.nmel >> 2;
+        for (int e = tid; e < kWarpRows * nq; e += 256) {
+            const int r = e / nq, q = e - r * nq, row = r0 + r;
+            if (row >= a.Tmax) break;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < T) {
+                const int ymin = s_ymin[r], cnt = abs(s_n[r]);
+                const float4* sp = reinterpret_cast<const float4*>(src + (long long)ymin * a.nmel) + q;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int y = 0; y < cnt; ++y) {
+                    const float4 p = __ldg(sp + (long long)y * nq);
+                    const double k = s_k[r][y];
+                    a0 = __dadd_rn(a0, __dmul_rn((double)p.x, k)); a1 = __dadd_rn(a1, __dmul_rn((double)p.y, k));
+                    a2 = __dadd_rn(a2, __dmul_rn((double)p.z, k)); a3 = __dadd_rn(a3, __dmul_rn((double)p.w, k));
+                }
+                v = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+            }
+            reinterpret_cast<float4*>(dst + (long long)row * a.nmel)[q] = v;
+            float* tp = s_tile + r * ostride + 4 * q;
+            tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w;
         }
-        dst[(long long)row * a.nmel + col] = v;
-        s_tile[r * ostride + col] = v;
+    } else {
+        for (int e = tid; e < kWarpRows * a.nmel; e += 256) {
+            const int r = e / a.nmel, col = e - r * a.nmel, row = r0 + r;
+            if (row >= a.Tmax) break;
+            float v = 0.f;
+            if (row < T) {
+                const int ymin = s_ymin[r], cnt = abs(s_n[r]);
+                double acc = 0.0;
+                for (int y = 0; y < cnt; ++y) acc = __dadd_rn(acc, __dmul_rn((double)src[(long long)(ymin + y) * a.nmel + col], s_k[r][y]));
+                v = (float)acc;
+            }
+            dst[(long long)row * a.nmel + col] = v;
+            s_tile[r * ostride + col] = v;
+        }
     }
     if (a.stats == nullptr) return;
     __syncthreads();
     const int nvalid = min(max(T - r0, 0), kWarpRows);
     if (nvalid <= 0) return;
-    const int nb = a.n_cls - 1;
-    const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
     double* sb = a.stats + (long long)utt * a.stats_stride;
-    for (int j = threadIdx.x; j < a.nmel; j += 256) {
-        int cls = bounds ? row_class(bounds, nb, r0) : 0;
-        double s1 = 0.0, s2 = 0.0;
-        for (int fr = 0; fr < nvalid; ++fr) {
-            if (bounds) {
-                const int cc = row_class(bounds, nb, r0 + fr);
-                if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
-            }
-            const double x = (double)s_tile[fr * ostride + j];
-            s1 += x;
-            s2 = fma(x, x, s2);
-        }
-        atomicAdd(sb + (long long)cls * a.nmel + j, s1);
-        atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
+    const int parts = max(1, min(256 / a.nmel, 3));
+    const int part = tid / a.nmel, j = tid - part * a.nmel;
+    if (part >= parts) return;
+    const int rb = (nvalid * part) / parts, re = (nvalid * (part + 1)) / parts;
+    if (re <= rb) return;
+    int cls = s_cls[rb];
+    double s1 = 0.0, s2 = 0.0;
+    for (int fr = rb; fr < re; ++fr) {
+        const int cc = s_cls[fr];
+        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
+        const double x = (double)s_tile[fr * ostride + j];
+        s1 += x;
+        s2 = fma(x, x, s2);
     }
+    atomicAdd(sb + (long long)cls * a.nmel + j, s1);
+    atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
 }
 
 // Vectorised in-place post pass for num_mel_bins % 4 == 0: thread = (row slot, 4 columns), float4

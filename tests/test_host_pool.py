@@ -84,3 +84,55 @@ def test_jobs_complete_in_submission_order(pool):
     for tk in reversed(tickets):                                                        # waiting out of order is allowed
         assert lib.b200fe_host_wait(h, tk) == 0
     assert np.array_equal(dst, big.astype(np.float32))
+
+
+def test_stale_ranges_of_a_recycled_batch_buffer():
+    """HostPipeline clears only what an earlier batch left inside this batch's padding: brute-force check of the interval logic."""
+    import importlib
+    hp = importlib.import_module("lighting-asr_b200.host_pipeline")
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        size = 260
+
+        def rand_intervals():
+            pts = np.sort(rng.choice(size, size=2 * int(rng.integers(0, 8)), replace=False))
+            return [(int(pts[2 * i]), int(pts[2 * i + 1])) for i in range(len(pts) // 2)]
+
+        dirty, valid = rand_intervals(), rand_intervals()
+        view = int(rng.integers(1, size))
+        valid = [(a, min(b, view)) for a, b in valid if a < view]
+        zero, after = hp.stale_ranges(dirty, valid, view)
+        buf = np.zeros(size, dtype=int)
+        for a, b in dirty:
+            buf[a:b] = 1
+        want = buf.copy()
+        for a, b in valid:
+            want[a:b] = 0
+        want[view:] = 0
+        got = np.zeros(size, dtype=int)
+        for a, b in zero:
+            assert b > a
+            got[a:b] += 1
+        assert np.array_equal(got, want)
+        state = buf.copy()
+        for a, b in zero:
+            state[a:b] = 0
+        for a, b in valid:
+            state[a:b] = 1
+        cover = np.zeros(size, dtype=int)
+        for a, b in after:
+            cover[a:b] = 1
+        assert np.all(cover >= state)
+
+
+def test_zero_ranges(pool):
+    lib, h = pool
+    buf = np.full(5000, 7, dtype=np.uint8)
+    off = np.array([3, 100, 4000], dtype=np.int64)
+    nb = np.array([50, 0, 999], dtype=np.int64)
+    tk = lib.b200fe_host_zero_ranges_begin(h, buf.ctypes.data, off.ctypes.data, nb.ctypes.data, 3)
+    assert tk > 0 and lib.b200fe_host_wait(h, tk) == 0
+    want = np.full(5000, 7, dtype=np.uint8)
+    want[3:53] = 0
+    want[4000:4999] = 0
+    assert np.array_equal(buf, want)
