@@ -70,7 +70,7 @@ long long b200fe_num_frames(const b200fe_plan* plan, long long num_samples);
 /* Introspection for tests / benchmarks: what = 0 straight-line mel path in use, 1 registers
  * loaded per lane (13|16), 2 dynamic shared memory per CTA, 3 resident CTAs per SM, 4 SM count, 5 frames
  * per tile (the granularity of b200fe_build_tile_table), 6 experimental warp-specialised kernel in use, 7 in-launch utterance CMVN
- * (apply tiles) available. */
+ * (apply tiles) available, 8 rows per CMVN-apply tile, 9 warps per CTA. */
 int b200fe_plan_info(const b200fe_plan* plan, int what);
 
 /* Host helper: fills table[2*i] = utterance, table[2*i+1] = first frame for every tile (b200fe_plan_info(plan, 5) frames)
@@ -94,13 +94,13 @@ int b200fe_build_tile_table_device(const b200fe_plan* plan, const long long* d_n
  * (2) apply_lag > 0: CMVN-APPLY tiles (utterance CMVN inside the fused launch instead of b200fe_postpass, for the
  * `_subtract_column_mean` semantics of TA:220-226,644 and its mean/variance extension): besides the frame and padding tiles of
  * utterance u, slot u of the list carries the apply tiles of utterance u - apply_lag, entries (utterance | 0x40000000, row0) =
- * normalise rows [row0, row0 + 240) of that utterance in place; the last apply_lag utterances' apply tiles close the list.  A
+ * normalise rows [row0, row0 + R) of that utterance (R = b200fe_plan_info(plan, 8)) in place; the last apply_lag utterances' apply tiles close the list.  A
  * persistent CTA that takes an apply tile waits until all frame tiles of that utterance have been signalled in
  * d_utt_done[utterance] (int32 [batch + 1], zeroed by this call; element [batch] becomes non-zero if an apply tile ever gave up
  * waiting -- never expected, checked by the tests), reads the utterance's column sums from d_stats and rewrites the rows while
  * they are still L2-resident.  64 is a good lag: a CTA publishes the completions of eight tiles behind one fence and the
  * persistent grid holds about 900 claimed tiles, so the frame tiles an apply tile depends on have normally been signalled when it
- * is claimed.  Capacity with apply tiles: b200fe_tile_table_capacity(...) + batch * ceil(max_frames / 240).  Pass d_utt_done and
+ * is claimed.  Capacity with apply tiles: b200fe_tile_table_capacity(...) + batch * ceil(max_frames / R).  Pass d_utt_done and
  * apply_cmvn_mode to b200fe_fbank_fused.  Needs b200fe_plan_info(plan, 7) != 0.  Measured on B200 (BASELINE config 2): 0.380 ms
  * per step against 0.382 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3. */
 int b200fe_build_work_list_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads, int apply_lag,

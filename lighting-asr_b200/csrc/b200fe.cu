@@ -386,6 +386,8 @@ extern "C" int b200fe_plan_info(const b200fe_plan* p, int what)
         case 5: return plan_tile_frames(p);
         case 6: return p->use_ws;
         case 7: return (plan_has_lean(p) && !p->use_ws) ? 1 : 0;
+        case 8: return kApplyRows;
+        case 9: return kWarps;
         default: return -1;
     }
 }

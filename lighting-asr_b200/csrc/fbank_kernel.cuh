@@ -57,10 +57,27 @@ constexpr int kHalfWarps = 2 * kWarps;
 #define B200FE_CTAS (B200FE_WARPS == 8 ? 2 : B200FE_WARPS == 4 ? 4 : 3)
 #endif
 constexpr int kCtasPerSm = B200FE_CTAS;
-constexpr bool kAliasStaging = kWarps == 6;
+constexpr bool kAliasStaging = false;      // (the 3 CTAs/SM variant used to alias the staging tile onto the transposition buffers)
 constexpr int kMelGroups = kWarps == 4 ? 8 : kWarps;   // bin groups of phase B (16-frame tiles: one per half-warp)   // 3 CTAs/SM only fit with the staging tile aliased onto the transposition buffers
 constexpr int kXRow = 17;           // padded row length (float2) of the transposition buffer
-constexpr int kPTStride = kFT + 1;   // PT4[k/4][frame] float4 groups; a row of kFT frames is padded by one group (4*(kFT+1) = 4 mod 32 words)
+// Power spectra live INSIDE the transposition buffers (a frame's 256 power values replace the 2 kB the FFT no longer needs):
+// every half-warp owns a region [transposition: 16 rows x 17 float2 = 544 words | PT row of its first frame: 256 words | pad],
+// the PT row of its second frame overwrites the transposition area once the frame's FFT has left it.  Strides are chosen so
+// that (a) the two half-warps of a warp, which store in the same instruction, hit disjoint banks (region stride = 16 mod 32
+// words) and (b) the eight frames a quarter-warp reads with one LDS.128 in phase B (four consecutive warps x two half-warps)
+// start 4 words apart modulo 32 (warp stride = 4 mod 32): both the writers and the readers are conflict free.
+constexpr int kXWords = 16 * 17 * 2;                 // transposition area of a half-warp (float2 rows padded to 17)
+constexpr int kRegionHW = kXWords + 256 + 16;        // 816 words = 16 mod 32
+constexpr int kRegionWarp = 2 * kRegionHW + 4;       // 1636 words = 4 mod 32
+static_assert(kRegionHW % 32 == 16 && kRegionWarp % 32 == 4, "bank layout of the power-spectrum rows");
+#ifndef B200FE_TABLES_L1
+#define B200FE_TABLES_L1 0          // 1: window / split twiddles are read through L1 (ld.global.nc) instead of shared-memory copies
+#endif
+constexpr bool kTablesL1 = B200FE_TABLES_L1 != 0;
+#ifndef B200FE_STW_ROT
+#define B200FE_STW_ROT 0            // 1: split twiddles -j W_512^(l + 16 r) = (lane's r = 0 value, two registers) x W_32^r (immediates): no table loads
+#endif
+constexpr bool kStwRot = B200FE_STW_ROT != 0;
 constexpr int kMaxMel = 128;
 constexpr int kMaxTimeMasks = 4;
 constexpr int kMaxFreqMasks = 4;
@@ -68,7 +85,7 @@ constexpr int kMaxRowClasses = 2 * kMaxTimeMasks + 1;
 constexpr int kPadTileRows = 256;   // rows zeroed by one padding tile of the compact work list (table entry with first frame < 0)
 constexpr int kStages = 1;         // one tile buffer: the next tile's TMA is issued right after the phase-A barrier
 constexpr int kApplyBit = 0x40000000;   // work-list entry (utt | kApplyBit, row0): CMVN-apply tile, rows [row0, row0 + kApplyRows)
-constexpr int kApplyRows = kWarps == 8 ? 240 : 96;         // rows of one apply tile: 240 * 80 * 4 B = 76.8 kB fit the transposition + staging + PT buffers
+constexpr int kApplyRows = kWarps == 8 ? 192 : 96;         // rows of one apply tile: 192 * 80 * 4 B = 61.4 kB fit the transposition/PT regions + the staging tile
 constexpr int kSigBatch = 8;            // completions a CTA collects before one fence publishes them
 constexpr int kReadyBit = 0x20000000;   // descriptor only: the utterance was already complete when the tile was claimed (no wait)
 
@@ -150,11 +167,10 @@ __host__ __device__ inline SmemLayout make_layout(int tile_floats, int nmel)
     int o = 0;
     for (int s = 0; s < kStages; ++s) { L.tile_off[s] = o; o += tile_floats * 4; }
     L.xbuf_off = o;
-    const int xbytes = kHalfWarps * 16 * kXRow * 8, obytes = (kFT * (nmel + 1) * 4 + 15) & ~15;
-    if (kAliasStaging) { L.outs_off = o; o += (xbytes > obytes ? xbytes : obytes); }     // closing barrier per tile
-    else { o += xbytes; L.outs_off = o; o += obytes; }   // phase C of tile i overlaps phase A of tile i+1
-    L.pt_off = o; o += 64 * kPTStride * 16;
-    L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (128 + 256) * 8;   // mean | istd | masks | split twiddles (k < 128) | window pairs
+    const int xbytes = kWarps * kRegionWarp * 4, obytes = (kFT * (nmel + 1) * 4 + 15) & ~15;
+    L.pt_off = o;                                        // power-spectrum rows live inside the half-warp regions
+    o += xbytes; L.outs_off = o; o += obytes;            // phase C of tile i overlaps phase A of tile i+1
+    L.misc_off = o; o += (2 * ((nmel + 3) & ~3) + 8) * 4 + (kTablesL1 ? 0 : (128 + 256) * 8);   // mean | istd | masks | split twiddles (k < 128) | window pairs
     L.bar_off = o; o += 32 + 32 + 48;       // 4 mbarrier slots | 2 tile descriptors (int4) | pending completion signals (count + kSigBatch utterances)
     L.total = o;
     return L;
@@ -195,6 +211,20 @@ struct TileGeom {
 // applied by the compact, warp-uniform phase C so that the straight-line mel code stays small.
 __device__ __forceinline__ void emit_bin(float* orow, int j, float e) { orow[j] = e; }
 
+
+// Word offset (inside the transposition / PT area) of the power-spectrum row of frame slot fl.  Frame slots are dealt to
+// (warp, half-warp, pass) as  fl = (slot & 3) + 8 (slot >> 2) + 4 h2,  slot = warp + kWarps * pass  (dual-256 mode: the half-warp
+// of frames fl, fl + 1 with  fl = 8 (warp >> 1) + 2 (warp & 1) + 4 h2);  the first frame of a half-warp sits behind its
+// transposition area, the second one on top of it.
+template <bool kDual>
+__device__ __forceinline__ int pt_row(int fl)
+{
+    const int h2 = (fl >> 2) & 1;
+    int warp, second;
+    if (kDual) { const int fa = fl & ~1; warp = 2 * (fa >> 3) + ((fa >> 1) & 1); second = fl & 1; }
+    else { const int slot = (fl & 3) + 4 * (fl >> 3); warp = slot % kWarps; second = slot / kWarps; }
+    return warp * kRegionWarp + h2 * kRegionHW + (second ? 0 : kXWords);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Phase A building blocks (all inlined; 16 lanes cooperate on one 256-point complex FFT)
@@ -424,7 +454,7 @@ __device__ __forceinline__ void pair_exchange(const float2 (&v)[16], float2 (&rc
 #define B200FE_MEL_DEVICE_CODE
 #define MGROUP_BEGIN(w) __device__ __forceinline__ void mel_static_group##w(const float4* __restrict__ pcol, float* __restrict__ orow) { \
         float au = 0.f, ad = 0.f, au1 = 0.f, ad1 = 0.f, up_prev = 0.f; float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f); int cur = -1; (void)p4; (void)cur;
-#define MK(k, wu, wd) { if (((k) >> 2) != cur) { cur = (k) >> 2; p4 = pcol[cur * kPTStride]; } \
+#define MK(k, wu, wd) { if (((k) >> 2) != cur) { cur = (k) >> 2; p4 = pcol[cur]; } \
         const float p = ((k) & 3) == 0 ? p4.x : ((k) & 3) == 1 ? p4.y : ((k) & 3) == 2 ? p4.z : p4.w; \
         if ((k) & 1) { if ((wu) != 0.f) au1 = fmaf((wu), p, au1); if ((wd) != 0.f) ad1 = fmaf((wd), p, ad1); } \
         else         { if ((wu) != 0.f) au = fmaf((wu), p, au);   if ((wd) != 0.f) ad = fmaf((wd), p, ad); } }
@@ -554,7 +584,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     const int warp = tid >> 5, lane = tid & 31;
     const int h2 = lane >> 4, l = lane & 15;
     const int hw = warp * 2 + h2;
-    float2* xbuf = xbuf_all + hw * 16 * kXRow;
+    float* region = reinterpret_cast<float*>(xbuf_all) + warp * kRegionWarp + h2 * kRegionHW;   // this half-warp's transposition area + first PT row
+    float2* xbuf = reinterpret_cast<float2*>(region);
+    (void)hw;
     // the straight-line mel path fixes num_mel_bins and the power spectrum at compile time
     const int nmel = kStaticMel ? B200FE_STATIC_NMEL : a.nmel;
     const bool use_power = kStaticMel ? true : (a.use_power != 0);
@@ -562,15 +594,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 
     // ---- per-lane constants (live in registers across all tiles) ----
     // window (x 2^15) as float2 pairs in shared memory: lane l reads pair l + 16 n2 (conflict free)
-    for (int k = tid; k < 256; k += kThreads) s_win[k] = make_float2(__ldg(a.window + 2 * k), __ldg(a.window + 2 * k + 1));
-    const float2* wl = s_win + l;
-    const float* wls = reinterpret_cast<const float*>(s_win) + l;     // dual-256 mode: scalars w[l + 16 n2]
+    if (!kTablesL1) for (int k = tid; k < 256; k += kThreads) s_win[k] = make_float2(__ldg(a.window + 2 * k), __ldg(a.window + 2 * k + 1));
+    const float2* wl = (kTablesL1 ? reinterpret_cast<const float2*>(a.window) : s_win) + l;
+    const float* wls = (kTablesL1 ? a.window : reinterpret_cast<const float*>(s_win)) + l;     // dual-256 mode: scalars w[l + 16 n2]
     float2 tw[16];
 #pragma unroll
     for (int k = 1; k < 16; ++k) tw[k] = __ldg(a.twiddle + l * 16 + k);
     // split twiddles -j W_512^k live in shared memory (lane l reads k = l + 16 r: conflict free)
-    for (int k = tid; k < 128; k += kThreads) s_stw[k] = __ldg(a.split_tw + k);   // k = l + 16 r, r < 8
-    const float2* stw = s_stw + l;
+    if (!kTablesL1) for (int k = tid; k < 128; k += kThreads) s_stw[k] = __ldg(a.split_tw + k);   // k = l + 16 r, r < 8
+    const float2* stw = (kTablesL1 ? a.split_tw : s_stw) + l;
+    const float2 sw0 = kStwRot ? __ldg(a.split_tw + l) : make_float2(0.f, 0.f);      // -j W_512^l
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -795,8 +828,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     fft256_halfwarp(v, tw, xbuf, l);
                     float2 rc[8];
                     pair_exchange(v, rc, l, h2);
-                    // PT4 layout: float index of (k, fl) = ((k>>2)*kPTStride + fl)*4 + (k&3)
-                    float* pa = pt + ((l >> 2) * kPTStride + fl) * 4 + (l & 3);                        // k = l + 16 r
+                    // power-spectrum row of this frame: the first frame of the half-warp behind its transposition area, the second
+                    // on top of it (the FFT has left the area: fft256_halfwarp ends with __syncwarp after its last read)
+                    float* prow = region + ((kDual || sub == 0) ? kXWords : 0);
+                    float* pa = prow + l;                                                              // k = l + 16 r
                     if (kDual) {
                         // ---- separate the two real spectra; |2 Xa|^2 and |2 Xb|^2 (0.25 folded in the mel weights)
                         const bool bvalid = fl + 1 < nvalid;
@@ -807,30 +842,35 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             S = mul2(S, S); D = mul2(D, D);
                             float pwa = S.x + S.y, pwb = D.x + D.y;
                             if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }
-                            if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
-                            if (bvalid) pa[r * 4 * kPTStride * 4 + 4] = pwb;
+                            if (fvalid) pa[16 * r] = pwa;
+                            if (bvalid) pa[16 * r - kXWords] = pwb;          // frame b: on top of the transposition area
                         }
                     } else {
                         // ---- real-FFT split + power: 2X[k] = S + T, 2 conj X[256-k] = S - T ----
-                        float* pb = pt + (((256 - l) >> 2) * kPTStride + fl) * 4 + ((256 - l) & 3);    // k = 256 - l - 16 r
+                        float* pb = prow + 256 - l;                                                    // k = 256 - l - 16 r
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             const float2 bcj = make_float2(rc[r].x, -rc[r].y);
                             const float2 S = add2(v[r], bcj), D = sub2(v[r], bcj);
-                            const float2 sw = stw[16 * r];
+                            // W_32^r = exp(-j pi r / 16)
+                            constexpr float kC32[8] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                                       0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+                            constexpr float kS32[8] = {0.0f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                                                       -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+                            const float2 sw = (kStwRot && r > 0) ? c_mul(sw0, kC32[r], kS32[r]) : (kStwRot ? sw0 : stw[16 * r]);
                             const float2 T = c_mul(D, sw.x, sw.y);
                             float2 xa = add2(S, T), xb = sub2(S, T);
                             xa = mul2(xa, xa); xb = mul2(xb, xb);
                             float pwa = xa.x + xa.y, pwb = xb.x + xb.y;
                             if (!use_power) { pwa = sqrtf(pwa); pwb = sqrtf(pwb); }   // 2|X| (0.5 folded in weights)
-                            if (fvalid) pa[r * 4 * kPTStride * 4] = pwa;
-                            if (fvalid && (r != 0 || l != 0)) pb[-r * 4 * kPTStride * 4] = pwb;
+                            if (fvalid) pa[16 * r] = pwa;
+                            if (fvalid && (r != 0 || l != 0)) pb[-16 * r] = pwb;
                         }
                         if (l == 0 && fvalid) {   // bin 128 is its own partner: X[128] = conj Z[128]
                             const float2 z = v[8];
                             float p = 4.0f * (z.x * z.x + z.y * z.y);
                             if (!use_power) p = sqrtf(p);
-                            pt[(32 * kPTStride + fl) * 4] = p;      // bin 128 = group 32
+                            prow[128] = p;                          // bin 128
                         }
                     }
                 }
@@ -880,7 +920,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 const int fl = kWarps == 4 ? (lane & 15) : lane;
                 const int grp = kWarps == 4 ? 2 * warp + (lane >> 4) : warp;
                 float* orow = outs + fl * ostride;
-                const float4* pcol = reinterpret_cast<const float4*>(pt) + fl;
+                const float4* pcol = reinterpret_cast<const float4*>(pt + pt_row<kDual>(fl < kFT ? fl : 0));
                 if (fl >= kFT) {
                     // 24-frame tiles leave lanes 24..31 idle in this phase
                 } else if (kStaticMel) {
@@ -901,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 } else {
                     const int jb = a.grp_begin[grp], je = a.grp_begin[grp + 1];
                     if (jb < je) {
-                        const float* pf = pt + fl * 4;
+                        const float* pf = pt + pt_row<kDual>(fl);
                         float up_prev = 0.f;
 #pragma unroll 1
                         for (int s = jb; s <= je; ++s) {
@@ -909,7 +949,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             float au = 0.f, ad = 0.f;
 #pragma unroll 2
                             for (int k = kb; k < ke; ++k) {
-                                const float p = pf[(k >> 2) * (kPTStride * 4) + (k & 3)];
+                                const float p = pf[k];
                                 const float2 w = a.w_updn[k];
                                 au = fmaf(w.x, p, au);
                                 ad = fmaf(w.y, p, ad);
@@ -1138,8 +1178,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 if (tid == 0) signal_pending(g.apply);
                 pending = -1;
                 if (g.apply) {
-                    static_assert(kAliasStaging || kHalfWarps * 16 * kXRow * 8 + ((kFT * (B200FE_STATIC_NMEL + 1) * 4 + 15) & ~15) + 64 * kPTStride * 16 >=
-                                  kApplyRows * B200FE_STATIC_NMEL * 4, "an apply tile must fit the transposition + staging + PT buffers");
+                    static_assert(kWarps * kRegionWarp * 4 + ((kFT * (B200FE_STATIC_NMEL + 1) * 4 + 15) & ~15) >= kApplyRows * B200FE_STATIC_NMEL * 4,
+                                  "an apply tile must fit the transposition / PT regions + the staging tile");
                     if (apply_cmvn_tile(a, g.utt, g.f0, g.T, g.ready, s_mean, s_istd, smem + L.xbuf_off, &bars[2], (phase_bits >> 1) & 1u, tid, nmel))
                         phase_bits ^= 2u;
                 }

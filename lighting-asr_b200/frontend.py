@@ -22,7 +22,6 @@ def _ptr(t):
 
 
 _PAD_ROWS = 256       # rows zeroed by one padding tile (kPadTileRows in fbank_kernel.cuh)
-_APPLY_ROWS = 240     # rows normalised by one CMVN-apply tile (kApplyRows in fbank_kernel.cuh)
 
 
 def _tile_table(T, ft, Tmax=None):
@@ -161,6 +160,7 @@ class FbankPlan:
         self.tile_frames = self.lib.b200fe_plan_info(h, 5)
         self.uses_ws = bool(self.lib.b200fe_plan_info(h, 6))
         self.has_apply_tiles = self.lib.b200fe_plan_info(h, 7) == 1      # utterance CMVN inside the fused launch
+        self.apply_rows = self.lib.b200fe_plan_info(h, 8)                # rows normalised by one CMVN-apply tile
         self.sample_frequency = sample_frequency
 
     def num_frames(self, n):
@@ -470,7 +470,7 @@ class GpuFbankFrontend(torch.nn.Module):
                 # its length and the counter reset come from one small kernel on the device-resident sample counts
                 cap = lib.b200fe_tile_table_capacity(plan.handle, nb, Tmax, 1 if pads else 0)
                 if apply_tiles:
-                    cap += nb * ((Tmax + _APPLY_ROWS - 1) // _APPLY_ROWS)
+                    cap += nb * ((Tmax + plan.apply_rows - 1) // plan.apply_rows)
                 work = torch.empty((2 * cap + 2 + (nb + 1 if apply_tiles else 0),), dtype=torch.int32, device=dev)   # table | n_tiles | counter | done[nb] | error
                 done_ptr = C.c_void_p(work.data_ptr() + 8 * cap + 8) if apply_tiles else C.c_void_p(0)
                 zero_ptr, zero_bytes = (off(stats, b0, (n_cls + 1) * D * 8), nb * (n_cls + 1) * D * 8) if need_post else (C.c_void_p(0), 0)
