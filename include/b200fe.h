@@ -123,6 +123,10 @@ int b200fe_peak_absmax_i16(const b200fe_plan* plan, const short* d_wav, long lon
  * features are written straight into the (batch, max_frames, num_mel_bins) layout, rows past an
  * utterance's frame count are zero (pad_audio = 0, R/example/asr_en/conf/config_baseline.yaml:70). */
 typedef struct b200fe_fbank_args {
+    /* = sizeof(b200fe_fbank_args) of the header the caller was built against: a binding whose struct is shorter or longer than
+     * the library's (a stale copy of this declaration) is rejected with B200FE_EINVAL instead of being read past its end.
+     * The same first field opens b200fe_post_args and b200fe_warp_args. */
+    unsigned int struct_size;
     const float* d_wav;          /* [batch][wav_stride] float32 */
     long long wav_stride;        /* elements between utterances */
     const long long* d_nsamp;    /* [batch] valid samples */
@@ -202,6 +206,31 @@ typedef struct b200fe_fbank_args {
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);
 
+/* ---- Streaming front end (BASELINE config 5): S INDEPENDENT audio streams per handle.  The reference has no
+ * streaming fbank -- ASRProcess.frontend (R/lasr/process/asrprocess.py:49-56) transforms whole utterances and its "online"
+ * encoders chunk finished features (R/lasr/modules/net/online_transformer/encoder.py:143-176) -- so the contract is: the
+ * concatenation of a stream's push outputs equals the offline fbank of everything pushed into it, frame for frame.
+ * The handle owns the per-stream state on the device (the window - shift ... window - 1 samples the next frames still need),
+ * allocated once by b200fe_stream_create on the current device; a push allocates nothing, never synchronises and reads no
+ * length on the host, so a push with fixed pointers can be captured in a CUDA graph and replayed.  Streams of one push may
+ * carry chunks of DIFFERENT lengths (0 = nothing arrived for that stream); different handles / CUDA streams are independent. */
+typedef struct b200fe_stream b200fe_stream;
+int b200fe_stream_create(const b200fe_plan* plan, int n_streams, int max_chunk /* samples per push and stream */, b200fe_stream** out);
+void b200fe_stream_destroy(b200fe_stream* st);
+/* Upper bound of the frames one push can complete for one stream: size d_out with it. */
+int b200fe_stream_max_frames(const b200fe_stream* st);
+/* Forgets the carry of the listed streams (d_ids device int32 [n]; NULL = streams 0 .. n-1). */
+int b200fe_stream_reset(b200fe_stream* st, const int* d_ids, int n, void* stream);
+/* Row i of the push feeds stream d_ids[i] (NULL: stream i) with d_chunk_len[i] samples (NULL: max_chunk for all) from
+ * d_chunks + i * chunk_stride (float32, device).  Output row i: d_out[i][max_out_frames][num_mel_bins], the d_out_frames[i]
+ * completed frames first, zero rows after them; optional global CMVN as in b200fe_fbank_fused.  Each stream may appear once
+ * per push. */
+int b200fe_stream_push(b200fe_stream* st, const int* d_ids, int n, const float* d_chunks, long long chunk_stride, const int* d_chunk_len,
+                       const float* d_cmvn_mean, const float* d_cmvn_istd, float* d_out, int max_out_frames, long long* d_out_frames, void* stream);
+/* Sticky error bits of the pushes so far (synchronises the given stream): 1 a chunk was longer than max_chunk and was
+ * clipped, 2 a push completed more frames than max_out_frames, 4 a stream id was out of range. */
+int b200fe_stream_flags(b200fe_stream* st, int* h_flags, void* stream);
+
 /* Host -> device staging of a zero-padded HOST batch (what batch_list builds, dataset.py:8-22) into the
  * packed device layout: only the valid samples of every utterance cross PCIe (one cudaMemcpyAsync per
  * utterance on `stream`; h_wav should be pinned).  h_offsets[u] = destination offset (elements). */
@@ -277,6 +306,7 @@ int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, c
  * row-class column sums.  cmvn_mode: 0 = statistics are already in the output domain,
  * 1 = subtract utterance mean, 2 = mean and variance (var floored at 1e-20). */
 typedef struct b200fe_post_args {
+    unsigned int struct_size;    /* = sizeof(b200fe_post_args) */
     float* d_feats;              /* [batch][max_frames][num_mel_bins], updated in place */
     const long long* d_nsamp;    /* [batch] (frame counts are derived exactly as in the fused launch) */
     int batch;
@@ -305,6 +335,7 @@ int b200fe_postpass(const b200fe_plan* plan, const b200fe_post_args* args, void*
  * Out of place: d_out gets the warped features (padded rows zero) and, optionally, their statistics in the
  * layout of b200fe_fbank_fused for the mean fills of the masks that follow. */
 typedef struct b200fe_warp_args {
+    unsigned int struct_size;    /* = sizeof(b200fe_warp_args) */
     const float* d_in;           /* [batch][max_frames][num_mel_bins] */
     float* d_out;                /* same shape, must not alias d_in */
     const long long* d_nsamp;    /* [batch] */

@@ -7,6 +7,6 @@ the repository root.  The hot path lives in ``csrc/`` (hand-written CUDA behind 
 """
 from . import _lib, build, cmvn, lasr_plugin, mask, specaug  # noqa: F401
 from .frontend import FbankPlan, GpuFbankFrontend  # noqa: F401
-from .streaming import StreamingFbank  # noqa: F401
+from .streaming import IndependentStreams, StreamingFbank  # noqa: F401
 
-__all__ = ["GpuFbankFrontend", "FbankPlan", "StreamingFbank", "specaug", "cmvn", "mask", "build"]
+__all__ = ["GpuFbankFrontend", "FbankPlan", "StreamingFbank", "IndependentStreams", "specaug", "cmvn", "mask", "build"]

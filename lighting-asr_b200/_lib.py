@@ -18,9 +18,17 @@ class Opts(C.Structure):
     ]
 
 
-class FbankArgs(C.Structure):
+class _Sized(C.Structure):
+    """Argument structs open with ``struct_size`` (= sizeof of the header's declaration): the library rejects a stale binding."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.struct_size = C.sizeof(self)
+
+
+class FbankArgs(_Sized):
     _fields_ = [
-        ("d_wav", C.c_void_p), ("wav_stride", c_ll), ("d_nsamp", C.c_void_p), ("batch", C.c_int),
+        ("struct_size", C.c_uint), ("d_wav", C.c_void_p), ("wav_stride", c_ll), ("d_nsamp", C.c_void_p), ("batch", C.c_int),
         ("d_peak", C.c_void_p), ("d_out", C.c_void_p), ("d_out_len", C.c_void_p), ("max_frames", C.c_int),
         ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p), ("cmvn_stride", c_ll),
         ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("mask_zero", C.c_int),
@@ -33,9 +41,9 @@ class FbankArgs(C.Structure):
     ]
 
 
-class PostArgs(C.Structure):
+class PostArgs(_Sized):
     _fields_ = [
-        ("d_feats", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
+        ("struct_size", C.c_uint), ("d_feats", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
         ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p), ("n_row_classes", C.c_int),
         ("cmvn_mode", C.c_int), ("d_cmvn_mean", C.c_void_p), ("d_cmvn_istd", C.c_void_p),
         ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("d_fills", C.c_void_p),
@@ -43,9 +51,9 @@ class PostArgs(C.Structure):
     ]
 
 
-class WarpArgs(C.Structure):
+class WarpArgs(_Sized):
     _fields_ = [
-        ("d_in", C.c_void_p), ("d_out", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
+        ("struct_size", C.c_uint), ("d_in", C.c_void_p), ("d_out", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
         ("d_warp", C.c_void_p), ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p),
         ("n_row_classes", C.c_int),
     ]
@@ -55,6 +63,7 @@ EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table", "b200fe_build_tile_table_padded", "b200fe_tile_table_capacity", "b200fe_build_tile_table_device", "b200fe_build_work_list_device",
     "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_specaug_plan", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
+    "b200fe_stream_create", "b200fe_stream_destroy", "b200fe_stream_max_frames", "b200fe_stream_reset", "b200fe_stream_push", "b200fe_stream_flags",
     "b200fe_host_pool_create", "b200fe_host_pool_destroy", "b200fe_host_pool_threads", "b200fe_host_pack_begin", "b200fe_host_zero_rows_begin", "b200fe_host_zero_ranges_begin", "b200fe_host_wait",
 ]
 
@@ -129,6 +138,18 @@ def load(build_if_missing=True):
     lib.b200fe_time_warp.restype = C.c_int
     lib.b200fe_cmvn_from_stats.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, c_fp, c_fp]
     lib.b200fe_cmvn_from_stats.restype = C.c_int
+    lib.b200fe_stream_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.b200fe_stream_create.restype = C.c_int
+    lib.b200fe_stream_destroy.argtypes = [C.c_void_p]
+    lib.b200fe_stream_destroy.restype = None
+    lib.b200fe_stream_max_frames.argtypes = [C.c_void_p]
+    lib.b200fe_stream_max_frames.restype = C.c_int
+    lib.b200fe_stream_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200fe_stream_reset.restype = C.c_int
+    lib.b200fe_stream_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_ll, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.b200fe_stream_push.restype = C.c_int
+    lib.b200fe_stream_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    lib.b200fe_stream_flags.restype = C.c_int
     lib.b200fe_host_pool_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.b200fe_host_pool_create.restype = C.c_int
     lib.b200fe_host_pool_destroy.argtypes = [C.c_void_p]

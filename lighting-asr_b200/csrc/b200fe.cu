@@ -15,6 +15,7 @@
 
 #include "host_pool.h"
 #include "aux_kernels.cuh"
+#include "stream_kernels.cuh"
 #include "fbank_kernel.cuh"
 #include "fbank_instances.h"
 #ifdef B200FE_WITH_WS          // the warp-specialised experiment (measured 30 % slower) is not part of the default build
@@ -761,6 +762,8 @@ extern "C" int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long
 extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args* g, void* stream)
 {
     if (!p || !g) return fail(B200FE_EINVAL, "fbank_fused: null argument");
+    if (g->struct_size != sizeof(b200fe_fbank_args))
+        return fail(B200FE_EINVAL, "fbank_fused: struct_size %u != sizeof(b200fe_fbank_args) %zu (stale binding of include/b200fe.h?)", g->struct_size, sizeof(b200fe_fbank_args));
     if (!g->d_wav || !g->d_nsamp || g->batch <= 0 || g->wav_stride <= 0) return fail(B200FE_EINVAL, "fbank_fused: bad waveform arguments");
     if (!g->d_out && !g->d_stats) return fail(B200FE_EINVAL, "fbank_fused: neither an output nor a statistics buffer");
     if (g->batch > 65535) return fail(B200FE_EINVAL, "fbank_fused: at most 65535 utterances per call (split the batch)");
@@ -867,9 +870,99 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     return B200FE_OK;
 }
 
+// ---- streaming front end: per-stream carry on the device, push = append -> fused launch on the state rows -> advance ----
+struct b200fe_stream {
+    const b200fe_plan* plan;
+    int n_streams, max_chunk, cap, device;
+    float* d_state = nullptr;        // [n_streams][cap]
+    int* d_fill = nullptr;           // [n_streams] samples held per stream
+    long long* d_offsets = nullptr;  // [n_streams] scratch of a push: row offsets / sample counts handed to the fused launch
+    long long* d_nsamp = nullptr;
+    int* d_flags = nullptr;
+};
+
+extern "C" int b200fe_stream_create(const b200fe_plan* plan, int n_streams, int max_chunk, b200fe_stream** out)
+{
+    if (!plan || !out || n_streams <= 0 || n_streams > 65535 || max_chunk <= 0 || max_chunk > (1 << 20))
+        return fail(B200FE_EINVAL, "stream_create: bad argument (1..65535 streams, 1..2^20 samples per push)");
+    b200fe_stream* st = new b200fe_stream();
+    st->plan = plan; st->n_streams = n_streams; st->max_chunk = max_chunk;
+    st->cap = (plan->win - 1 + max_chunk + 7) & ~7;            // 16-byte aligned rows (TMA loader), also for int16-sized offsets
+    cudaError_t e = cudaGetDevice(&st->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_state, sizeof(float) * (size_t)n_streams * st->cap + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_fill, sizeof(int) * n_streams);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_offsets, sizeof(long long) * n_streams);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_nsamp, sizeof(long long) * n_streams);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_flags, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(st->d_state, 0, sizeof(float) * (size_t)n_streams * st->cap + 64);
+    if (e == cudaSuccess) e = cudaMemset(st->d_fill, 0, sizeof(int) * n_streams);
+    if (e == cudaSuccess) e = cudaMemset(st->d_flags, 0, sizeof(int));
+    if (e != cudaSuccess) { b200fe_stream_destroy(st); return fail(B200FE_ECUDA, "stream_create: %s", cudaGetErrorString(e)); }
+    *out = st;
+    return B200FE_OK;
+}
+
+extern "C" void b200fe_stream_destroy(b200fe_stream* st)
+{
+    if (!st) return;
+    cudaFree(st->d_state); cudaFree(st->d_fill); cudaFree(st->d_offsets); cudaFree(st->d_nsamp); cudaFree(st->d_flags);
+    delete st;
+}
+
+extern "C" int b200fe_stream_max_frames(const b200fe_stream* st)
+{
+    if (!st) return fail(B200FE_EINVAL, "stream_max_frames: null handle");
+    const int n = st->plan->win - 1 + st->max_chunk;
+    return n >= st->plan->win ? 1 + (n - st->plan->win) / st->plan->shift : 0;
+}
+
+extern "C" int b200fe_stream_reset(b200fe_stream* st, const int* d_ids, int n, void* stream)
+{
+    if (!st || n < 0 || n > st->n_streams) return fail(B200FE_EINVAL, "stream_reset: bad argument");
+    if (n == 0) return B200FE_OK;
+    stream_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st->d_fill, st->n_streams, d_ids, n);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_stream_push(b200fe_stream* st, const int* d_ids, int n, const float* d_chunks, long long chunk_stride, const int* d_chunk_len,
+                                  const float* d_cmvn_mean, const float* d_cmvn_istd, float* d_out, int max_out_frames, long long* d_out_frames, void* stream)
+{
+    if (!st || n <= 0 || n > st->n_streams || !d_chunks || !d_out || max_out_frames <= 0 || chunk_stride < 0)
+        return fail(B200FE_EINVAL, "stream_push: bad argument");
+    if ((d_cmvn_mean == nullptr) != (d_cmvn_istd == nullptr)) return fail(B200FE_EINVAL, "stream_push: cmvn mean and istd go together");
+    const b200fe_plan* p = st->plan;
+    cudaStream_t cs = (cudaStream_t)stream;
+    stream_append_kernel<<<n, 256, 0, cs>>>(st->d_state, st->d_fill, st->cap, st->n_streams, d_ids, d_chunks, chunk_stride, d_chunk_len, st->max_chunk,
+                                            p->win, p->shift, max_out_frames, st->d_offsets, st->d_nsamp, d_out_frames, st->d_flags);
+    CUDA_TRY(cudaGetLastError());
+    b200fe_fbank_args a;
+    memset(&a, 0, sizeof a);
+    a.struct_size = sizeof a;
+    a.d_wav = st->d_state; a.wav_stride = st->cap; a.d_wav_offsets = st->d_offsets; a.offsets_aligned = 1;
+    a.d_nsamp = st->d_nsamp; a.batch = n; a.d_out = d_out; a.max_frames = max_out_frames;
+    a.d_cmvn_mean = d_cmvn_mean; a.d_cmvn_istd = d_cmvn_istd; a.cmvn_stride = 0;
+    const int rc = b200fe_fbank_fused(p, &a, stream);
+    if (rc != B200FE_OK) return rc;
+    stream_advance_kernel<<<n, 128, 0, cs>>>(st->d_state, st->d_fill, st->cap, st->n_streams, d_ids, st->d_nsamp, p->win, p->shift);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_stream_flags(b200fe_stream* st, int* h_flags, void* stream)
+{
+    if (!st || !h_flags) return fail(B200FE_EINVAL, "stream_flags: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(h_flags, st->d_flags, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, void* stream)
 {
-    if (!p || !g || !g->d_feats || !g->d_nsamp || g->batch <= 0 || g->max_frames <= 0) return fail(B200FE_EINVAL, "postpass: bad argument");
+    if (!p || !g) return fail(B200FE_EINVAL, "postpass: null argument");
+    if (g->struct_size != sizeof(b200fe_post_args))
+        return fail(B200FE_EINVAL, "postpass: struct_size %u != sizeof(b200fe_post_args) %zu (stale binding of include/b200fe.h?)", g->struct_size, sizeof(b200fe_post_args));
+    if (!g->d_feats || !g->d_nsamp || g->batch <= 0 || g->max_frames <= 0) return fail(B200FE_EINVAL, "postpass: bad argument");
     const int nm = g->n_freq_masks + g->n_time_masks;
     const bool masks = g->d_masks != nullptr && nm > 0;
     if (!masks && g->cmvn_mode == 0) return B200FE_OK;
@@ -914,7 +1007,10 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
 
 extern "C" int b200fe_time_warp(const b200fe_plan* p, const b200fe_warp_args* g, void* stream)
 {
-    if (!p || !g || !g->d_in || !g->d_out || !g->d_nsamp || !g->d_warp || g->batch <= 0 || g->max_frames <= 0)
+    if (!p || !g) return fail(B200FE_EINVAL, "time_warp: null argument");
+    if (g->struct_size != sizeof(b200fe_warp_args))
+        return fail(B200FE_EINVAL, "time_warp: struct_size %u != sizeof(b200fe_warp_args) %zu (stale binding of include/b200fe.h?)", g->struct_size, sizeof(b200fe_warp_args));
+    if (!g->d_in || !g->d_out || !g->d_nsamp || !g->d_warp || g->batch <= 0 || g->max_frames <= 0)
         return fail(B200FE_EINVAL, "time_warp: bad argument");
     if (g->d_in == g->d_out) return fail(B200FE_EINVAL, "time_warp: in-place operation is not possible");
     WarpArgs a;

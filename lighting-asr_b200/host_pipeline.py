@@ -102,6 +102,12 @@ class HostPipeline:
         self._turn = 0
         self._streams = None
         self.h2d_bytes = self.d2h_bytes = 0
+        self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
+
+    def _stamp(self, label):
+        if self.trace is not None:
+            import time
+            self.trace.append((label, time.perf_counter()))
 
     def __del__(self):
         try:
@@ -119,6 +125,7 @@ class HostPipeline:
         B = len(wavs)
         if B == 0:
             raise ValueError("empty batch")
+        self._stamp("submit")
         arrs = [np.asarray(w) for w in wavs]
         dt = arrs[0].dtype
         if dt not in _SRC_CODE or any(a.dtype != dt for a in arrs):
@@ -209,8 +216,10 @@ class HostPipeline:
         if self._out_done[so] is not None:
             main.wait_event(self._out_done[so])        # D2H of the call that last used this device feature slot
         self.h2d_bytes = self.d2h_bytes = 0
+        self._stamp("prepared")
         for (b0, b1), tk in zip(zip(bounds[:-1], bounds[1:]), tickets):
             _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")
+            self._stamp("packed")
             o0 = int(offs[b0])
             o1 = int(offs[b1]) if b1 < B else total
             with torch.cuda.stream(s_in):
@@ -229,6 +238,7 @@ class HostPipeline:
                                                   int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
                 fe.launch_count += 1
                 self.d2h_bytes += int(T_host[b0:b1].sum()) * D * 4
+            self._stamp("issued")
         self._in_free[si] = torch.cuda.Event()
         self._in_free[si].record(s_in)
         self._comp_done[si] = torch.cuda.Event()
@@ -248,11 +258,14 @@ class HostPipeline:
         """Blocks until the batch of ``submit`` is complete on the host (``to_host``) and returns (feats, feat_len)."""
         if not h["to_host"]:
             return h["dfeats"], h["dlen"]
+        self._stamp("result")
         h["done"].synchronize()
+        self._stamp("device done")
         if h["zero"]:
             _lib.check(self.lib.b200fe_host_wait(self.pool, h["zero"]), "b200fe_host_wait")
             h["zero"] = None
         h["keep"] = None
+        self._stamp("returned")
         return h["hfeats"], h["hlen"]
 
     def run(self, wavs, to_host=True):

@@ -113,3 +113,131 @@ class StreamingFbank:
         self.start += T * self.shift
         self.frames_out += T
         return feats
+
+
+class IndependentStreams:
+    """S independent streams behind the C ABI's ``b200fe_stream_*`` handle (include/b200fe.h): every stream keeps its own carry on
+    the device, a push may feed any subset of the streams with chunks of different lengths (a decode server's requests arrive
+    asynchronously, lasr/process/asrprocess.py:49-74 serves one utterance per call).
+
+    ``push(ids, chunks)``: host-side convenience -- the chunks (list of 1-D float arrays) go through one pinned staging buffer
+    and one H2D copy, the push itself is a CUDA graph of three kernels replayed per call (``graph=True``), the completed frames
+    come back as a list of (T_i, D) CUDA tensors (views of the handle's output buffer, valid until the next push).
+    ``push_device(...)`` is the raw device-pointer call."""
+
+    def __init__(self, n_streams, device="cuda:0", max_chunk=4096, graph=True, **frontend_kwargs):
+        for k in ("specaug", "peak_norm"):
+            if frontend_kwargs.get(k):
+                raise ValueError("%s needs the whole utterance and is not available in streaming mode" % k)
+        if frontend_kwargs.get("cmvn", "none") not in ("none", "global"):
+            raise ValueError("utterance CMVN needs the whole utterance; use cmvn='global' when streaming")
+        if frontend_kwargs.get("dither", 0.0) != 0.0:
+            raise ValueError("dither is not available through the stream handle")
+        self.fe = GpuFbankFrontend(**frontend_kwargs)
+        self.device = torch.device(device)
+        self.S, self.max_chunk = int(n_streams), int(max_chunk)
+        self._plan = self.fe.plan(self.device)
+        self.lib = self._plan.lib
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200fe_stream_create(self._plan.handle, self.S, self.max_chunk, C.byref(h)), "b200fe_stream_create")
+        self.handle = h
+        self.max_frames = self.lib.b200fe_stream_max_frames(h)
+        D = self.fe.num_mel_bins
+        self.D = D
+        dev = self.device
+        # static buffers: a graph replays fixed pointers; row i of a push <-> entry i of these
+        self.d_ids = torch.zeros((self.S,), dtype=torch.int32, device=dev)
+        self.d_len = torch.zeros((self.S,), dtype=torch.int32, device=dev)
+        self.d_chunks = torch.zeros((self.S, self.max_chunk), dtype=torch.float32, device=dev)
+        self.d_out = torch.zeros((self.S, max(self.max_frames, 1), D), dtype=torch.float32, device=dev)
+        self.d_frames = torch.zeros((self.S,), dtype=torch.int64, device=dev)
+        self.h_meta = torch.zeros((2, self.S), dtype=torch.int32, pin_memory=True)          # ids | lengths
+        self.h_chunks = torch.zeros((self.S, self.max_chunk), dtype=torch.float32, pin_memory=True)
+        self.h_frames = torch.zeros((self.S,), dtype=torch.int64, pin_memory=True)
+        self.d_meta = torch.zeros((2, self.S), dtype=torch.int32, device=dev)
+        self.use_graph = bool(graph)
+        self._graphs = {}
+        if self.fe.cmvn == "global":
+            self.fe.cmvn_mean = self.fe.cmvn_mean.to(dev)
+            self.fe.cmvn_istd = self.fe.cmvn_istd.to(dev)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.b200fe_stream_destroy(self.handle)
+                self.handle = None
+        except Exception:  # noqa: BLE001
+            pass
+
+    def push_device(self, n, d_ids, d_chunks, chunk_stride, d_len, d_out, max_out_frames, d_frames, stream=None):
+        cm = self.fe.cmvn_mean.data_ptr() if self.fe.cmvn == "global" else 0
+        ci = self.fe.cmvn_istd.data_ptr() if self.fe.cmvn == "global" else 0
+        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.b200fe_stream_push(self.handle, C.c_void_p(d_ids), int(n), C.c_void_p(d_chunks), int(chunk_stride), C.c_void_p(d_len),
+                                               C.c_void_p(cm), C.c_void_p(ci), C.c_void_p(d_out), int(max_out_frames), C.c_void_p(d_frames), C.c_void_p(st)),
+                   "b200fe_stream_push")
+        self.fe.launch_count += 3
+
+    def _launch(self, n):
+        """The push over rows 0 .. n-1 of the static buffers: a captured graph per n (replay), or three direct launches."""
+        args = (n, self.d_meta[0].data_ptr(), self.d_chunks.data_ptr(), self.max_chunk, self.d_meta[1].data_ptr(), self.d_out.data_ptr(),
+                self.d_out.shape[1], self.d_frames.data_ptr())
+        if not self.use_graph:
+            self.push_device(*args)
+            return
+        g = self._graphs.get(n)
+        if g is None:
+            # warm up outside the capture (module loading, attribute set-up), then capture the three launches
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self.push_device(*args, stream=side.cuda_stream)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[n] = g
+        g.replay()
+        self.fe.launch_count += 3
+
+    @torch.no_grad()
+    def push(self, ids, chunks, sync=True):
+        """ids: stream indices (each at most once); chunks: list of 1-D float arrays (len <= max_chunk, may be empty).
+        Returns a list of (T_i, D) CUDA tensors, one per id."""
+        n = len(ids)
+        if n == 0:
+            return []
+        if n > self.S or len(chunks) != n or len(set(int(i) for i in ids)) != n:
+            raise ValueError("one chunk per listed stream, each stream at most once per push")
+        meta = self.h_meta.numpy()
+        hc = self.h_chunks.numpy()
+        for i, (sid, c) in enumerate(zip(ids, chunks)):
+            c = np.asarray(c, dtype=np.float32).reshape(-1)
+            if not 0 <= int(sid) < self.S:
+                raise ValueError("stream id out of range")
+            if c.shape[0] > self.max_chunk:
+                raise ValueError("chunk larger than max_chunk")
+            meta[0, i], meta[1, i] = int(sid), c.shape[0]
+            hc[i, : c.shape[0]] = c
+        self.d_meta[:, :n].copy_(self.h_meta[:, :n], non_blocking=True)
+        self.d_chunks[:n].copy_(self.h_chunks[:n], non_blocking=True)
+        self._launch(n)
+        self.h_frames[:n].copy_(self.d_frames[:n], non_blocking=True)
+        if not sync:
+            return None
+        torch.cuda.current_stream(self.device).synchronize()
+        T = self.h_frames[:n].tolist()
+        return [self.d_out[i, : int(t)] for i, t in enumerate(T)]
+
+    def reset(self, ids=None):
+        if ids is None:
+            _lib.check(self.lib.b200fe_stream_reset(self.handle, C.c_void_p(0), self.S, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "b200fe_stream_reset")
+            return
+        t = torch.as_tensor(list(ids), dtype=torch.int32).to(self.device)
+        _lib.check(self.lib.b200fe_stream_reset(self.handle, C.c_void_p(t.data_ptr()), int(t.numel()), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "b200fe_stream_reset")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def flags(self):
+        f = C.c_int(0)
+        _lib.check(self.lib.b200fe_stream_flags(self.handle, C.byref(f), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "b200fe_stream_flags")
+        return f.value

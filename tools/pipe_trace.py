@@ -1,0 +1,24 @@
+"""Where a B200Collate call spends its wall time (host stamps of HostPipeline): float64 and int16 C2 lists."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import lasr_b200
+from bench import make_list
+
+lists = [make_list(s)[0] for s in (1, 101)]
+col = lasr_b200.lasr_plugin.B200Collate("cuda:0", to_host=True, cmvn="utt_meanvar")
+for kind in ("float64", "int16", "int16 to_host=False"):
+    ls = lists if kind == "float64" else [[np.round(w * 32767).astype(np.int16) for w in l] for l in lists]
+    col.to_host = "False" not in kind
+    for i in range(4):
+        col(ls[i % 2])
+    col.pipeline.trace = []
+    col(ls[0]); col(ls[1])
+    tr = col.pipeline.trace
+    col.pipeline.trace = None
+    t0 = tr[0][1]
+    print("==", kind)
+    prev = t0
+    for lab, t in tr:
+        print("  %-12s %8.3f ms  (+%.3f)" % (lab, (t - t0) * 1e3, (t - prev) * 1e3))
+        prev = t
