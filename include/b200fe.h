@@ -300,6 +300,15 @@ int b200fe_src_mask(const b200fe_plan* plan, const long long* d_len, int len_is_
 int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
                        const long long* d_nbytes, int batch, long long max_bytes, void* stream);
 
+/* bfloat16 feature emission: the encoder's first layer (Conv2dSubsampling,
+ * R/lasr/modules/net/transformer/subsampling.py:53-57) runs in bfloat16 under autocast.  b200fe_cast_bf16 converts n float32
+ * values (round to nearest even, = tensor.to(torch.bfloat16)); b200fe_copy_ragged_bf16 is b200fe_copy_ragged with the
+ * conversion folded in (d_nbytes = bytes of float32 per row, multiples of 16; destination rows hold half as many bytes), so
+ * features that go to the host cross PCIe as bfloat16 with no extra pass. */
+int b200fe_cast_bf16(const float* d_in, void* d_out, long long n, void* stream);
+int b200fe_copy_ragged_bf16(const float* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
+                            const long long* d_nbytes, int batch, long long max_bytes, void* stream);
+
 /* Turns per-utterance statistics into (a) utterance CMVN vectors and (b) the SpecAugment mean
  * fills of R/lasr/utils/specaugment.py:71-74,102-105 (each mask is filled with the mean of the
  * CURRENT array, i.e. after CMVN and after all earlier masks), evaluated in closed form from the

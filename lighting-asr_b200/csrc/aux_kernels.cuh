@@ -1,6 +1,7 @@
 // Auxiliary kernels: peak abs-max, statistics finalisation (utterance CMVN vectors and
 // SpecAugment mean fills) and the in-place post pass (CMVN apply + mask fill).
 #pragma once
+#include <cuda_bf16.h>
 #include "b200fe_common.cuh"
 #include "fbank_kernel.cuh"
 
@@ -104,6 +105,58 @@ __global__ void __launch_bounds__(kCopyThreads) ragged_copy_kernel(const char* _
                 *reinterpret_cast<unsigned*>(d + off) = *reinterpret_cast<const unsigned*>(s + off);
         } else {
             for (long long off = c0 + threadIdx.x; off < lim; off += kCopyThreads) d[off] = s[off];
+        }
+    }
+}
+
+// ---- bfloat16 feature emission (the consumer's precision) --------------------------------------------
+// The encoder's first layer (Conv2dSubsampling, R/lasr/modules/net/transformer/subsampling.py:53-57) runs in bfloat16 under
+// autocast; handing it bfloat16 features halves the bytes of the hand-off (and of the D2H copy when features go to the host).
+// Round to nearest even, the same rounding `tensor.to(torch.bfloat16)` applies.
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v)
+{
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const unsigned*>(&lo);
+    r.y = *reinterpret_cast<const unsigned*>(&hi);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n)
+{
+    const long long n4 = n >> 2;
+    const float4* i4 = reinterpret_cast<const float4*>(in);
+    uint2* o4 = reinterpret_cast<uint2*>(out);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) o4[i] = pack_bf16x4(__ldcs(i4 + i));
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// Ragged row copy float32 -> bfloat16: row u = nbytes[u] bytes of float32 from src + src_off[u] to bfloat16 at dst + dst_off[u]
+// (byte offsets, 16-byte aligned rows, nbytes a multiple of 16).  The destination may be pinned host memory: the D2H copy of
+// the features and their conversion are one pass, and only half the bytes cross PCIe.
+__global__ void __launch_bounds__(kCopyThreads) ragged_cast_bf16_kernel(const char* __restrict__ src, const long long* __restrict__ src_off,
+                                                                        char* __restrict__ dst, const long long* __restrict__ dst_off,
+                                                                        const long long* __restrict__ nbytes, int B, int chunks_per_row)
+{
+    const long long total = (long long)B * chunks_per_row;
+    for (long long v = blockIdx.x; v < total; v += gridDim.x) {
+        const int u = (int)(v / chunks_per_row);
+        const long long c0 = (v - (long long)u * chunks_per_row) * kCopyChunk;
+        const long long nb = nbytes[u];
+        if (c0 >= nb) continue;
+        const char* s = src + src_off[u];
+        char* d = dst + dst_off[u];
+        const long long lim = min(nb, c0 + (long long)kCopyChunk);
+        float4 vreg[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const long long off = c0 + ((long long)r * kCopyThreads + threadIdx.x) * 16;
+            if (off + 16 <= lim) vreg[r] = __ldcs(reinterpret_cast<const float4*>(s + off));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const long long off = c0 + ((long long)r * kCopyThreads + threadIdx.x) * 16;
+            if (off + 16 <= lim) __stcs(reinterpret_cast<uint2*>(d + (off >> 1)), pack_bf16x4(vreg[r]));
         }
     }
 }

@@ -745,6 +745,31 @@ extern "C" int b200fe_copy_ragged(const void* src, const long long* d_src_off, v
     return B200FE_OK;
 }
 
+extern "C" int b200fe_cast_bf16(const float* d_in, void* d_out, long long n, void* stream)
+{
+    if (!d_in || !d_out || n < 0) return fail(B200FE_EINVAL, "cast_bf16: bad argument");
+    if (((reinterpret_cast<uintptr_t>(d_in) & 15) | (reinterpret_cast<uintptr_t>(d_out) & 7)) != 0) return fail(B200FE_EINVAL, "cast_bf16: buffers must be 16 / 8-byte aligned");
+    if (n == 0) return B200FE_OK;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148 * 16));
+    cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, static_cast<__nv_bfloat16*>(d_out), n);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_copy_ragged_bf16(const float* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
+                                       const long long* d_nbytes, int batch, long long max_bytes, void* stream)
+{
+    if (!src || !dst || !d_src_off || !d_dst_off || !d_nbytes || batch < 0 || max_bytes < 0) return fail(B200FE_EINVAL, "copy_ragged_bf16: bad argument");
+    if (batch == 0 || max_bytes == 0) return B200FE_OK;
+    const long long cpr = (max_bytes + kCopyChunk - 1) / kCopyChunk;
+    if (cpr > 0x7fffffffLL) return fail(B200FE_EINVAL, "copy_ragged_bf16: row too long");
+    const int grid = (int)std::max<long long>(1, std::min<long long>(cpr * batch, 16LL));
+    ragged_cast_bf16_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const char*>(src), d_src_off, static_cast<char*>(dst), d_dst_off,
+                                                                             d_nbytes, batch, (int)cpr);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 extern "C" int b200fe_d2h_ragged(const float* d_feats, long long row_elems, long long utt_rows, const long long* h_rows, int batch,
                                  float* h_feats, void* stream)
 {

@@ -287,11 +287,27 @@ class GpuFbankFrontend(torch.nn.Module):
     # -- the hot path ------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, wav, wav_len, max_frames=None, masks=None, out=None, out_len=None, wav_offsets=None, dither_noise=None,
-                uniform_frames=False, packed_out=False):
+                uniform_frames=False, packed_out=False, out_dtype=None):
         """``wav_offsets`` (int64 host array, multiples of 4) switches to the packed layout: ``wav`` is then
-        a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``."""
+        a 1-D CUDA tensor and utterance b occupies ``wav[wav_offsets[b] : wav_offsets[b] + wav_len[b]]``.
+        ``out_dtype=torch.bfloat16`` returns the features in the precision the encoder's first convolution runs
+        in under autocast (subsampling.py:53-57): computed in float32 as always, rounded once (nearest even) by one extra pass."""
         if not wav.is_cuda:
             raise RuntimeError("GpuFbankFrontend has no CPU path: wav must be a CUDA tensor")
+        if out_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+        if out_dtype == torch.bfloat16:
+            if out is not None and (out.dtype != torch.bfloat16 or not out.is_contiguous()):
+                raise ValueError("out must be a contiguous bfloat16 tensor when out_dtype is bfloat16")
+            f32, flen = self.forward(wav, wav_len, max_frames=max_frames, masks=masks, out_len=out_len, wav_offsets=wav_offsets,
+                                     dither_noise=dither_noise, uniform_frames=uniform_frames, packed_out=packed_out)
+            dst = out if out is not None else torch.empty(f32.shape, dtype=torch.bfloat16, device=f32.device)
+            if tuple(dst.shape) != tuple(f32.shape):
+                raise ValueError("out must have shape %s" % (tuple(f32.shape),))
+            _lib.check(_lib.load().b200fe_cast_bf16(_ptr(f32), _ptr(dst), f32.numel(), C.c_void_p(torch.cuda.current_stream(f32.device).cuda_stream)),
+                       "b200fe_cast_bf16")
+            self.launch_count += 1
+            return dst, flen
         if self.time_warp:
             if packed_out:
                 raise ValueError("packed_out is not available together with time_warp")

@@ -81,7 +81,10 @@ class _Grow:
 
 
 class HostPipeline:
-    def __init__(self, frontend, device="cuda:0", ring=3, threads=None, group_bytes=32 << 20):
+    def __init__(self, frontend, device="cuda:0", ring=3, threads=None, group_bytes=32 << 20, out_dtype=torch.float32):
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+        self.out_dtype = out_dtype          # bfloat16: converted inside the D2H copy kernel, half the D2H bytes
         self.fe = frontend
         self.dev = torch.device(device)
         self.lib = _lib.load()
@@ -94,6 +97,7 @@ class HostPipeline:
         self._in = {}          # dst dtype -> [(_Grow pinned, _Grow device)] * 2
         self._hout = [_Grow(torch.uint8, zero=True) for _ in range(self.ring)]
         self._dout = [_Grow(torch.uint8, self.dev) for _ in range(self.ring)]
+        self._dout16 = [_Grow(torch.uint8, self.dev) for _ in range(self.ring)]
         self._hlen = [torch.empty((0,), dtype=torch.int64)] * self.ring
         self._dlen = [None] * self.ring
         self._in_free = [None, None]        # H2D of the call that last used the pinned / device input slot has completed
@@ -102,6 +106,7 @@ class HostPipeline:
         self._turn = 0
         self._streams = None
         self.h2d_bytes = self.d2h_bytes = 0
+        self.d2h_mode = "kernel"            # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
     def _stamp(self, label):
@@ -169,16 +174,27 @@ class HostPipeline:
                 acc = 0
         if bounds[-1] != B:
             bounds.append(B)
+        ptrs = (C.c_void_p * B)(*[a.__array_interface__["data"][0] for a in arrs])     # (ndarray.ctypes.data costs ~1.5 us per array)
+        tickets = []
+        for b0, b1 in zip(bounds[:-1], bounds[1:]):
+            tk = lib.b200fe_host_pack_begin(self.pool, C.c_void_p(C.addressof(ptrs) + 8 * b0), C.c_void_p(lens.ctypes.data + 8 * b0), b1 - b0, code,
+                                            C.c_void_p(hin.data_ptr()), C.c_void_p(offs.ctypes.data + 8 * b0), hin.numel())
+            if tk <= 0:
+                _lib.check(int(tk), "b200fe_host_pack_begin")
+            tickets.append(tk)
         # ---- host output slot: only what an earlier batch left in this batch's padding rows has to be cleared ----
         obytes = B * Tmax * D * 4
+        bf16 = self.out_dtype == torch.bfloat16
+        osz = 2 if bf16 else 4
+        hbytes = B * Tmax * D * osz
         zero_ticket = None
         hfeats = hlen = None
         if to_host:
-            hbuf = self._hout[so].get(obytes)
-            hfeats = hbuf[:obytes].view(torch.float32).view(B, Tmax, D)
-            row0 = np.arange(B, dtype=np.int64) * (Tmax * D * 4)
-            valid = [(int(a), int(a + t * D * 4)) for a, t in zip(row0, T_host) if t > 0]
-            zr, self._hout[so].dirty = stale_ranges(self._hout[so].dirty, valid, obytes)
+            hbuf = self._hout[so].get(hbytes)
+            hfeats = hbuf[:hbytes].view(self.out_dtype).view(B, Tmax, D)
+            row0 = np.arange(B, dtype=np.int64) * (Tmax * D * osz)
+            valid = [(int(a), int(a + t * D * osz)) for a, t in zip(row0, T_host) if t > 0]
+            zr, self._hout[so].dirty = stale_ranges(self._hout[so].dirty, valid, hbytes)
             if zr:
                 zo = np.array([r[0] for r in zr], dtype=np.int64)
                 zn = np.array([r[1] - r[0] for r in zr], dtype=np.int64)
@@ -188,14 +204,6 @@ class HostPipeline:
                 self.zero_bytes = int(zn.sum())
             else:
                 self.zero_bytes = 0
-        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
-        tickets = []
-        for b0, b1 in zip(bounds[:-1], bounds[1:]):
-            tk = lib.b200fe_host_pack_begin(self.pool, C.c_void_p(C.addressof(ptrs) + 8 * b0), C.c_void_p(lens.ctypes.data + 8 * b0), b1 - b0, code,
-                                            C.c_void_p(hin.data_ptr()), C.c_void_p(offs.ctypes.data + 8 * b0), hin.numel())
-            if tk <= 0:
-                _lib.check(int(tk), "b200fe_host_pack_begin")
-            tickets.append(tk)
         # ---- device output slot ----
         dfeats = self._dout[so].get(obytes)[:obytes].view(torch.float32).view(B, Tmax, D)
         if self._dlen[so] is None or self._dlen[so].numel() < B:
@@ -206,7 +214,8 @@ class HostPipeline:
                 self._hlen[so] = torch.empty((max(B, 256),), dtype=torch.int64, pin_memory=True)
             hlen = self._hlen[so][:B]
             # device-readable (offset, bytes) of every utterance's valid rows, same offsets on both sides (padded layout)
-            tab = np.stack([np.arange(B, dtype=np.int64) * (Tmax * D * 4), T_host.astype(np.int64) * (D * 4)])
+            tab = np.stack([np.arange(B, dtype=np.int64) * (Tmax * D * 4), T_host.astype(np.int64) * (D * 4),
+                            np.arange(B, dtype=np.int64) * (Tmax * D * osz)])          # source row offsets | float32 bytes per row block | host row offsets
             tab_dev = torch.from_numpy(tab).to(dev, non_blocking=True)
             ev_tab = torch.cuda.Event()
             ev_tab.record(main)
@@ -233,17 +242,31 @@ class HostPipeline:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
                 s_out.wait_event(ev_c)
-                _lib.check(lib.b200fe_copy_ragged(C.c_void_p(dfeats.data_ptr()), C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(hfeats.data_ptr()),
-                                                  C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(tab_dev.data_ptr() + 8 * (B + b0)), b1 - b0,
-                                                  int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
+                if self.d2h_mode == "dma" and not bf16:
+                    rows = np.ascontiguousarray(T_host[b0:b1].astype(np.int64))
+                    _lib.check(lib.b200fe_d2h_ragged(C.c_void_p(dfeats.data_ptr() + b0 * Tmax * D * 4), D, Tmax, C.c_void_p(rows.ctypes.data), b1 - b0,
+                                                     C.c_void_p(hfeats.data_ptr() + b0 * Tmax * D * 4), C.c_void_p(s_out.cuda_stream)), "b200fe_d2h_ragged")
+                    self.d2h_bytes += int(T_host[b0:b1].sum()) * D * osz
+                    self._stamp("issued")
+                    continue
+                copy = lib.b200fe_copy_ragged_bf16 if bf16 else lib.b200fe_copy_ragged
+                _lib.check(copy(C.c_void_p(dfeats.data_ptr()), C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(hfeats.data_ptr()),
+                                C.c_void_p(tab_dev.data_ptr() + 8 * (2 * B + b0)), C.c_void_p(tab_dev.data_ptr() + 8 * (B + b0)), b1 - b0,
+                                int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
                 fe.launch_count += 1
-                self.d2h_bytes += int(T_host[b0:b1].sum()) * D * 4
+                self.d2h_bytes += int(T_host[b0:b1].sum()) * D * osz
             self._stamp("issued")
         self._in_free[si] = torch.cuda.Event()
         self._in_free[si].record(s_in)
         self._comp_done[si] = torch.cuda.Event()
         self._comp_done[si].record(main)
         done = None
+        if bf16 and not to_host:
+            # the encoder consumes the batch on the device: one conversion pass over the padded batch (zero rows stay zero)
+            d16 = self._dout16[so].get(hbytes)[:hbytes].view(torch.bfloat16).view(B, Tmax, D)
+            _lib.check(lib.b200fe_cast_bf16(C.c_void_p(dfeats.data_ptr()), C.c_void_p(d16.data_ptr()), B * Tmax * D, C.c_void_p(main.cuda_stream)), "b200fe_cast_bf16")
+            fe.launch_count += 1
+            dfeats = d16
         if to_host:
             with torch.cuda.stream(s_out):
                 hlen.copy_(dlen, non_blocking=True)

@@ -93,12 +93,13 @@ class B200Collate:
     ``prefetch(iterable)`` yields the batch of item k while item k + 1 is already being packed and
     copied (what a DataLoader's prefetching does for the reference's CPU workers)."""
 
-    def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, **frontend_kwargs):
+    def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, out_dtype=torch.float32, **frontend_kwargs):
         from .host_pipeline import HostPipeline
         self.device = torch.device(device)
         self.to_host = to_host
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
-        self.pipeline = HostPipeline(self.frontend, self.device, ring=ring, threads=threads)
+        # out_dtype=torch.bfloat16: features in the precision of the encoder's first convolution under autocast (F2)
+        self.pipeline = HostPipeline(self.frontend, self.device, ring=ring, threads=threads, out_dtype=out_dtype)
 
     def __call__(self, wavs):
         feats, flen = self.pipeline.run(wavs, to_host=self.to_host)

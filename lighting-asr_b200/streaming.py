@@ -161,6 +161,10 @@ class IndependentStreams:
         if self.fe.cmvn == "global":
             self.fe.cmvn_mean = self.fe.cmvn_mean.to(dev)
             self.fe.cmvn_istd = self.fe.cmvn_istd.to(dev)
+        # one empty push (zero-length chunk: no state changes) loads the three kernels outside any graph capture
+        self.push_device(1, self.d_meta[0].data_ptr(), self.d_chunks.data_ptr(), self.max_chunk, self.d_meta[1].data_ptr(), self.d_out.data_ptr(),
+                         self.d_out.shape[1], self.d_frames.data_ptr())
+        torch.cuda.current_stream(dev).synchronize()
 
     def __del__(self):
         try:

@@ -158,3 +158,32 @@ def test_sharded_statistics_sum_to_the_fp64_definition(lasr_b200):
     mean, istd = lasr_b200.cmvn.mean_istd(total)
     rm, ri = lasr_frontend.cmvn_from_stats(ref)
     assert np.allclose(mean, rm, rtol=1e-6, atol=1e-6) and np.allclose(istd, ri, rtol=1e-6, atol=1e-6)
+
+
+def test_bfloat16_feature_emission(lasr_b200):
+    """Row F2: features in the consumer's precision (Conv2dSubsampling under autocast, subsampling.py:53-57): the float32
+    result rounded once to bfloat16 (nearest even, = tensor.to(torch.bfloat16)), on the device and through the D2H copy."""
+    rng = np.random.default_rng(26)
+    shapes = [(16000, 24000, 4321), (40000, 8000, 30011, 12000)]
+    batches = _batches(rng, shapes)
+    ref_col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, cmvn="utt_meanvar")
+    for to_host in (True, False):
+        col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=to_host, cmvn="utt_meanvar", out_dtype=torch.bfloat16)
+        for wavs in batches + batches[::-1]:
+            want = ref_col(wavs)
+            got = col(wavs)
+            f = got["wav_array"]
+            assert f.dtype == torch.bfloat16 and f.is_cuda != to_host and tuple(f.shape) == tuple(want["wav_array"].shape)
+            assert torch.equal(f.cpu(), want["wav_array"].to(torch.bfloat16))
+            assert torch.equal(got["wav_len"].cpu(), want["wav_len"])
+    fe = lasr_b200.GpuFbankFrontend()
+    buf = np.zeros((2, 24000), dtype=np.float32)
+    buf[0, :16000] = batches[0][0]
+    buf[1] = batches[0][1]
+    w = torch.from_numpy(buf).to(DEV)
+    n = np.array([16000, 24000])
+    f32, _ = fe(w, n)
+    f16, fl = fe(w, n, out_dtype=torch.bfloat16)
+    assert f16.dtype == torch.bfloat16 and torch.equal(f16, f32.to(torch.bfloat16)) and fl.tolist() == [98, 148]
+    with pytest.raises(ValueError):
+        fe(w, n, out_dtype=torch.float16)

@@ -7,9 +7,19 @@ from bench import make_list
 
 lists = [make_list(s)[0] for s in (1, 101)]
 col = lasr_b200.lasr_plugin.B200Collate("cuda:0", to_host=True, cmvn="utt_meanvar")
-for kind in ("float64", "int16", "int16 to_host=False"):
+import time
+for kind in ("float64", "int16", "int16 dma", "int16 to_host=False", "int16 bf16"):
     ls = lists if kind == "float64" else [[np.round(w * 32767).astype(np.int16) for w in l] for l in lists]
     col.to_host = "False" not in kind
+    col.pipeline.d2h_mode = "dma" if "dma" in kind else "kernel"
+    if "bf16" in kind:
+        col = lasr_b200.lasr_plugin.B200Collate("cuda:0", to_host=True, cmvn="utt_meanvar", out_dtype=torch.bfloat16)
+    for i in range(4):
+        col(ls[i % 2])
+    t0 = time.perf_counter()
+    for i in range(10):
+        col(ls[i % 2])
+    print("== %s: %.3f ms per synchronous call" % (kind, (time.perf_counter() - t0) * 100))
     for i in range(4):
         col(ls[i % 2])
     col.pipeline.trace = []
