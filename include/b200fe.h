@@ -260,6 +260,13 @@ int b200fe_host_pool_threads(const b200fe_host_pool* pool);
  * (PCM as the file holds it), 2 float64 -> float32.  dst_capacity = elements h_dst can hold. */
 long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
                                  void* h_dst, const long long* dst_offsets, long long dst_capacity);
+/* b200fe_host_pack_begin plus the upload: the pool thread that finishes the job's last task issues ONE
+ * cudaMemcpyAsync(d_dst + dst_offsets[0], h_dst + dst_offsets[0], copy_elems elements, copy_stream) on `device` and records
+ * `copy_event` (a cudaEvent_t, optional) behind it, before the ticket completes -- so the DMA of a group starts the moment its
+ * packing ends, independent of what the calling thread is doing.  h_dst must be pinned. */
+long long b200fe_host_pack_copy_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                      void* h_dst, const long long* dst_offsets, long long dst_capacity,
+                                      void* d_dst, long long copy_elems, int device, void* copy_stream, void* copy_event);
 /* Clears rows [valid_rows[u], utt_rows) of every utterance of a host [batch][utt_rows][row_elems] float32 tensor. */
 long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, int batch, long long utt_rows, long long row_elems,
                                       const long long* valid_rows, int elem_bytes /* 4 float32, 2 bfloat16 */);
@@ -299,6 +306,18 @@ int b200fe_src_mask(const b200fe_plan* plan, const long long* d_len, int len_is_
  * (lasr/data/dataset.py:8-22, one numpy row assignment per utterance).  16-byte aligned rows move as 128-bit accesses. */
 int b200fe_copy_ragged(const void* src, const long long* d_src_off, void* dst, const long long* d_dst_off,
                        const long long* d_nbytes, int batch, long long max_bytes, void* stream);
+
+/* Waveform ingest on the device.  b200fe_resample_poly: rational-ratio polyphase resampling of a ragged
+ * batch, utterance u = d_n_in[u] samples at d_in + d_in_off[u] -> d_n_out[u] samples at d_out + d_out_off[u]:
+ *     out[m] = scale * sum_j h[(m + pre_remove) * down - j * up] * in[j]
+ * (the index arithmetic of scipy.signal.resample_poly / upfirdn; h = d_filter[filter_len], built by the caller).  Stands in for
+ * ReSample (librosa `kaiser_fast`, R/lasr/data/datatrans.py:16-20) and, with up/down = 10/11 or 10/9, for SoxSpeedPt (sox `speed`,
+ * datatrans.py:29-39); both reference filters live in libraries absent here -- see DESIGN.md for what is and is not pinned.
+ * b200fe_avg_channels: y[i] = mean over c of x[i][c] for interleaved (n, channels) input (AverageChanl, datatrans.py:10-14). */
+int b200fe_resample_poly(const float* d_in, const long long* d_in_off, const long long* d_n_in, int batch, float* d_out,
+                         const long long* d_out_off, const long long* d_n_out, long long max_n_out, const float* d_filter, int filter_len,
+                         int up, int down, int pre_remove, float scale, void* stream);
+int b200fe_avg_channels(const float* d_in, float* d_out, long long n, int channels, void* stream);
 
 /* bfloat16 feature emission: the encoder's first layer (Conv2dSubsampling,
  * R/lasr/modules/net/transformer/subsampling.py:53-57) runs in bfloat16 under autocast.  b200fe_cast_bf16 converts n float32

@@ -5,7 +5,7 @@ The directory name contains a hyphen (repository layout contract); import it wit
 the repository root.  The hot path lives in ``csrc/`` (hand-written CUDA behind the C ABI of
 ``include/b200fe.h``); the Python here mirrors the reference's interfaces around it.
 """
-from . import _lib, build, cmvn, lasr_plugin, mask, specaug  # noqa: F401
+from . import _lib, build, cmvn, lasr_plugin, mask, resample, specaug  # noqa: F401
 from .frontend import FbankPlan, GpuFbankFrontend  # noqa: F401
 from .streaming import IndependentStreams, StreamingFbank  # noqa: F401
 

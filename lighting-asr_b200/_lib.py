@@ -63,9 +63,9 @@ EXPORTS = [
     "b200fe_default_opts", "b200fe_plan_create", "b200fe_plan_destroy", "b200fe_last_error",
     "b200fe_window_size", "b200fe_window_shift", "b200fe_padded_window_size", "b200fe_num_frames", "b200fe_plan_info", "b200fe_build_tile_table", "b200fe_build_tile_table_padded", "b200fe_tile_table_capacity", "b200fe_build_tile_table_device", "b200fe_build_work_list_device",
     "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_specaug_plan", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
-    "b200fe_cast_bf16", "b200fe_copy_ragged_bf16",
+    "b200fe_cast_bf16", "b200fe_copy_ragged_bf16", "b200fe_resample_poly", "b200fe_avg_channels",
     "b200fe_stream_create", "b200fe_stream_destroy", "b200fe_stream_max_frames", "b200fe_stream_reset", "b200fe_stream_push", "b200fe_stream_flags",
-    "b200fe_host_pool_create", "b200fe_host_pool_destroy", "b200fe_host_pool_threads", "b200fe_host_pack_begin", "b200fe_host_zero_rows_begin", "b200fe_host_zero_ranges_begin", "b200fe_host_wait",
+    "b200fe_host_pool_create", "b200fe_host_pool_destroy", "b200fe_host_pool_threads", "b200fe_host_pack_begin", "b200fe_host_pack_copy_begin", "b200fe_host_zero_rows_begin", "b200fe_host_zero_ranges_begin", "b200fe_host_wait",
 ]
 
 _lib = None
@@ -139,6 +139,11 @@ def load(build_if_missing=True):
     lib.b200fe_time_warp.restype = C.c_int
     lib.b200fe_cmvn_from_stats.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, c_fp, c_fp]
     lib.b200fe_cmvn_from_stats.restype = C.c_int
+    lib.b200fe_resample_poly.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_ll, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.b200fe_resample_poly.restype = C.c_int
+    lib.b200fe_avg_channels.argtypes = [C.c_void_p, C.c_void_p, c_ll, C.c_int, C.c_void_p]
+    lib.b200fe_avg_channels.restype = C.c_int
     lib.b200fe_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, c_ll, C.c_void_p]
     lib.b200fe_cast_bf16.restype = C.c_int
     lib.b200fe_copy_ragged_bf16.argtypes = lib.b200fe_copy_ragged.argtypes
@@ -163,6 +168,9 @@ def load(build_if_missing=True):
     lib.b200fe_host_pool_threads.restype = C.c_int
     lib.b200fe_host_pack_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_ll]
     lib.b200fe_host_pack_begin.restype = c_ll
+    lib.b200fe_host_pack_copy_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_ll,
+                                                C.c_void_p, c_ll, C.c_int, C.c_void_p, C.c_void_p]
+    lib.b200fe_host_pack_copy_begin.restype = c_ll
     lib.b200fe_host_zero_rows_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_ll, c_ll, C.c_void_p, C.c_int]
     lib.b200fe_host_zero_rows_begin.restype = c_ll
     lib.b200fe_host_zero_ranges_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

@@ -16,6 +16,7 @@
 #include "host_pool.h"
 #include "aux_kernels.cuh"
 #include "stream_kernels.cuh"
+#include "resample_kernels.cuh"
 #include "fbank_kernel.cuh"
 #include "fbank_instances.h"
 #ifdef B200FE_WITH_WS          // the warp-specialised experiment (measured 30 % slower) is not part of the default build
@@ -527,8 +528,8 @@ extern "C" int b200fe_host_pool_create(int n_threads, b200fe_host_pool** pool)
 extern "C" void b200fe_host_pool_destroy(b200fe_host_pool* pool) { delete pool; }
 extern "C" int b200fe_host_pool_threads(const b200fe_host_pool* pool) { return pool ? (int)pool->threads.size() : 0; }
 
-extern "C" long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
-                                            void* h_dst, const long long* dst_offsets, long long dst_capacity)
+static long long host_pack_submit(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                  void* h_dst, const long long* dst_offsets, long long dst_capacity, std::function<void()> on_done)
 {
     if (!pool || !h_src || !nsamp || !h_dst || !dst_offsets || batch < 0) return fail(B200FE_EINVAL, "host_pack: bad argument");
     if (src_dtype < 0 || src_dtype > 2) return fail(B200FE_EINVAL, "host_pack: src_dtype must be 0 (float32), 1 (int16) or 2 (float64)");
@@ -554,7 +555,31 @@ extern "C" long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* 
         }
     }
     if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_dst; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
-    return pool->submit(tasks);
+    return pool->submit(tasks, std::move(on_done));
+}
+
+extern "C" long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                            void* h_dst, const long long* dst_offsets, long long dst_capacity)
+{
+    return host_pack_submit(pool, h_src, nsamp, batch, src_dtype, h_dst, dst_offsets, dst_capacity, nullptr);
+}
+
+extern "C" long long b200fe_host_pack_copy_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
+                                                 void* h_dst, const long long* dst_offsets, long long dst_capacity,
+                                                 void* d_dst, long long copy_elems, int device, void* copy_stream, void* copy_event)
+{
+    if (!d_dst || copy_elems < 0 || batch <= 0 || !dst_offsets) return fail(B200FE_EINVAL, "host_pack_copy: bad argument");
+    const long long dsz = src_dtype == 1 ? 2 : 4;
+    const char* hs = static_cast<const char*>(h_dst) + dst_offsets[0] * dsz;
+    char* dd = static_cast<char*>(d_dst) + dst_offsets[0] * dsz;
+    const size_t bytes = (size_t)(copy_elems * dsz);
+    auto upload = [=]() {
+        // runs on a pool thread: the runtime API needs the stream's device current on THIS thread
+        cudaSetDevice(device);
+        if (bytes > 0) cudaMemcpyAsync(dd, hs, bytes, cudaMemcpyHostToDevice, (cudaStream_t)copy_stream);
+        if (copy_event) cudaEventRecord((cudaEvent_t)copy_event, (cudaStream_t)copy_stream);
+    };
+    return host_pack_submit(pool, h_src, nsamp, batch, src_dtype, h_dst, dst_offsets, dst_capacity, upload);
 }
 
 extern "C" long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, int batch, long long utt_rows, long long row_elems,
@@ -741,6 +766,30 @@ extern "C" int b200fe_copy_ragged(const void* src, const long long* d_src_off, v
     (void)sms;
     ragged_copy_kernel<<<grid, kCopyThreads, 0, (cudaStream_t)stream>>>(static_cast<const char*>(src), d_src_off, static_cast<char*>(dst), d_dst_off,
                                                                         d_nbytes, batch, (int)cpr);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_resample_poly(const float* d_in, const long long* d_in_off, const long long* d_n_in, int batch, float* d_out,
+                                    const long long* d_out_off, const long long* d_n_out, long long max_n_out, const float* d_filter, int filter_len,
+                                    int up, int down, int pre_remove, float scale, void* stream)
+{
+    if (!d_in || !d_in_off || !d_n_in || !d_out || !d_out_off || !d_n_out || !d_filter || batch <= 0 || batch > 65535 || filter_len <= 0 || up <= 0 || down <= 0 ||
+        pre_remove < 0 || max_n_out < 0)
+        return fail(B200FE_EINVAL, "resample_poly: bad argument");
+    if (max_n_out == 0) return B200FE_OK;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((max_n_out + 255) / 256, 4096)), (unsigned)batch);
+    resample_poly_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_in_off, d_n_in, d_out, d_out_off, d_n_out, d_filter, filter_len, up, down, pre_remove, scale);
+    CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_avg_channels(const float* d_in, float* d_out, long long n, int channels, void* stream)
+{
+    if (!d_in || !d_out || n < 0 || channels <= 0) return fail(B200FE_EINVAL, "avg_channels: bad argument");
+    if (n == 0) return B200FE_OK;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 16));
+    avg_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n, channels);
     CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }

@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -23,6 +24,8 @@ namespace b200fe_host {
 
 struct Job {
     std::atomic<long long> remaining{0};
+    std::atomic<bool> done{false};
+    std::function<void()> on_done;      // runs on the thread that finishes the job's last task, before waiters are released
     std::mutex m;
     std::condition_variable cv;
 };
@@ -107,7 +110,12 @@ struct b200fe_host_pool {
     }
     static void finish(const b200fe_host::Task& t)
     {
-        if (t.job->remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(t.job->m); t.job->cv.notify_all(); }
+        if (t.job->remaining.fetch_sub(1) == 1) {
+            if (t.job->on_done) t.job->on_done();
+            std::lock_guard<std::mutex> g(t.job->m);
+            t.job->done = true;
+            t.job->cv.notify_all();
+        }
     }
     void worker()
     {
@@ -123,10 +131,11 @@ struct b200fe_host_pool {
             finish(t);
         }
     }
-    long long submit(std::vector<b200fe_host::Task>& tasks)
+    long long submit(std::vector<b200fe_host::Task>& tasks, std::function<void()> on_done = nullptr)
     {
         auto job = std::make_shared<b200fe_host::Job>();
         job->remaining = (long long)tasks.size();
+        job->on_done = std::move(on_done);
         for (auto& t : tasks) t.job = job;
         long long ticket;
         {
@@ -149,7 +158,7 @@ struct b200fe_host_pool {
             job = it->second;
             jobs.erase(it);
         }
-        while (job->remaining.load() > 0) {
+        while (!job->done.load()) {
             b200fe_host::Task t;
             bool have = false;
             {
@@ -158,7 +167,7 @@ struct b200fe_host_pool {
             }
             if (have) { b200fe_host::run_task(t); finish(t); continue; }
             std::unique_lock<std::mutex> g(job->m);
-            job->cv.wait(g, [&] { return job->remaining.load() <= 0; });
+            job->cv.wait(g, [&] { return job->done.load(); });
         }
         return 0;
     }

@@ -105,7 +105,10 @@ class HostPipeline:
         self._out_done = [None] * self.ring
         self._turn = 0
         self._streams = None
+        self._events = []                   # per-group upload events, recorded by the pool thread that issues the group's DMA
         self.h2d_bytes = self.d2h_bytes = 0
+        self.resampler = None               # resample.Resampler: applied on the device to every group before the fused launch (F3)
+        self.speed = None                   # resample.SpeedPerturb: one numpy.random.choice per utterance, then resampling by 1 / ratio
         self.d2h_mode = "kernel"            # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
@@ -132,6 +135,9 @@ class HostPipeline:
             raise ValueError("empty batch")
         self._stamp("submit")
         arrs = [np.asarray(w) for w in wavs]
+        if any(a.ndim == 2 for a in arrs):
+            # multi-channel files: the reference's own `avgchannel` (numpy.average(wav, axis=1), datatrans.py:10-14)
+            arrs = [np.average(a, axis=1) if a.ndim == 2 else a for a in arrs]
         dt = arrs[0].dtype
         if dt not in _SRC_CODE or any(a.dtype != dt for a in arrs):
             dt = np.dtype(np.float64) if dt not in _SRC_CODE else dt
@@ -144,10 +150,19 @@ class HostPipeline:
         esz = 2 if code == 1 else 4
         al = 16 // esz
         lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=B)
-        T_host, win = fe.frame_counts(lens)
-        if (lens < win).any():
+        lens_eff, ratios = lens, None
+        if self.resampler is not None or self.speed is not None:
+            if code == 1:
+                raise ValueError("device resampling / speed perturbation takes float waveforms (int16 PCM lists are not resampled)")
+            if self.resampler is not None:
+                lens_eff = self.resampler.out_lengths(lens_eff)
+            if self.speed is not None:
+                ratios = self.speed.draw(B)
+                lens_eff = np.array([int(self.speed._rs[r].out_lengths(n)) for r, n in zip(ratios, lens_eff)], dtype=np.int64)
+        T_host, win = fe.frame_counts(lens_eff)
+        if (lens_eff < win).any():
             # torchaudio asserts (TA:142); LASR filters min_duration upstream (dataset.py:243,272)
-            raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(lens.min())))
+            raise AssertionError("choose a window size {} that is [2, {}]".format(win, int(lens_eff.min())))
         offs = np.zeros(B, dtype=np.int64)
         np.cumsum((lens[:-1] + al - 1) // al * al, out=offs[1:])
         total = int(offs[-1] + (lens[-1] + al - 1) // al * al)
@@ -175,13 +190,26 @@ class HostPipeline:
         if bounds[-1] != B:
             bounds.append(B)
         ptrs = (C.c_void_p * B)(*[a.__array_interface__["data"][0] for a in arrs])     # (ndarray.ctypes.data costs ~1.5 us per array)
+        if self._comp_done[si] is not None:
+            s_in.wait_event(self._comp_done[si])       # kernels of the call that last read this device staging buffer
+        while len(self._events) < len(bounds) - 1:
+            ev = torch.cuda.Event()
+            ev.record(s_in)                            # materialises the cudaEvent_t the pool threads re-record
+            self._events.append(ev)
         tickets = []
-        for b0, b1 in zip(bounds[:-1], bounds[1:]):
-            tk = lib.b200fe_host_pack_begin(self.pool, C.c_void_p(C.addressof(ptrs) + 8 * b0), C.c_void_p(lens.ctypes.data + 8 * b0), b1 - b0, code,
-                                            C.c_void_p(hin.data_ptr()), C.c_void_p(offs.ctypes.data + 8 * b0), hin.numel())
+        self.h2d_bytes = 0
+        for g, (b0, b1) in enumerate(zip(bounds[:-1], bounds[1:])):
+            o0 = int(offs[b0])
+            o1 = int(offs[b1]) if b1 < B else total
+            # pack + convert on the pool; the thread that finishes the group issues its DMA on s_in and records the group's event
+            tk = lib.b200fe_host_pack_copy_begin(self.pool, C.c_void_p(C.addressof(ptrs) + 8 * b0), C.c_void_p(lens.ctypes.data + 8 * b0), b1 - b0, code,
+                                                 C.c_void_p(hin.data_ptr()), C.c_void_p(offs.ctypes.data + 8 * b0), hin.numel(),
+                                                 C.c_void_p(dwav.data_ptr()), o1 - o0, dev.index or 0, C.c_void_p(s_in.cuda_stream),
+                                                 C.c_void_p(self._events[g].cuda_event))
             if tk <= 0:
-                _lib.check(int(tk), "b200fe_host_pack_begin")
+                _lib.check(int(tk), "b200fe_host_pack_copy_begin")
             tickets.append(tk)
+            self.h2d_bytes += (o1 - o0) * esz
         # ---- host output slot: only what an earlier batch left in this batch's padding rows has to be cleared ----
         obytes = B * Tmax * D * 4
         bf16 = self.out_dtype == torch.bfloat16
@@ -220,24 +248,20 @@ class HostPipeline:
             ev_tab = torch.cuda.Event()
             ev_tab.record(main)
             s_out.wait_event(ev_tab)
-        if self._comp_done[si] is not None:
-            s_in.wait_event(self._comp_done[si])       # kernels of the call that last read this device staging buffer
         if self._out_done[so] is not None:
             main.wait_event(self._out_done[so])        # D2H of the call that last used this device feature slot
-        self.h2d_bytes = self.d2h_bytes = 0
+        self.d2h_bytes = 0
         self._stamp("prepared")
-        for (b0, b1), tk in zip(zip(bounds[:-1], bounds[1:]), tickets):
-            _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")
+        for g, ((b0, b1), tk) in enumerate(zip(zip(bounds[:-1], bounds[1:]), tickets)):
+            _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")      # packed, DMA issued, event recorded
             self._stamp("packed")
-            o0 = int(offs[b0])
-            o1 = int(offs[b1]) if b1 < B else total
-            with torch.cuda.stream(s_in):
-                dwav[o0:o1].copy_(hin[o0:o1], non_blocking=True)
-            ev_in = torch.cuda.Event()
-            ev_in.record(s_in)
-            self.h2d_bytes += (o1 - o0) * esz
-            main.wait_event(ev_in)
-            fe.forward(dwav, lens[b0:b1], max_frames=Tmax, out=dfeats[b0:b1], out_len=dlen[b0:b1], wav_offsets=offs[b0:b1])
+            main.wait_event(self._events[g])
+            gw, gl, go = dwav, lens[b0:b1], offs[b0:b1]
+            if self.resampler is not None:
+                gw, gl, go = self.resampler(gw, gl, go)
+            if self.speed is not None:
+                gw, gl, go, _ = self.speed(gw, gl, go, ratios=ratios[b0:b1])
+            fe.forward(gw, gl, max_frames=Tmax, out=dfeats[b0:b1], out_len=dlen[b0:b1], wav_offsets=go)
             if to_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)

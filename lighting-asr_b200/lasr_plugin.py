@@ -93,13 +93,22 @@ class B200Collate:
     ``prefetch(iterable)`` yields the batch of item k while item k + 1 is already being packed and
     copied (what a DataLoader's prefetching does for the reference's CPU workers)."""
 
-    def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, out_dtype=torch.float32, **frontend_kwargs):
+    def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, out_dtype=torch.float32, input_rate=None, speed_perturb=None,
+                 **frontend_kwargs):
         from .host_pipeline import HostPipeline
+        from . import resample as _rs
         self.device = torch.device(device)
         self.to_host = to_host
         self.frontend = GpuFbankFrontend(**frontend_kwargs)
         # out_dtype=torch.bfloat16: features in the precision of the encoder's first convolution under autocast (F2)
         self.pipeline = HostPipeline(self.frontend, self.device, ring=ring, threads=threads, out_dtype=out_dtype)
+        # F3 ingest on the device: `resample:16k` (datatrans.py:16-20) when the files' rate differs from the front end's, and
+        # `soxspeed` (datatrans.py:29-39) with the reference's ratio list, e.g. speed_perturb=(1, 1.1, 0.9)
+        rate = self.frontend.opts["sample_frequency"]
+        if input_rate is not None and float(input_rate) != float(rate):
+            self.pipeline.resampler = _rs.Resampler(int(input_rate), int(rate))
+        if speed_perturb:
+            self.pipeline.speed = _rs.SpeedPerturb(speed_perturb)
 
     def __call__(self, wavs):
         feats, flen = self.pipeline.run(wavs, to_host=self.to_host)
