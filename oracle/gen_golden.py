@@ -136,5 +136,51 @@ def main():
     print("wrote", os.listdir(OUT))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--batching" not in sys.argv:
     main()
+
+
+def gen_batching():
+    """Batch formation goldens: BatchAudioDataSet.check_dataset's shuffle / stable sort / filter and
+    make_batch_size / make_batch_duration (R/lasr/data/dataset.py:260-305) run UNMODIFIED on synthetic (wav_len, token_len)
+    items; only the parent's file-reading check_dataset (dataset.py:106-133: audio durations, tokenizer) is skipped."""
+    import_reference()
+    import lasr.data.dataset as ds
+    rng = np.random.default_rng(77)
+    out = {}
+    cases = [dict(batch_type="duration", batch_duration=120, batch_sort=True), dict(batch_type="size", batch_size=7, batch_sort=True),
+             dict(batch_type="duration", batch_duration=40, batch_sort=False), dict(batch_type="size", batch_size=5, batch_sort=True, min_token=2, text_freq=0.2)]
+    parent = ds.AudioDataSet.check_dataset
+    ds.AudioDataSet.check_dataset = lambda self: None
+    try:
+        for ci, kw in enumerate(cases):
+            n = 60 + 11 * ci
+            wav_len = np.round(rng.uniform(0.1, 33.0, n), 2)
+            wav_len[9::9] = wav_len[1:-8:9][: len(wav_len[9::9])]      # ties: the stable sort keeps the shuffled order
+            token_len = rng.integers(0, 60, n)
+            obj = object.__new__(ds.BatchAudioDataSet)
+            obj.train_set = [{"id": i, "wav_len": float(wav_len[i]), "token_len": int(token_len[i])} for i in range(n)]
+            full = dict(batch_sort=True, batch_size=32, batch_duration=320, batch_type="size", max_duration=30, min_duration=0.3, text_freq=0.08,
+                        min_token=0, max_token=5000)
+            full.update(kw)
+            for k, v in full.items():
+                setattr(obj, k, v)
+            random.seed(100 + ci)
+            obj.check_dataset()
+            flat = np.array([it["id"] for b in obj.train_set for it in b], dtype=np.int64)
+            sizes = np.array([len(b) for b in obj.train_set], dtype=np.int64)
+            out["c%d_wav_len" % ci] = wav_len
+            out["c%d_token_len" % ci] = token_len
+            out["c%d_flat" % ci] = flat
+            out["c%d_sizes" % ci] = sizes
+            out["c%d_kw" % ci] = np.array(repr(full))
+            out["c%d_after" % ci] = np.array(random.random())           # the global generator's position afterwards
+    finally:
+        ds.AudioDataSet.check_dataset = parent
+    out["cases"] = np.arange(len(cases))
+    np.savez_compressed(os.path.join(OUT, "batch_reference.npz"), **out)
+    print("wrote batch_reference.npz")
+
+
+if __name__ == "__main__" and "--batching" in sys.argv:
+    gen_batching()

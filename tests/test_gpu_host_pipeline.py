@@ -74,7 +74,7 @@ def test_collate_input_types_and_prefetch(lasr_b200):
     with pytest.raises(AssertionError):
         col([np.zeros(16000), np.zeros(399)])                     # torchaudio asserts on short input (TA:142)
     with pytest.raises(ValueError):
-        col([np.zeros((100, 2))])
+        col([np.zeros((100, 2, 2))])
 
 
 def test_zero_masks_with_utterance_cmvn_are_applied_after_normalisation(lasr_b200):
@@ -187,3 +187,45 @@ def test_bfloat16_feature_emission(lasr_b200):
     assert f16.dtype == torch.bfloat16 and torch.equal(f16, f32.to(torch.bfloat16)) and fl.tolist() == [98, 148]
     with pytest.raises(ValueError):
         fe(w, n, out_dtype=torch.float16)
+
+
+def test_cmvn_stats_cli(lasr_b200, tmp_path):
+    """Row F4: tools/compute_cmvn_stats.py writes the Kaldi text statistics of a corpus (npy + PCM-16 wav files); the file
+    loads into cmvn='global' and equals the fp64 definition on the device's features."""
+    import sys
+    import wave
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1] / "tools"))
+    import compute_cmvn_stats as cli
+    rng = np.random.default_rng(27)
+    paths, wavs = [], []
+    for i, n in enumerate((16000, 24000, 4321, 300, 9999)):
+        w = np.clip(rng.normal(0, 0.2, n), -1, 1)
+        if i % 2 == 0:
+            p = tmp_path / ("u%d.npy" % i)
+            np.save(p, w.astype(np.float32))
+            wavs.append(w.astype(np.float32))
+        else:
+            p = tmp_path / ("u%d.wav" % i)
+            pcm = np.round(w * 32767).astype(np.int16)
+            with wave.open(str(p), "wb") as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+            wavs.append(pcm.astype(np.float32) / 32768.0)
+        paths.append(str(p))
+    lst = tmp_path / "wavs.txt"
+    lst.write_text("\n".join("utt%d %s" % (i, p) for i, p in enumerate(paths)) + "\n")
+    out = tmp_path / "cmvn.stats"
+    cli.main(["--list", str(lst), "--out", str(out), "--batch-seconds", "2"])
+    st = lasr_b200.cmvn.load_stats(str(out))
+    fe = lasr_b200.GpuFbankFrontend()
+    feats = []
+    for w in wavs:
+        if len(w) < 400:
+            continue
+        pad = (-len(w)) % 4
+        f, fl = fe(torch.from_numpy(np.pad(w, (0, pad))).to(DEV).unsqueeze(0), np.array([len(w)]))
+        feats.append(f[0, : int(fl[0])].cpu().numpy())
+    ref = lasr_frontend.cmvn_stats(feats)
+    assert st.shape == (2, 81) and st[0, 80] == ref[0, 80]
+    assert np.allclose(st, ref, rtol=2e-7, atol=1e-4)
+    g = lasr_b200.GpuFbankFrontend(cmvn="global", cmvn_stats=st)
+    assert np.allclose(g.cmvn_mean.numpy(), lasr_frontend.cmvn_from_stats(ref)[0], rtol=1e-6, atol=1e-6)

@@ -54,7 +54,7 @@ def test_independent_streams_equal_offline(lasr_b200, graph, sf):
         else:
             # 256-point family: two consecutive frames share one complex FFT, so a frame's last bits depend on which frame it is
             # paired with -- and the pairing follows the chunk boundaries
-            assert np.allclose(have, want, rtol=5e-6, atol=5e-5), (s, float(np.abs(have - want).max()))
+            assert int((np.abs(have - want) > 1e-5 + 1e-4 * np.abs(want)).sum()) == 0, (s, float(np.abs(have - want).max()))    # north_star tolerance
 
 
 def test_stream_reset_and_global_cmvn(lasr_b200):
