@@ -117,6 +117,13 @@ class HostPipeline:
             import time
             self.trace.append((label, time.perf_counter()))
 
+    def _dev_stamp(self, label, stream):
+        """tracing only: a timing event on `stream`; tools/pipe_trace.py prints when the device reached it"""
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.dev_trace.append((label, ev))
+
     def __del__(self):
         try:
             if getattr(self, "pool", None):
@@ -134,6 +141,10 @@ class HostPipeline:
         if B == 0:
             raise ValueError("empty batch")
         self._stamp("submit")
+        if self.trace is not None and not hasattr(self, "dev_trace"):
+            self.dev_trace = []
+        if self.trace is not None:
+            self._dev_stamp("start", torch.cuda.current_stream(self.dev))
         arrs = [np.asarray(w) for w in wavs]
         if any(a.ndim == 2 for a in arrs):
             # multi-channel files: the reference's own `avgchannel` (numpy.average(wav, axis=1), datatrans.py:10-14)
@@ -255,6 +266,7 @@ class HostPipeline:
         for g, ((b0, b1), tk) in enumerate(zip(zip(bounds[:-1], bounds[1:]), tickets)):
             _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")      # packed, DMA issued, event recorded
             self._stamp("packed")
+            self._dev_stamp("h2d %d done" % g, s_in)
             main.wait_event(self._events[g])
             gw, gl, go = dwav, lens[b0:b1], offs[b0:b1]
             if self.resampler is not None:
@@ -262,6 +274,7 @@ class HostPipeline:
             if self.speed is not None:
                 gw, gl, go, _ = self.speed(gw, gl, go, ratios=ratios[b0:b1])
             fe.forward(gw, gl, max_frames=Tmax, out=dfeats[b0:b1], out_len=dlen[b0:b1], wav_offsets=go)
+            self._dev_stamp("compute %d done" % g, main)
             if to_host:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
@@ -279,6 +292,7 @@ class HostPipeline:
                                 int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
                 fe.launch_count += 1
                 self.d2h_bytes += int(T_host[b0:b1].sum()) * D * osz
+                self._dev_stamp("d2h %d done" % g, s_out)
             self._stamp("issued")
         self._in_free[si] = torch.cuda.Event()
         self._in_free[si].record(s_in)

@@ -23,6 +23,15 @@ for kind in ("float64", "int16", "int16 dma", "int16 to_host=False", "int16 bf16
     for i in range(4):
         col(ls[i % 2])
     col.pipeline.trace = []
+    col.pipeline.dev_trace = []
+    col(ls[0])
+    torch.cuda.synchronize()
+    dtr = col.pipeline.dev_trace
+    print("== %s: device timeline of one call (ms after the call's first stream operation)" % kind)
+    for lab, ev in dtr[1:]:
+        print("  %-18s %8.3f" % (lab, dtr[0][1].elapsed_time(ev)))
+    col.pipeline.trace = []
+    col.pipeline.dev_trace = []
     col(ls[0]); col(ls[1])
     tr = col.pipeline.trace
     col.pipeline.trace = None
