@@ -568,7 +568,12 @@ extern "C" long long b200fe_host_pack_copy_begin(b200fe_host_pool* pool, const v
                                                  void* h_dst, const long long* dst_offsets, long long dst_capacity,
                                                  void* d_dst, long long copy_elems, int device, void* copy_stream, void* copy_event)
 {
-    if (!d_dst || copy_elems < 0 || batch <= 0 || !dst_offsets) return fail(B200FE_EINVAL, "host_pack_copy: bad argument");
+    if (!pool || !d_dst || copy_elems < 0 || batch <= 0 || !dst_offsets) return fail(B200FE_EINVAL, "host_pack_copy: bad argument");
+    if (pool->device.load() != device) {
+        // the workers attach to the device's primary context before their next task (once per thread), not inside an upload
+        pool->bind_device = [](int dev) { cudaSetDevice(dev); cudaFree(nullptr); };
+        pool->device.store(device);
+    }
     const long long dsz = src_dtype == 1 ? 2 : 4;
     const char* hs = static_cast<const char*>(h_dst) + dst_offsets[0] * dsz;
     char* dd = static_cast<char*>(d_dst) + dst_offsets[0] * dsz;

@@ -95,6 +95,10 @@ struct b200fe_host_pool {
     std::condition_variable cv;
     std::deque<b200fe_host::Task> q;
     bool stop = false;
+    // CUDA device the completion hooks (uploads) use: every worker binds it ONCE, before its first task after it was set -- the
+    // first runtime call of a thread attaches the primary context, which costs milliseconds and must not sit inside a batch
+    std::atomic<int> device{-1};
+    void (*bind_device)(int) = nullptr;
     long long next_ticket = 1;
     std::map<long long, std::shared_ptr<b200fe_host::Job>> jobs;
 
@@ -119,6 +123,7 @@ struct b200fe_host_pool {
     }
     void worker()
     {
+        int bound = -1;
         for (;;) {
             b200fe_host::Task t;
             {
@@ -127,6 +132,8 @@ struct b200fe_host_pool {
                 if (q.empty()) return;
                 t = q.front(); q.pop_front();
             }
+            const int want = device.load();
+            if (want >= 0 && want != bound && bind_device) { bind_device(want); bound = want; }
             b200fe_host::run_task(t);
             finish(t);
         }
