@@ -494,6 +494,12 @@ def main():
                            "float32, 'wav_len': (B,) int64}; synchronous call, rotating distinct batches",
                     "host_threads": pipe.threads, "host_pack_convert_ms": pack_ms,
                     "pcie_floor_ms": fl_both, "vs_pcie_floor": per / fl_both if fl_both > 0 else None,
+                    # float64 lists are bound by the HOST memory system, not by PCIe: per step the cores read 8 B/sample and write 4 B/sample
+                    # (pack), the DMA engines read those 4 B/sample again and write the features; the pack alone measures what this box's
+                    # memory system sustains
+                    "host_memory": {"bytes_per_step": 3 * h2d + h2d + d2h, "pack_alone_gbs": 3 * h2d / pack_ms / 1e6 if pack_ms > 0 else None,
+                                    "floor_ms": (3 * h2d + h2d + d2h) / (3 * h2d / pack_ms) if pack_ms > 0 else None,
+                                    "vs_floor": per / ((3 * h2d + h2d + d2h) / (3 * h2d / pack_ms)) if pack_ms > 0 else None},
                     "matches_device_path": {"max_abs_diff": e2e_max_diff, "lengths_equal": e2e_len_ok}},
             "gpu_launches": launches,
             "clocks": clocks,

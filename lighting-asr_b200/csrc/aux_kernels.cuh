@@ -678,4 +678,53 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
     }
 }
 
+// Plain utterance CMVN (no SpecAugment fills): the post pass of BASELINE config 2.  Same arithmetic as postpass_vec_kernel's
+// CMVN path, as a kernel of its own so that its register count (and with it the number of resident CTAs) is not set by the
+// mask logic: the ncu capture of the shared kernel (profiles/r03_ncu_postpass.json) shows a LATENCY-bound pass -- 52 registers,
+// 4 CTAs per SM, long-scoreboard stalls 12 per issue, DRAM 52 % -- not a bandwidth-bound one.
+#ifndef B200FE_POST_OCC
+#define B200FE_POST_OCC 5          // measured on B200 (C2 step): 4 -> +61.5 us, 5 -> +58.0, 6 (32 B of spills) -> +64.2, 8 (spills) -> +92
+#endif
+__global__ void __launch_bounds__(256, B200FE_POST_OCC) postpass_cmvn_kernel(const PostArgs a)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int utt = (int)(gridDim.y - 1 - blockIdx.y);          // backwards: the rows the fused launch wrote last are the most likely L2 hits
+    const long long n = a.nsamp[utt];
+    const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
+    const int r0 = (int)(gridDim.x - 1 - blockIdx.x) * a.rows_per_cta;
+    if (r0 >= T) return;
+    __shared__ __align__(16) float s_mu[kMaxMel], s_is[kMaxMel];
+    {
+        const double* sb = a.stats + (long long)utt * a.stats_stride;
+        for (int d = threadIdx.x; d < a.nmel; d += 256) {
+            const double mean = sb[d] / T;
+            double istd = 1.0;
+            if (a.cmvn_mode == 2) {
+                const double var = sb[(long long)a.n_cls * a.nmel + d] / T - mean * mean;
+                istd = 1.0 / sqrt(var > 1e-20 ? var : 1e-20);
+            }
+            s_mu[d] = (float)mean; s_is[d] = (float)istd;
+            if (r0 == 0) { a.cm_mean[(long long)utt * a.nmel + d] = (float)mean; a.cm_istd[(long long)utt * a.nmel + d] = (float)istd; }
+        }
+    }
+    __syncthreads();
+    const int r1 = min(r0 + a.rows_per_cta, T);
+    const int nq = a.nmel >> 2, slots = 256 / nq;
+    const int q = threadIdx.x % nq, slot = threadIdx.x / nq;
+    if (slot >= slots) return;
+    const float4 mu = *reinterpret_cast<const float4*>(s_mu + 4 * q), is = *reinterpret_cast<const float4*>(s_is + 4 * q);
+    float4* base = reinterpret_cast<float4*>(a.feats + (a.feat_offsets != nullptr ? a.feat_offsets[utt] : (long long)utt * a.Tmax) * a.nmel);
+    for (int rb = r0 + slot; rb < r1; rb += 4 * slots) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int r = rb + u * slots; if (r < r1) v[u] = base[(long long)r * nq + q]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = rb + u * slots;
+            if (r < r1) base[(long long)r * nq + q] = make_float4((v[u].x - mu.x) * is.x, (v[u].y - mu.y) * is.y, (v[u].z - mu.z) * is.z, (v[u].w - mu.w) * is.w);
+        }
+    }
+}
+
 }  // namespace b200fe

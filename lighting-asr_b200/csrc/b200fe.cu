@@ -1076,7 +1076,9 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     dim3 grid((unsigned)((g->max_frames + a.rows_per_cta - 1) / a.rows_per_cta), (unsigned)g->batch);
     if (vec) {
         void* pargs[] = {(void*)&a};
-        CUDA_TRY(launch_pdl((const void*)postpass_vec_kernel, grid, dim3(256), pargs, 0, st));
+        // plain utterance CMVN has its own lean kernel (more resident CTAs: the pass is latency bound)
+        const bool lean_cmvn = a.inline_finalize && p->nmel <= kMaxMel;
+        CUDA_TRY(launch_pdl(lean_cmvn ? (const void*)postpass_cmvn_kernel : (const void*)postpass_vec_kernel, grid, dim3(256), pargs, 0, st));
     } else {
         postpass_kernel<<<grid, 256, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());

@@ -25,8 +25,9 @@ y64 = np.concatenate(frames64)                                                  
 y32 = y64.astype(np.float32)
 z = (y32[:, 0::2] + 1j * y32[:, 1::2]).astype(np.complex64)
 n = len(z)
-os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-fin, fout = os.path.join(ROOT, "gpurun_out", "tc_frames.bin"), os.path.join(ROOT, "gpurun_out", "tc_out.bin")
+import tempfile
+tmp = tempfile.mkdtemp()                                                          # 2 x 32 MB of scratch: not under gpurun_out/ (64 MiB cap)
+fin, fout = os.path.join(tmp, "tc_frames.bin"), os.path.join(tmp, "tc_out.bin")
 z.view(np.float32).tofile(fin)
 mel = kaldi_fbank.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, np.float64)
 mel = mel[0] if isinstance(mel, tuple) else mel
