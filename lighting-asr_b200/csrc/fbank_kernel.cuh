@@ -11,13 +11,15 @@
 //             utterance.  256 threads = 16 half-warps.
 //   * load  : the waveform span of a tile ((FT-1)*shift + win samples, each sample fetched once
 //             per tile) is brought to shared memory with one 1-D TMA bulk copy (UBLKCP) per
-//             tile into a 2-stage ring, completion on an mbarrier.
+//             tile into ONE tile buffer (kStages = 1: the next tile's copy is issued right after the
+//             phase-A barrier), completion on an mbarrier.
 //   * phase A (half-warp per frame, 2 frames each): 16 lanes x 16 complex registers hold the
 //             frame packed as a 256-point complex sequence z[n] = y[2n] + j y[2n+1].
 //             DC removal, pre-emphasis and the window are applied while loading; DFT-16 in
 //             registers (packed FADD2/FFMA2), twiddle, one transposition through shared memory,
-//             second DFT-16, conjugate-pair exchange with warp shuffles, real-FFT split and
-//             |X|^2 -> power spectrum written transposed, PT4[k/4][frame][k%4].
+//             second DFT-16, conjugate-pair exchange with warp shuffles, real-FFT split (split twiddles = the
+//             lane's r = 0 value x W_32^r immediates) and |X|^2 -> the frame's power row INSIDE the half-warp's
+//             transposition region (see kRegionHW below).
 //   * phase B (warp = group of mel bins, lane = frame): sparse triangular mel accumulate.  For the
 //             LASR default option set the projection is straight-line code with the weights as
 //             immediates (mel_static_default.inc); otherwise the (up, down) weights are
