@@ -29,7 +29,19 @@ plan = fe.plan(dev)
 res["ctas_per_sm"] = plan.lib.b200fe_plan_info(plan.handle, 3)
 res["warps_per_cta"] = plan.lib.b200fe_plan_info(plan.handle, 9)
 res["smem_per_cta"] = plan.lib.b200fe_plan_info(plan.handle, 2)
-for key, fn in (("plain_ms", lambda: fe(wav, nd, max_frames=Tmax, out=out)), ("c2_step_ms", lambda: fc(wav, nd, max_frames=Tmax, out=out))):
+fa = lasr_b200.GpuFbankFrontend(cmvn="utt_meanvar")
+fa.inlaunch_cmvn = True
+ref = fc(wav, n, max_frames=Tmax)[0].clone()
+got = fa(wav, n, max_frames=Tmax)[0]
+torch.cuda.synchronize()
+res["inlaunch_ran"] = fa.last["apply_flags"] is not None
+if res["inlaunch_ran"]:
+    w_, i_ = fa.last["apply_flags"]
+    res["inlaunch_error_flag"] = int(w_[i_].item())
+    res["inlaunch_max_diff_vs_post_pass"] = float((got - ref).abs().max())
+del ref, got
+for key, fn in (("plain_ms", lambda: fe(wav, nd, max_frames=Tmax, out=out)), ("c2_step_ms", lambda: fc(wav, nd, max_frames=Tmax, out=out)),
+                ("c2_inlaunch_ms", lambda: fa(wav, n, max_frames=Tmax, out=out))):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     best = []
