@@ -446,7 +446,8 @@ __device__ __forceinline__ double pil_bicubic(double x)
 }
 
 constexpr int kWarpRows = 32;    // output rows per CTA
-constexpr int kWarpTaps = 32;    // >= ceil(2 * scale) * 2 + 1 for |in - out| <= 5
+constexpr int kWarpTaps = 16;    // taps per output row: xmax - xmin <= min(in_size, 2 * support + 1); with |in - out| <= W (max_time_warp, 5 in the
+                                 // reference) a scale above 2 needs out < W, i.e. in < 2 W, so 16 taps cover W <= 8 (larger windows are clipped as before)
 
 // Work split (second version; the first spent 218 thread-instructions per output cell, most of them in the coefficient
 // set-up that 32 of 256 threads ran alone): (1) 32 threads derive the tap window of their output row (one float64 division
