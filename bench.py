@@ -68,6 +68,16 @@ def make_batch(rank=0, world=1):
     return wav, n
 
 
+def config_dict(world, B, hours, wav_bytes):
+    """The `config` entry of the JSON line -- identical for the repo arm and for `--impl reference` (same workload, same inputs)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "audio_hours_per_gpu_step": hours,
+            "inputs": "value: float32 waveforms (B, Nmax) and int64 sample counts resident in HBM, features + frame counts written to HBM; "
+                      "e2e and the reference arm: lists of host float64 ndarrays, one per utterance (what soundfile.read returns), four distinct "
+                      "C2-shaped batches (seeds %s) rotating -- both arms receive the same lists" % (BATCH_SEEDS,),
+            "l2": "inputs (%.0f MB/step/GPU) exceed the 126 MB L2; no flush needed" % (wav_bytes / 1e6),
+            "parallelism": "global batch of %d utterances sharded per utterance (length-balanced) x%d, no data-path collective" % (256 * world, world)}
+
+
 def algorithmic_bytes(n, T, B):
     """4 B per sample read once + 80*4 B per frame written once + 8 B per length."""
     return 4 * int(n.sum()) + 320 * int(T.sum()) + 8 * B
@@ -131,7 +141,8 @@ def reference_arm(args, rank, world, out):
     if rank != 0:
         return
     from oracle import cpu_baseline
-    lists = [make_list(s)[0] for s in BATCH_SEEDS]
+    lists = [make_list(s, 0, world)[0] for s in BATCH_SEEDS]       # rank 0's shard of every global batch: what the repo arm's rank 0 receives
+    n0 = np.array([len(w) for w in lists[0]], dtype=np.int64)
     allw = [w for lst in lists for w in lst]
     first = np.cumsum([0] + [len(lst) for lst in lists])
     cores = os.cpu_count() or 1
@@ -154,8 +165,7 @@ def reference_arm(args, rank, world, out):
     line = {"impl": "reference", "metric": "audio-hours/sec", "value": val, "unit": "audio-h/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "inputs": "lists of host float64 ndarrays, one per utterance (what soundfile.read returns), four distinct "
-                                                       "C2-shaped batches (seeds %s) rotating -- the same lists the repo arm's e2e receives" % (BATCH_SEEDS,)},
+            "config": config_dict(world, len(n0), float(n0.sum()) / SR / 3600.0, len(n0) * int((n0.max() + 3) // 4 * 4) * 4),
             "cpu_baseline": {"value": val, "unit": "audio-h/s", "cores": cores, "kind": "port",
                              "sample": "one full 256-utterance C2 batch per step (%.3f audio-h on average): torchaudio.compliance.kaldi.fbank via the oracle's "
                                        "restatement of WavToKaldiFbank + fp64 utterance CMVN + batch_list, %d single-threaded worker processes" % (float(np.mean(hours)), cores)},
@@ -476,12 +486,7 @@ def main():
             "metric": "audio-hours/sec", "value": hours_all / (step_ms * 1e-3), "unit": "audio-h/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "audio_hours_per_gpu_step": hours,
-                       "inputs": "value: float32 waveforms (B, Nmax) and int64 sample counts resident in HBM, features + frame counts written to HBM; "
-                                 "e2e: lists of host float64 ndarrays, one per utterance, four distinct C2-shaped batches (seeds %s) rotating -- the same "
-                                 "lists `--impl reference` receives" % (BATCH_SEEDS,),
-                       "l2": "inputs (%.0f MB/step/GPU) exceed the 126 MB L2; no flush needed" % (wav_dev.numel() * 4 / 1e6),
-                       "parallelism": "global batch of %d utterances sharded per utterance (length-balanced) x%d, no data-path collective" % (256 * world, world)},
+            "config": config_dict(world, B, hours, wav_dev.numel() * 4),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "traffic_capture": traffic_info,
                          "kernel": "fbank_fused_kernel<13,true,false,false,false,false,true> = lean instantiation of the default option set (every fused launch of one step, incl. the zero fill of the padded rows by its padding tiles)",
