@@ -151,8 +151,9 @@ class HostPipeline:
             arrs = [np.average(a, axis=1) if a.ndim == 2 else a for a in arrs]
         dt = arrs[0].dtype
         if dt not in _SRC_CODE or any(a.dtype != dt for a in arrs):
-            dt = np.dtype(np.float64) if dt not in _SRC_CODE else dt
-            arrs = [np.ascontiguousarray(a, dtype=dt) for a in arrs]
+            # mixed or unusual element types: everything becomes float32, int16 PCM scaled to [-1, 1) like the reader does (exact)
+            dt = np.dtype(np.float32)
+            arrs = [(a.astype(np.float32) * np.float32(1.0 / 32768.0)) if a.dtype == np.int16 else np.ascontiguousarray(a, dtype=np.float32) for a in arrs]
         if any(a.ndim != 1 for a in arrs):
             raise ValueError("expected mono 1-D waveforms (run 'avgchannel' first, datatrans.py:10-14)")
         arrs = [a if a.flags.c_contiguous else np.ascontiguousarray(a) for a in arrs]

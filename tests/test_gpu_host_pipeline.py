@@ -66,6 +66,9 @@ def test_collate_input_types_and_prefetch(lasr_b200):
         a = col(w16)["wav_array"].clone()
         b = col([x.astype(np.float32) / 32768.0 for x in w16])["wav_array"]
         assert torch.equal(a, b)                                  # (float)s16 == float sample * 2^15 exactly
+    mixed = [pcm[0][0], b64[0][1].astype(np.float32), (pcm[0][2].astype(np.float64) / 32768.0)]      # int16 + float32 + float64 in one list
+    want_mixed = col([pcm[0][0].astype(np.float32) / 32768.0, b64[0][1].astype(np.float32), pcm[0][2].astype(np.float32) / 32768.0])["wav_array"].clone()
+    assert torch.equal(col(mixed)["wav_array"], want_mixed)
     outs = [d["wav_array"].clone() for d in col.prefetch(b64)]
     assert len(outs) == len(want) and all(torch.equal(a, b) for a, b in zip(outs, want))
     dev_col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=False)
