@@ -181,7 +181,9 @@ typedef struct b200fe_fbank_args {
     /* Lock-step streaming: non-zero promises that EVERY utterance of this call yields exactly max_frames frames
      * (d_nsamp[u] in [(max_frames-1)*shift + window, max_frames*shift + window) for all u).  With max_frames <= 16 the
      * fused kernel then packs several utterances into one 32-frame tile (8 streams x 4 frames for a 40 ms push).
-     * Ignored together with peak normalisation, statistics, masks, per-utterance CMVN, dither or a tile table. */
+     * Ignored together with peak normalisation, statistics, masks, per-utterance CMVN, dither or a tile table.
+     * 2 = the weaker promise "AT MOST max_frames frames each" (independent streams, b200fe_stream_push): tiles are shared the
+     * same way, frame slots without a frame are masked and their output rows are zero. */
     int uniform_frames;
     /* Packed feature output: [batch] first output ROW of every utterance, ascending; d_out is then
      * [sum of frames][num_mel_bins] with no padding rows (utterance u occupies rows [d_out_offsets[u],

@@ -916,6 +916,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         const int upt = std::min(kFT / g->max_frames, p->multi_tile_floats / span);
         if (upt >= 2) {
             a.multi_fpu = g->max_frames; a.multi_upt = upt; a.multi_span = span;
+            a.multi_ragged = g->uniform_frames == 2 ? 1 : 0;
             a.ntiles = (g->batch + upt - 1) / upt;
             a.tile_floats = p->multi_tile_floats;
         }
@@ -1021,6 +1022,7 @@ extern "C" int b200fe_stream_push(b200fe_stream* st, const int* d_ids, int n, co
     a.d_wav = st->d_state; a.wav_stride = st->cap; a.d_wav_offsets = st->d_offsets; a.offsets_aligned = 1;
     a.d_nsamp = st->d_nsamp; a.batch = n; a.d_out = d_out; a.max_frames = max_out_frames;
     a.d_cmvn_mean = d_cmvn_mean; a.d_cmvn_istd = d_cmvn_istd; a.cmvn_stride = 0;
+    a.uniform_frames = 2;          // every stream yields AT MOST max_out_frames frames: several streams share one 32-frame tile
     const int rc = b200fe_fbank_fused(p, &a, stream);
     if (rc != B200FE_OK) return rc;
     stream_advance_kernel<<<n, 128, 0, cs>>>(st->d_state, st->d_fill, st->cap, st->n_streams, d_ids, st->d_nsamp, p->win, p->shift);

@@ -146,6 +146,7 @@ struct FbankArgs {
     // multi-utterance tiles (lock-step streaming: every utterance yields exactly Tmax = multi_fpu frames): a tile takes
     // multi_upt consecutive utterances, multi_fpu frames each; utterance j's samples sit at j * multi_span in the tile buffer
     int multi_fpu, multi_upt, multi_span;
+    int multi_ragged;               // 1: an utterance may yield FEWER than multi_fpu frames (independent streams): per-slot validity mask
     // utterance CMVN inside the launch (apply tiles of the work list; lean instantiation only)
     int apply_mode;                 // 0 off, 1 mean, 2 mean + variance
     int* utt_done;                  // [B] frame tiles of the utterance whose features and statistics are globally visible; [B] = error flag
@@ -205,6 +206,7 @@ static __device__ long long g_timeline[296][8][kTlTiles][kTlStamps];   // one co
 #endif
 
 struct TileGeom {
+    unsigned mask;                  // multi-utterance tiles: bit fl = frame slot fl holds a real frame
     int utt, f0, nvalid, nrows, T;
     bool apply, ready;
 };
@@ -655,7 +657,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         if (id < ntiles) {
             if (multi) {                                    // the tile's utterances form one run of consecutive output rows
                 d.utt = id * a.multi_upt;
-                d.T = a.multi_fpu * min(a.multi_upt, a.B - d.utt);
+                const int nu = min(a.multi_upt, a.B - d.utt);
+                d.T = a.multi_fpu * nu;
+                unsigned m = 0xffffffffu;               // f0 (always 0 for these tiles) carries the mask of valid frame slots
+                if (a.multi_ragged) {
+                    m = 0u;
+                    for (int j = 0; j < nu; ++j) {
+                        const unsigned n = (unsigned)__ldg(a.nsamp + d.utt + j);
+                        const int Tj = n >= (unsigned)a.win ? min((int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift), a.multi_fpu) : 0;
+                        m |= ((1u << Tj) - 1u) << (j * a.multi_fpu);
+                    }
+                }
+                d.f0 = (int)m;
                 return d;
             }
             if (dyn) { const int2 e = __ldg(a.tile_table + id); d.utt = e.x; d.f0 = e.y; }
@@ -674,7 +687,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     };
     auto geom = [&](const Desc& d) -> TileGeom {
         TileGeom g;
-        g.utt = d.utt; g.f0 = d.f0; g.T = d.T; g.apply = false; g.ready = false;
+        g.utt = d.utt; g.f0 = d.f0; g.T = d.T; g.apply = false; g.ready = false; g.mask = 0xffffffffu;
+        if (multi) {                 // slots of consecutive utterances; which of them hold frames says the mask
+            g.f0 = 0; g.mask = (unsigned)d.f0;
+            g.nvalid = min(max(d.T, 0), kFT);
+            g.nrows = g.nvalid;
+            return g;
+        }
         if (kApply && (d.utt & kApplyBit)) {   // CMVN-apply tile: no frames, no padding rows; handled after the phase-C block
             g.utt = d.utt & ~(kApplyBit | kReadyBit); g.nvalid = 0; g.nrows = 0; g.apply = true; g.ready = (d.utt & kReadyBit) != 0;
             return g;
@@ -694,9 +713,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         const int esz = kI16 ? 2 : 4;
         if (multi) {
             const int nu = g.nvalid / a.multi_fpu;
-            const uint32_t bytes = (uint32_t)((((a.multi_fpu - 1) * a.shift + a.win) * esz + 15) & ~15);
-            mbar_expect_tx(&bars[stage], bytes * (uint32_t)nu);
+            uint32_t total = 0;
             for (int j = 0; j < nu; ++j) {
+                const int Tj = __popc((g.mask >> (j * a.multi_fpu)) & ((1u << a.multi_fpu) - 1u));
+                if (Tj > 0) total += (uint32_t)((((Tj - 1) * a.shift + a.win) * esz + 15) & ~15);
+            }
+            mbar_expect_tx(&bars[stage], total);          // (a tile whose streams all delivered nothing completes with 0 bytes)
+            for (int j = 0; j < nu; ++j) {
+                const int Tj = __popc((g.mask >> (j * a.multi_fpu)) & ((1u << a.multi_fpu) - 1u));
+                if (Tj <= 0) continue;
+                const uint32_t bytes = (uint32_t)((((Tj - 1) * a.shift + a.win) * esz + 15) & ~15);
                 const long long eoff = a.wav_offsets ? __ldg(a.wav_offsets + g.utt + j) : (long long)(g.utt + j) * a.wav_stride;
                 tma_load_1d(smem + L.tile_off[stage] + (size_t)j * a.multi_span * esz, reinterpret_cast<const char*>(a.wav) + eoff * esz, bytes, &bars[stage]);
             }
@@ -764,8 +790,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         } else if (nvalid > 0) {
             // generic path (unaligned base / stride): cooperative coalesced loads
             const int nu = multi ? nvalid / a.multi_fpu : 1;
-            const int nsmp = ((multi ? a.multi_fpu : nvalid) - 1) * a.shift + a.win;
             for (int j = 0; j < nu; ++j) {
+                const int Tj = multi ? __popc((g.mask >> (j * a.multi_fpu)) & ((1u << a.multi_fpu) - 1u)) : nvalid;
+                if (Tj <= 0) continue;
+                const int nsmp = (Tj - 1) * a.shift + a.win;
                 const long long eoff = (a.wav_offsets ? __ldg(a.wav_offsets + utt + j) : (long long)(utt + j) * a.wav_stride) + (long long)f0 * a.shift;
                 if (kI16) {
                     const short* src = reinterpret_cast<const short*>(a.wav) + eoff;
@@ -803,9 +831,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 const int slot = warp + kWarps * sub;
                 const int fl = kDual ? (8 * (warp >> 1) + 2 * (warp & 1) + 4 * h2)            // frames fl (a), fl + 1 (b)
                                      : ((slot & 3) + 8 * (slot >> 2) + 4 * h2);
-                const bool fvalid = fl < nvalid;
+                const bool fvalid = fl < nvalid && (!multi || ((g.mask >> fl) & 1u));
                 const bool last_pass = kDual || sub == 1;
-                if (fl - 4 * h2 >= nvalid) {
+                // (ragged multi-utterance tiles: a warp whose two half-warps hold no real frame skips the pass as well)
+                const unsigned wm = multi ? (g.mask >> (fl - 4 * h2)) : 0xffffffffu;
+                if (fl - 4 * h2 >= nvalid || (multi && ((wm | (wm >> 4) | (kDual ? ((wm >> 1) | (wm >> 5)) : 0u)) & 1u) == 0u)) {
                     if (kEarlyTma && last_pass && a.use_tma && lane == 0) mbar_arrive(&bars[kStages]);
                 } else {
                     float2 v[16];
@@ -818,7 +848,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     // sample offset of the frame inside the tile buffer (multi-utterance tiles: slot -> (utterance, frame))
                     int foff = fl * a.shift;
                     if (multi) { const int uj = fl / a.multi_fpu; foff = uj * a.multi_span + (fl - uj * a.multi_fpu) * a.shift; }
-                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + foff + l, xs + foff + a.shift + l, wls, fc, l, fl + 1 < nvalid);
+                    if (kDual) load_frame_dual<NLOAD, kPeak, !kStaticMel>(v, xs + foff + l, xs + foff + a.shift + l, wls, fc, l,
+                                                                          fl + 1 < nvalid && (!multi || ((g.mask >> (fl + 1)) & 1u)));
                     else if (kI16) load_frame_single_i16<NLOAD, kPeak>(v, reinterpret_cast<const short*>(xs) + foff + 2 * l, wl, fc, l);
                     else load_frame_single<NLOAD, kPeak, !kStaticMel>(v, xs + foff + 2 * l, wl, fc, l);
                     if (kEarlyTma && last_pass && a.use_tma) {
@@ -836,7 +867,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     float* pa = prow + l;                                                              // k = l + 16 r
                     if (kDual) {
                         // ---- separate the two real spectra; |2 Xa|^2 and |2 Xb|^2 (0.25 folded in the mel weights)
-                        const bool bvalid = fl + 1 < nvalid;
+                        const bool bvalid = fl + 1 < nvalid && (!multi || ((g.mask >> (fl + 1)) & 1u));
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             const float2 bcj = make_float2(rc[r].x, -rc[r].y);
@@ -997,7 +1028,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                     const float cm = affine ? s_mean[col] : 0.f, ci = affine ? s_istd[col] : 1.f;
                     // zero masks (replace_with_zero): the column bit is fixed per thread, row k of the thread is rg + k * parts
                     const bool colz = !kLean && zmask && ((s_cmask[col >> 5] >> (col & 31)) & 1u);
-                    const unsigned rowz = (!kLean && zmask) ? (colz ? 0xffffffffu : s_cmask[4]) >> rg : 0u;
+                    // rows of a ragged multi-utterance tile that hold no frame are written as zeros (the padded rows of their utterance)
+                    const unsigned rowz = (((!kLean && zmask) ? (colz ? 0xffffffffu : s_cmask[4]) : 0u) | (multi ? ~g.mask : 0u)) >> rg;
                     float pivot = 0.f, s1 = 0.f, s2 = 0.f;
                     int cnt = 0;
                     if (kStaticMel && nvalid == kFT) {
@@ -1057,7 +1089,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
 #pragma unroll
                     for (int i = 0; i < kPer; ++i) { const int e = tid + i * kThreads; x[i] = outs[e + e / B200FE_STATIC_NMEL]; }
 #pragma unroll
-                    for (int i = 0; i < kPer; ++i) obase[tid + i * kThreads] = fast_log(fmaxf(x[i], lf));
+                    for (int i = 0; i < kPer; ++i) {
+                        float y = fast_log(fmaxf(x[i], lf));
+                        if (multi && !((g.mask >> ((tid + i * kThreads) / B200FE_STATIC_NMEL)) & 1u)) y = 0.f;
+                        obase[tid + i * kThreads] = y;
+                    }
                 } else if (kStaticMel && a.use_log != 0 && !zmask && !affine && wb && nvalid == kFT) {
                     // full tile in statistics mode (utterance CMVN is applied by the post pass): same ten chains, the
                     // log-mel values are also written back for the column reducers
@@ -1081,6 +1117,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                             float* sp = outs + e + row;
                             float x = fast_log(fmaxf(*sp, lf));
                             x = (x - s_mean[col]) * s_istd[col];
+                            if (multi && !((g.mask >> row) & 1u)) x = 0.f;
                             if (obase) obase[e] = x;
                             if (wb) *sp = x;
                         }
@@ -1089,7 +1126,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                         for (int e = tid; e < nv; e += kThreads) {
                             const int row = e / nmel;
                             float* sp = outs + e + row;
-                            const float x = fast_log(fmaxf(*sp, lf));
+                            float x = fast_log(fmaxf(*sp, lf));
+                            if (multi && !((g.mask >> row) & 1u)) x = 0.f;
                             if (obase) obase[e] = x;
                             if (wb) *sp = x;
                         }
@@ -1105,6 +1143,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                         if (lg) x = fast_log(fmaxf(x, lf));
                         if (affine) x = (x - s_mean[col]) * s_istd[col];
                         if (zmask && (((rmask >> row) & 1u) || ((s_cmask[col >> 5] >> (col & 31)) & 1u))) x = 0.f;
+                        if (multi && !((g.mask >> row) & 1u)) x = 0.f;
                         if (obase) obase[e] = x;
                         if (wb) *sp = x;
                     }
@@ -1121,7 +1160,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             }
         }
         if (multi) {
-            if (a.out_len != nullptr && tid * a.multi_fpu < nvalid) a.out_len[utt + tid] = a.multi_fpu;
+            if (a.out_len != nullptr && tid * a.multi_fpu < nvalid)
+                a.out_len[utt + tid] = __popc((g.mask >> (tid * a.multi_fpu)) & ((1u << a.multi_fpu) - 1u));
         } else if (a.out_len != nullptr && f0 == 0 && nrows > 0 && tid == 0) a.out_len[utt] = g.T;
         if (a.stats != nullptr && nvalid > 0 && !stats_fused) {
             // Column statistics of what phase C wrote back into the staging tile.  thread = (column j, row
