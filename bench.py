@@ -566,7 +566,8 @@ def other_config(args, rank, world, dev, peak_gbs, peak_src, real_stdout, barrie
         r = bc.run_c1(dev, steps=max(args.steps, 20), warmup=args.warmup)
         base.update(value=r["value"], ms_per_step=r["ms_per_step"], config={"workload": r["workload"], "note": r["note"]}, e2e=r["e2e"], gpu_launches=2 * args.steps,
                     roofline={"bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": r["achieved_gbs"] / peak_gbs, "traffic": None,
-                              "peak_source": peak_src, "algorithmic_bytes_per_step": r["algorithmic_bytes"], "kernel": "whole step (list builder + one fused launch)"})
+                              "peak_source": peak_src, "algorithmic_bytes_per_step": r["algorithmic_bytes"], "kernel": "whole step (list builder + one fused launch)"},
+                    extra={"gpu_transform_latency_10s_utterance": r["gpu_transform_latency_10s_utterance"]})
         if rank == 0 and not args.no_cpu_baseline:
             t = cpu_baseline.time_chain(bc.c1_inputs(), SR, "none", False, cores, min_seconds=10.0)
             cpu = {"value": t["value"], "unit": "audio-h/s", "cores": cores, "kind": "port", "sample": "%d x the C1 batch in %.1f s, fbank:80 via live torchaudio + batch_list" % (t["reps"], t["seconds"])}
