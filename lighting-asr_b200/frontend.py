@@ -570,10 +570,7 @@ class GpuFbankFrontend(torch.nn.Module):
         m_np, b_np, w_np = _specaug.plan_batch(T_host, D, return_warp=True, **self.sa)
         n_f, n_t = self.sa["n_freq_mask"], self.sa["n_time_mask"]
         n_cls = 2 * n_t + 1
-        masks_dev = _h2d(m_np, dev)
-        bounds_dev = _h2d(b_np, dev)
-        warp_dev = _h2d(w_np, dev)
-        len_dev = _h2d(len_host, dev)
+        masks_dev, bounds_dev, warp_dev, len_dev = _h2d_many([m_np, b_np, w_np, len_host], dev)     # one upload (each costs ~80 us of host time)
         if out is not None:
             if out.shape != pre.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() == pre.data_ptr():
                 raise ValueError("out must be a distinct contiguous float32 (B, Tmax, D) tensor")
