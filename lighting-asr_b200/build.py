@@ -49,8 +49,8 @@ def _extra():
 
 
 def needs_build():
-    if os.environ.get("B200FE_LIB"):
-        return not os.path.exists(LIB)
+    if os.environ.get("B200FE_LIB") and __name__ != "__main__":
+        return not os.path.exists(LIB)              # a variant library is used as built (the GPU box must not rebuild it)
     return any(_stale(LIB, deps) for _, _, _, deps in _units())
 
 

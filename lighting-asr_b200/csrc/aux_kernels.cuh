@@ -435,6 +435,8 @@ struct WarpArgs {
     long long stats_stride;
     const int* row_bounds;
     int n_cls;
+    int win_rows;                // source rows the dynamic shared memory holds as float64 (0 = no staging)
+    int part_ok;                 // the dynamic shared memory holds 2 * min(1024 / nmel, kWarpRows) * nmel floats for the statistics partials
 };
 
 __device__ __forceinline__ double pil_bicubic(double x)
@@ -446,36 +448,73 @@ __device__ __forceinline__ double pil_bicubic(double x)
 }
 
 #ifndef B200FE_WARP_ROWS
-#define B200FE_WARP_ROWS 64       // measured on B200 (C3 full specaug step): 32 rows 0.637 ms, 64 rows 0.605 ms (128 exceed the static + dynamic shared-memory limit)
+#define B200FE_WARP_ROWS 64       // C3 full specaug step on B200: 32 rows 0.595 ms, 48 rows 0.630, 64 rows 0.576 (v5, 5 CTAs per SM)
+#endif
+#ifndef B200FE_WARP_OCC
+#define B200FE_WARP_OCC 5
 #endif
 constexpr int kWarpRows = B200FE_WARP_ROWS;    // output rows per CTA
 constexpr int kWarpTaps = 16;    // taps per output row: xmax - xmin <= min(in_size, 2 * support + 1); with |in - out| <= W (max_time_warp, 5 in the
                                  // reference) a scale above 2 needs out < W, i.e. in < 2 W, so 16 taps cover W <= 8 (larger windows are clipped as before)
+#ifndef B200FE_WARP_STAGE
+#define B200FE_WARP_STAGE 1
+#endif
+constexpr bool kWarpStage = B200FE_WARP_STAGE != 0;
+constexpr int kWarpWinExtra = 20;   // source rows staged per CTA beyond kWarpRows: 2 x (|center - warped| <= 5 in the reference's setting, + 5 for the support)
 
-// Work split (second version; the first spent 218 thread-instructions per output cell, most of them in the coefficient
-// set-up that 32 of 256 threads ran alone): (1) 32 threads derive the tap window of their output row (one float64 division
-// per row); (2) ALL threads evaluate the raw bicubic coefficients, one (row, tap) pair each; (3) 32 threads add a row's
-// coefficients in Pillow's order (the sum's rounding depends on it), (4) all threads normalise, one division per pair;
-// (5) thread = (row, 4 columns): 128-bit loads of the source taps, float64 multiply and add per tap in source order, one
-// rounding to float32, 128-bit store; (6) statistics from the shared-memory copy of the tile: thread = (row third, column),
-// row classes looked up once per row.
-__global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
+// Work split (fifth version).  History: v1 spent 218 thread-instructions per output cell in a coefficient set-up that 32 of 256
+// threads ran alone; v2 (parallel set-up, 128-bit taps) 174 us on C3; its ncu capture (profiles/r03_ncu_time_warp.json) shows the
+// XU pipe -- the float32 -> float64 converter, one conversion per tap and output cell, 64-bit results at half rate -- as the
+// limiter ("xu_realtime" 209 %), which is why halving the set-up / statistics instructions and prefetching taps changed nothing.
+// A second capture after those cuts (98 M instead of 125 M warp instructions, yet 184 us) settled it: the kernel waits for its tap
+// loads (long-scoreboard stalls 7.3 per issue), and neither more loads in flight per thread (66-80 registers: fewer warps, slower)
+// nor a float64 copy of the source rows in shared memory (twice the shared-memory bytes per tap, slower) pays.  v5: (0) thread 0
+// requests the CTA's source rows -- [r0 - m, r0 + rows + m), contiguous in memory -- with ONE bulk copy (cp.async.bulk, mbarrier)
+// before anything else; (1) one thread per output row derives its tap window (one float64 division per row); (2) one warp
+// compacts the live (row, tap) pairs; (3) raw bicubic coefficients, one live pair per thread; (4) one thread per row adds them in
+// Pillow's order (the sum's rounding depends on it); (5) one division per live pair; (6) wait for the copy (it has had the whole
+// set-up to land); thread = (row slot, 4 columns): 128-bit taps from shared memory, float64 multiply and add per tap in source
+// order, one rounding to float32, 128-bit store; (7) statistics from the rows just written (same CTA, after a barrier): float32
+// partial sums per (row slot, column), added in float64 in a fixed order, one atomic per (moment, column).
+__global__ void __launch_bounds__(256, B200FE_WARP_OCC) time_warp_kernel(const WarpArgs a)
 {
     const int utt = blockIdx.y;
     const long long n = a.nsamp[utt];
     const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
     const int r0 = blockIdx.x * kWarpRows;
     if (r0 >= a.Tmax) return;
-    __shared__ double s_k[kWarpRows][kWarpTaps];
+    __shared__ __align__(16) double s_k[kWarpRows][kWarpTaps];
     __shared__ double s_c[kWarpRows], s_ss[kWarpRows], s_ww[kWarpRows];
-    __shared__ int s_ymin[kWarpRows], s_n[kWarpRows], s_xmin[kWarpRows], s_cls[kWarpRows];
-    extern __shared__ float s_tile[];              // [kWarpRows][nmel + 1]
+    __shared__ int s_ymin[kWarpRows], s_n[kWarpRows], s_xmin[kWarpRows], s_cls[kWarpRows], s_npairs;
+    __shared__ unsigned short s_pair[kWarpRows * kWarpTaps];
+    extern __shared__ __align__(16) float s_win[];               // [win_rows][nmel]: the CTA's source rows (one bulk copy); later the statistics partials
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x;
     const int center = a.warp[2 * utt], warped = a.warp[2 * utt + 1];
     const float* src = a.in + (long long)utt * a.Tmax * a.nmel;
     float* dst = a.out + (long long)utt * a.Tmax * a.nmel;
     const int nb = a.n_cls - 1;
     const int* bounds = (a.stats != nullptr && a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
+    const int nvalid = min(max(T - r0, 0), kWarpRows);            // rows of this CTA that hold frames
+    const int nq = a.nmel >> 2;
+    const bool vec = (a.nmel & 3) == 0 && nq <= 256 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    // Source window of the CTA, requested before anything else so that the copy flies during the coefficient set-up: an output
+    // row's taps lie within |center - warped| + 1/2 rows of the row itself plus the filter support (2 x scale, scale ~ 1), so
+    // [r0 - m, r0 + rows + m) with m = |center - warped| + 5 holds them; a row whose taps fall outside after all (checked per
+    // row) reads global memory.
+    int w0 = 0, wn = 0;
+    if (vec && a.win_rows > 0 && nvalid > 0) {
+        const int m = (center >= 0 ? abs(center - warped) : 0) + 5;
+        w0 = max(r0 - m, 0);
+        wn = min(min(r0 + nvalid + m, T) - w0, a.win_rows);
+    }
+    if (tid == 0 && wn > 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t bytes = (uint32_t)wn * a.nmel * sizeof(float);
+        mbar_expect_tx(&s_bar, bytes);
+        tma_load_1d(s_win, src + (long long)w0 * a.nmel, bytes, &s_bar);
+    }
     if (tid < kWarpRows) {
         const int row = r0 + tid;
         int ymin = row, cnt = 1, xmin = 0;
@@ -507,9 +546,27 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
         if (cnt > 0) s_k[tid][0] = 1.0;
     }
     __syncthreads();
-    for (int i = tid; i < kWarpRows * kWarpTaps; i += 256) {
-        const int r = i / kWarpTaps, x = i - r * kWarpTaps;
-        if (x < -s_n[r]) s_k[r][x] = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + s_xmin[r]), s_c[r]), 0.5), s_ss[r]));
+    // one warp lists the (row, tap) pairs that need a coefficient, so that the float64 divisions below run on full warps (a
+    // row has 5-6 of the 16 tap slots in use; mapping slots to threads directly left two thirds of every warp idle)
+    if (tid < 32) {
+        int base = 0;
+        for (int c = 0; c < kWarpRows; c += 32) {
+            const int r = c + tid;
+            const int cr = r < kWarpRows ? max(-s_n[r], 0) : 0;
+            int inc = cr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+            const int off = base + inc - cr;
+            for (int x = 0; x < cr; ++x) s_pair[off + x] = (unsigned short)((r << 4) | x);
+            base += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) s_npairs = base;
+    }
+    __syncthreads();
+    const int np = s_npairs;
+    for (int i = tid; i < np; i += 256) {
+        const int r = s_pair[i] >> 4, x = s_pair[i] & 15;
+        s_k[r][x] = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + s_xmin[r]), s_c[r]), 0.5), s_ss[r]));
     }
     __syncthreads();
     if (tid < kWarpRows && s_n[tid] < 0) {
@@ -518,34 +575,44 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
         s_ww[tid] = ww;
     }
     __syncthreads();
-    for (int i = tid; i < kWarpRows * kWarpTaps; i += 256) {
-        const int r = i / kWarpTaps, x = i - r * kWarpTaps;
-        if (x < -s_n[r] && s_ww[r] != 0.0) s_k[r][x] = s_k[r][x] / s_ww[r];
+    for (int i = tid; i < np; i += 256) {
+        const int r = s_pair[i] >> 4, x = s_pair[i] & 15;
+        if (s_ww[r] != 0.0) s_k[r][x] = s_k[r][x] / s_ww[r];
     }
     __syncthreads();
-    const int ostride = a.nmel + 1;
-    const bool vec = (a.nmel & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    if (wn > 0) mbar_wait(&s_bar, 0);                              // initialised before the first barrier above; the copy has had the whole set-up to land
     if (vec) {
-        const int nq = a.nmel >> 2;
-        for (int e = tid; e < kWarpRows * nq; e += 256) {
-            const int r = e / nq, q = e - r * nq, row = r0 + r;
-            if (row >= a.Tmax) break;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < T) {
-                const int ymin = s_ymin[r], cnt = abs(s_n[r]);
-                const float4* sp = reinterpret_cast<const float4*>(src + (long long)ymin * a.nmel) + q;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                for (int y = 0; y < cnt; ++y) {
-                    const float4 p = __ldg(sp + (long long)y * nq);
-                    const double k = s_k[r][y];
-                    a0 = __dadd_rn(a0, __dmul_rn((double)p.x, k)); a1 = __dadd_rn(a1, __dmul_rn((double)p.y, k));
-                    a2 = __dadd_rn(a2, __dmul_rn((double)p.z, k)); a3 = __dadd_rn(a3, __dmul_rn((double)p.w, k));
+        const int slots = 256 / nq, slot = tid / nq, q = tid - slot * nq;      // thread = (row slot, 4 columns): no division in the row loop
+        if (slot < slots) {
+            for (int r = slot; r < kWarpRows; r += slots) {
+                const int row = r0 + r;
+                if (row >= a.Tmax) break;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < T) {
+                    const int cnt = abs(s_n[r]), ymin = s_ymin[r];
+                    const double* kp = s_k[r];
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    if (ymin >= w0 && ymin + cnt <= w0 + wn) {
+                        const float4* sp = reinterpret_cast<const float4*>(s_win + (ymin - w0) * a.nmel) + q;
+                        for (int y = 0; y < cnt; ++y, sp += nq) {
+                            const float4 p = *sp;
+                            const double k = kp[y];
+                            a0 = __dadd_rn(a0, __dmul_rn((double)p.x, k)); a1 = __dadd_rn(a1, __dmul_rn((double)p.y, k));
+                            a2 = __dadd_rn(a2, __dmul_rn((double)p.z, k)); a3 = __dadd_rn(a3, __dmul_rn((double)p.w, k));
+                        }
+                    } else {
+                        const float4* sp = reinterpret_cast<const float4*>(src + (long long)ymin * a.nmel) + q;
+                        for (int y = 0; y < cnt; ++y, sp += nq) {
+                            const float4 p = __ldg(sp);
+                            const double k = kp[y];
+                            a0 = __dadd_rn(a0, __dmul_rn((double)p.x, k)); a1 = __dadd_rn(a1, __dmul_rn((double)p.y, k));
+                            a2 = __dadd_rn(a2, __dmul_rn((double)p.z, k)); a3 = __dadd_rn(a3, __dmul_rn((double)p.w, k));
+                        }
+                    }
+                    v = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
                 }
-                v = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+                reinterpret_cast<float4*>(dst + (long long)row * a.nmel)[q] = v;
             }
-            reinterpret_cast<float4*>(dst + (long long)row * a.nmel)[q] = v;
-            float* tp = s_tile + r * ostride + 4 * q;
-            tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w;
         }
     } else {
         for (int e = tid; e < kWarpRows * a.nmel; e += 256) {
@@ -559,30 +626,56 @@ __global__ void __launch_bounds__(256) time_warp_kernel(const WarpArgs a)
                 v = (float)acc;
             }
             dst[(long long)row * a.nmel + col] = v;
-            s_tile[r * ostride + col] = v;
         }
     }
     if (a.stats == nullptr) return;
-    __syncthreads();
-    const int nvalid = min(max(T - r0, 0), kWarpRows);
+    __syncthreads();                                               // the CTA's rows of `dst` are visible to all of its threads from here on
     if (nvalid <= 0) return;
     double* sb = a.stats + (long long)utt * a.stats_stride;
-    const int parts = max(1, min(256 / a.nmel, 3));
-    const int part = tid / a.nmel, j = tid - part * a.nmel;
-    if (part >= parts) return;
-    const int rb = (nvalid * part) / parts, re = (nvalid * (part + 1)) / parts;
-    if (re <= rb) return;
-    int cls = s_cls[rb];
-    double s1 = 0.0, s2 = 0.0;
-    for (int fr = rb; fr < re; ++fr) {
-        const int cc = s_cls[fr];
-        if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
-        const double x = (double)s_tile[fr * ostride + j];
-        s1 += x;
-        s2 = fma(x, x, s2);
+    const float* orow = dst + (long long)r0 * a.nmel;
+    if (vec && a.part_ok && s_cls[0] == s_cls[nvalid - 1]) {
+        // all rows of this CTA lie in one SpecAugment row class (row classes ascend with the row, so first == last says so; true
+        // for all but a handful of CTAs per utterance): thread = (row slot, 4 columns) as in the main loop -- it reads back its own
+        // stores -- float32 partial sums over its <= ceil(rows / slots) rows, partials through the source window (idle since
+        // the barrier above), then one thread per (moment, column) adds the slots' partials in float64, in a fixed order.
+        const int slots = 256 / nq, slot = tid / nq, q = tid - slot * nq;
+        const int used = min(slots, nvalid);                          // slots that own a row
+        float* part1 = s_win;                                         // [used][nmel]
+        float* part2 = part1 + min(slots, kWarpRows) * a.nmel;        // [used][nmel]; the host sizes the buffer for 2 * min(slots, kWarpRows) * nmel floats
+        if (slot < used) {
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+            for (int r = slot; r < nvalid; r += slots) {
+                const float4 v = reinterpret_cast<const float4*>(orow + (long long)r * a.nmel)[q];
+                s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+                s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+            }
+            *reinterpret_cast<float4*>(part1 + slot * a.nmel + 4 * q) = s1;
+            *reinterpret_cast<float4*>(part2 + slot * a.nmel + 4 * q) = s2;
+        }
+        __syncthreads();
+        const int cls = s_cls[0];
+        for (int i = tid; i < 2 * a.nmel; i += 256) {
+            const int m = i >= a.nmel, j = i - m * a.nmel;
+            const float* pp = (m ? part2 : part1) + j;
+            double acc = 0.0;
+            for (int k = 0; k < used; ++k) acc += (double)pp[k * a.nmel];
+            atomicAdd(sb + (long long)(m ? a.n_cls : cls) * a.nmel + j, acc);
+        }
+        return;
     }
-    atomicAdd(sb + (long long)cls * a.nmel + j, s1);
-    atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
+    for (int j = tid; j < a.nmel; j += 256) {                      // a class boundary inside the CTA's rows, or an odd layout: one thread per column
+        int cls = s_cls[0];
+        double s1 = 0.0, s2 = 0.0;
+        for (int fr = 0; fr < nvalid; ++fr) {
+            const int cc = s_cls[fr];
+            if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
+            const double x = (double)orow[(long long)fr * a.nmel + j];
+            s1 += x;
+            s2 = fma(x, x, s2);
+        }
+        atomicAdd(sb + (long long)cls * a.nmel + j, s1);
+        atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
+    }
 }
 
 // Vectorised in-place post pass for num_mel_bins % 4 == 0: thread = (row slot, 4 columns), float4

@@ -1104,9 +1104,22 @@ extern "C" int b200fe_time_warp(const b200fe_plan* p, const b200fe_warp_args* g,
     a.n_cls = g->d_stats ? (g->n_row_classes > 0 ? g->n_row_classes : 1) : 1;
     if (a.n_cls > kMaxRowClasses) return fail(B200FE_EINVAL, "time_warp: too many row classes");
     dim3 grid((unsigned)((g->max_frames + kWarpRows - 1) / kWarpRows), (unsigned)g->batch);
-    const size_t smem = (size_t)kWarpRows * (p->nmel + 1) * sizeof(float);
+    // dynamic shared memory (static tables + this stay below 48 kB, no opt-in): the CTA's source rows when staging is compiled in
+    // and enough of them fit, else just the statistics partials; with neither, taps come from global memory and the statistics
+    // take the generic path
+    const size_t budget = 48 * 1024 - sizeof(double) * kWarpRows * (kWarpTaps + 3) - sizeof(int) * kWarpRows * 4 - 2 * kWarpRows * kWarpTaps - 2048;
+    size_t smem = 0;
+    if ((p->nmel & 3) == 0) {
+        const size_t rowb = (size_t)p->nmel * sizeof(float);
+        const size_t part = (size_t)2 * std::min(1024 / p->nmel, kWarpRows) * rowb;      // (row slots that own a row) x columns x 2 moments
+        const int fit = (int)std::min<size_t>(budget / rowb, (size_t)(kWarpRows + kWarpWinExtra));
+        if (kWarpStage && fit >= kWarpRows + 12 && (size_t)fit * rowb >= part) { a.win_rows = fit; a.part_ok = 1; smem = (size_t)fit * rowb; }
+        else if (part <= budget) { a.part_ok = 1; smem = part; }
+    }
     time_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(B200FE_ECUDA, "time_warp: launch failed: %s (grid %u x %u, %zu B dynamic shared memory, %d staged rows)", cudaGetErrorString(e), grid.x, grid.y, smem, a.win_rows);
     return B200FE_OK;
 }
 
