@@ -363,7 +363,8 @@ int b200fe_postpass(const b200fe_plan* plan, const b200fe_post_args* args, void*
  * accumulation, one rounding to float32) -- bit-identical to the reference.  (center, warped) are drawn on
  * the host with the reference's generator; center < 0 copies the utterance (T - W <= W, no draw).
  * Out of place: d_out gets the warped features (padded rows zero) and, optionally, their statistics in the
- * layout of b200fe_fbank_fused for the mean fills of the masks that follow. */
+ * layout of b200fe_fbank_fused for the mean fills of the masks that follow -- or the masked result itself
+ * (d_masks). */
 typedef struct b200fe_warp_args {
     unsigned int struct_size;    /* = sizeof(b200fe_warp_args) */
     const float* d_in;           /* [batch][max_frames][num_mel_bins] */
@@ -376,6 +377,14 @@ typedef struct b200fe_warp_args {
     long long stats_stride;
     const int* d_row_bounds;
     int n_row_classes;
+    /* Optional: the SpecAugment masks that follow the warp (specaugment.py:47-106), applied in the same launch by the CTA that
+     * completes an utterance -- fills derived as b200fe_postpass derives them (running mean of the current array, or zero),
+     * later masks win.  Needs d_stats (+ d_row_bounds for mean fills).  NULL = warp only (call b200fe_postpass for the masks). */
+    const int* d_masks;          /* [batch][n_freq_masks + n_time_masks][2] int32 (lo, hi) */
+    int n_freq_masks, n_time_masks;
+    float* d_fills;              /* [batch][n_freq_masks + n_time_masks] outputs */
+    int fill_zero;               /* 1 = replace_with_zero */
+    int* d_utt_done;             /* [batch] int32 workspace: zero before the first call, left zero by every call */
 } b200fe_warp_args;
 
 int b200fe_time_warp(const b200fe_plan* plan, const b200fe_warp_args* args, void* stream);

@@ -56,6 +56,7 @@ class WarpArgs(_Sized):
         ("struct_size", C.c_uint), ("d_in", C.c_void_p), ("d_out", C.c_void_p), ("d_nsamp", C.c_void_p), ("batch", C.c_int), ("max_frames", C.c_int),
         ("d_warp", C.c_void_p), ("d_stats", C.c_void_p), ("stats_stride", c_ll), ("d_row_bounds", C.c_void_p),
         ("n_row_classes", C.c_int),
+        ("d_masks", C.c_void_p), ("n_freq_masks", C.c_int), ("n_time_masks", C.c_int), ("d_fills", C.c_void_p), ("fill_zero", C.c_int), ("d_utt_done", C.c_void_p),
     ]
 
 

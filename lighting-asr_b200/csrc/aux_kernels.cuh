@@ -301,16 +301,17 @@ struct PostArgs {
     int inline_finalize;             // utterance CMVN without masks: the post pass derives the vectors itself (no finalize launch)
 };
 
-// One CTA (128 threads, thread d = mel column d) per utterance.
-__global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a)
+// One CTA of NT threads (thread d = mel column d; d >= num_mel_bins only helps in the reductions) per utterance.  Also the tail of
+// time_warp_kernel (NT = 256), which is why the statistics are read past L1.
+template <int NT>
+__device__ __forceinline__ void finalize_body(const PostArgs& a, const int utt, const int d)
 {
-    const int utt = blockIdx.x, d = threadIdx.x;
     const long long n = a.nsamp[utt];
     const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;
     const int nb = a.n_cls - 1;
     const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
     const double* sb = a.stats + (long long)utt * a.stats_stride;
-    __shared__ double red[4];
+    __shared__ double red[NT / 32];
     __shared__ int cls_lo[kMaxRowClasses + 1];
     if (d == 0) {
         cls_lo[0] = 0;
@@ -323,11 +324,11 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a)
     const bool col = d < a.nmel;
     if (col) {
         double tot = 0.0;
-        for (int c = 0; c < a.n_cls; ++c) { S[c] = sb[(long long)c * a.nmel + d]; tot += S[c]; }
+        for (int c = 0; c < a.n_cls; ++c) { S[c] = __ldcg(sb + (long long)c * a.nmel + d); tot += S[c]; }
         if (a.cmvn_mode != 0 && T > 0) {
             mean = tot / T;
             if (a.cmvn_mode == 2) {
-                double var = sb[(long long)a.n_cls * a.nmel + d] / T - mean * mean;
+                double var = __ldcg(sb + (long long)a.n_cls * a.nmel + d) / T - mean * mean;
                 istd = 1.0 / sqrt(var > 1e-20 ? var : 1e-20);
             }
             a.cm_mean[(long long)utt * a.nmel + d] = (float)mean;
@@ -347,7 +348,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a)
         __syncthreads();
         if ((d & 31) == 0) red[d >> 5] = v;
         __syncthreads();
-        return red[0] + red[1] + red[2] + red[3];
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) t += red[w];
+        return t;
     };
     double part = 0.0;
     for (int c = 0; c < a.n_cls; ++c) part += S[c];
@@ -380,6 +384,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a)
         if (d == 0) a.fills[(long long)utt * nm + i] = (float)fill;
     }
 }
+
+__global__ void __launch_bounds__(128) finalize_kernel(const PostArgs a) { finalize_body<128>(a, blockIdx.x, threadIdx.x); }
 
 // In-place post pass: rows of one utterance, thread = (row, column).  Applies utterance CMVN and
 // overwrites masked cells with the fill of the LAST mask that covers them (later masks overwrite
@@ -436,6 +442,11 @@ struct WarpArgs {
     const int* row_bounds;
     int n_cls;
     int win_rows;                // source rows the dynamic shared memory holds as float64 (0 = no staging)
+    const int* masks;            // optional: SpecAugment masks applied by the CTA that completes an utterance (finalize + fill in this launch)
+    int n_fmask, n_tmask;
+    float* fills;
+    int fill_zero;
+    int* done;                   // [B] completion counters, zero on entry, zero again on exit
     int part_ok;                 // the dynamic shared memory holds 2 * min(1024 / nmel, kWarpRows) * nmel floats for the statistics partials
 };
 
@@ -445,6 +456,67 @@ __device__ __forceinline__ double pil_bicubic(double x)
     if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, x), 2.5), x), x), 1.0);
     if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), -0.5);
     return 0.0;
+}
+
+// Tail of time_warp_kernel for the CTA that completes an utterance: fills as finalize_kernel derives them, then the masked cells.
+// (As a __noinline__ call it slowed the whole kernel -- C3 full step 0.552 -> 0.596 ms: 240 B of stack frame -- so it is inlined.)
+__device__ __forceinline__ void warp_mask_tail(const WarpArgs& a, const int utt, const int T, float* dst, const bool vec)
+{
+    const int tid = threadIdx.x;
+    const int nq = a.nmel >> 2;
+    PostArgs q;
+    q.feats = dst; q.nsamp = a.nsamp; q.B = a.B; q.Tmax = a.Tmax; q.nmel = a.nmel; q.win = a.win; q.shift = a.shift;
+    q.stats = a.stats; q.stats_stride = a.stats_stride; q.row_bounds = a.row_bounds; q.n_cls = a.n_cls;
+    q.cmvn_mode = 0; q.cm_mean = nullptr; q.cm_istd = nullptr;
+    q.masks = a.masks; q.n_fmask = a.n_fmask; q.n_tmask = a.n_tmask; q.fills = a.fills; q.fill_zero = a.fill_zero;
+    q.rows_per_cta = 0; q.feat_offsets = nullptr; q.inline_finalize = 0;
+    finalize_body<256>(q, utt, tid);
+    __syncthreads();                                               // the fills (written by thread 0) are visible to the CTA
+    const int nm = a.n_fmask + a.n_tmask;
+    const int* mk = a.masks + (long long)utt * nm * 2;
+    const float* fl = a.fills + (long long)utt * nm;
+    int tlo[kMaxTimeMasks], thi[kMaxTimeMasks];
+    float tfill[kMaxTimeMasks];
+#pragma unroll
+    for (int i = 0; i < kMaxTimeMasks; ++i) {
+        tlo[i] = 0; thi[i] = 0; tfill[i] = 0.f;
+        if (i < a.n_tmask) { tlo[i] = mk[2 * (a.n_fmask + i)]; thi[i] = mk[2 * (a.n_fmask + i) + 1]; tfill[i] = fl[a.n_fmask + i]; }
+    }
+    if (vec) {
+        const int slots = 256 / nq, slot = tid / nq, qd = tid - slot * nq;
+        if (slot >= slots) return;
+        int fhit[4] = {-1, -1, -1, -1};
+        float ffill[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < a.n_fmask; ++i) {
+            const int lo = mk[2 * i], hi = mk[2 * i + 1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * qd + c >= lo && 4 * qd + c < hi) { fhit[c] = i; ffill[c] = fl[i]; }
+        }
+        const bool anyf = fhit[0] >= 0 || fhit[1] >= 0 || fhit[2] >= 0 || fhit[3] >= 0;
+        const bool allf = fhit[0] >= 0 && fhit[1] >= 0 && fhit[2] >= 0 && fhit[3] >= 0;
+        for (int r = slot; r < T; r += slots) {
+            int thit = -1; float tf = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMaxTimeMasks; ++i) if (r >= tlo[i] && r < thi[i]) { thit = i; tf = tfill[i]; }
+            float* ptr = dst + (long long)r * a.nmel + 4 * qd;
+            if (thit >= 0) *reinterpret_cast<float4*>(ptr) = make_float4(tf, tf, tf, tf);
+            else if (allf) *reinterpret_cast<float4*>(ptr) = make_float4(ffill[0], ffill[1], ffill[2], ffill[3]);
+            else if (anyf) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (fhit[c] >= 0) ptr[c] = ffill[c];      // partial float4: no read-modify-write, the other cells stay as they are
+            }
+        }
+    } else {
+        for (long long e = tid; e < (long long)T * a.nmel; e += 256) {
+            const int r = (int)(e / a.nmel), d = (int)(e - (long long)r * a.nmel);
+            int hit = -1; float f = 0.f;
+            for (int i = 0; i < a.n_fmask; ++i) if (d >= mk[2 * i] && d < mk[2 * i + 1]) { hit = i; f = fl[i]; }
+#pragma unroll
+            for (int i = 0; i < kMaxTimeMasks; ++i) if (r >= tlo[i] && r < thi[i]) { hit = a.n_fmask + i; f = tfill[i]; }
+            if (hit >= 0) dst[e] = f;
+        }
+    }
 }
 
 #ifndef B200FE_WARP_ROWS
@@ -630,10 +702,9 @@ __global__ void __launch_bounds__(256, B200FE_WARP_OCC) time_warp_kernel(const W
     }
     if (a.stats == nullptr) return;
     __syncthreads();                                               // the CTA's rows of `dst` are visible to all of its threads from here on
-    if (nvalid <= 0) return;
     double* sb = a.stats + (long long)utt * a.stats_stride;
     const float* orow = dst + (long long)r0 * a.nmel;
-    if (vec && a.part_ok && s_cls[0] == s_cls[nvalid - 1]) {
+    if (nvalid > 0 && vec && a.part_ok && s_cls[0] == s_cls[nvalid - 1]) {
         // all rows of this CTA lie in one SpecAugment row class (row classes ascend with the row, so first == last says so; true
         // for all but a handful of CTAs per utterance): thread = (row slot, 4 columns) as in the main loop -- it reads back its own
         // stores -- float32 partial sums over its <= ceil(rows / slots) rows, partials through the source window (idle since
@@ -661,21 +732,39 @@ __global__ void __launch_bounds__(256, B200FE_WARP_OCC) time_warp_kernel(const W
             for (int k = 0; k < used; ++k) acc += (double)pp[k * a.nmel];
             atomicAdd(sb + (long long)(m ? a.n_cls : cls) * a.nmel + j, acc);
         }
-        return;
-    }
-    for (int j = tid; j < a.nmel; j += 256) {                      // a class boundary inside the CTA's rows, or an odd layout: one thread per column
-        int cls = s_cls[0];
-        double s1 = 0.0, s2 = 0.0;
-        for (int fr = 0; fr < nvalid; ++fr) {
-            const int cc = s_cls[fr];
-            if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
-            const double x = (double)orow[(long long)fr * a.nmel + j];
-            s1 += x;
-            s2 = fma(x, x, s2);
+    } else if (nvalid > 0) {
+        for (int j = tid; j < a.nmel; j += 256) {                  // a class boundary inside the CTA's rows, or an odd layout: one thread per column
+            int cls = s_cls[0];
+            double s1 = 0.0, s2 = 0.0;
+            for (int fr = 0; fr < nvalid; ++fr) {
+                const int cc = s_cls[fr];
+                if (cc != cls) { atomicAdd(sb + (long long)cls * a.nmel + j, s1); s1 = 0.0; cls = cc; }
+                const double x = (double)orow[(long long)fr * a.nmel + j];
+                s1 += x;
+                s2 = fma(x, x, s2);
+            }
+            atomicAdd(sb + (long long)cls * a.nmel + j, s1);
+            atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
         }
-        atomicAdd(sb + (long long)cls * a.nmel + j, s1);
-        atomicAdd(sb + (long long)a.n_cls * a.nmel + j, s2);
     }
+    if (a.done == nullptr) return;
+
+    // ---- SpecAugment masks in the same launch: the CTA whose arrival completes the utterance (its rows and statistics are all
+    // in L2 by then) derives the fills and overwrites the masked cells; later masks win, time masks come after frequency masks
+    // (specaugment.py applies them in that order).  Replaces a finalize launch and a mask-fill pass over the whole batch.
+    __shared__ int s_last;
+    __syncthreads();
+    if (tid == 0) {
+        // this CTA's rows and statistics before its arrival (cumulative over the barrier); fence.acq_rel, not __threadfence():
+        // the latter is a sequentially consistent fence plus an L1 invalidate, several times the cost on every CTA's tail
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        const int prev = atomicAdd(a.done + utt, 1);
+        s_last = prev == (int)gridDim.x - 1;
+        if (s_last) { a.done[utt] = 0; asm volatile("fence.acq_rel.gpu;" ::: "memory"); }   // every CTA of the utterance has arrived: the counter is free again
+    }
+    __syncthreads();
+    if (!s_last) return;
+    warp_mask_tail(a, utt, T, dst, vec);
 }
 
 // Vectorised in-place post pass for num_mel_bins % 4 == 0: thread = (row slot, 4 columns), float4

@@ -1103,6 +1103,12 @@ extern "C" int b200fe_time_warp(const b200fe_plan* p, const b200fe_warp_args* g,
     a.stats = g->d_stats; a.stats_stride = g->stats_stride; a.row_bounds = g->d_row_bounds;
     a.n_cls = g->d_stats ? (g->n_row_classes > 0 ? g->n_row_classes : 1) : 1;
     if (a.n_cls > kMaxRowClasses) return fail(B200FE_EINVAL, "time_warp: too many row classes");
+    if (g->d_masks) {
+        if (!g->d_stats || !g->d_fills || !g->d_utt_done) return fail(B200FE_EINVAL, "time_warp: masks need d_stats, d_fills and d_utt_done");
+        if (g->n_freq_masks < 0 || g->n_freq_masks > kMaxFreqMasks || g->n_time_masks < 0 || g->n_time_masks > kMaxTimeMasks)
+            return fail(B200FE_EINVAL, "time_warp: at most %d frequency and %d time masks", kMaxFreqMasks, kMaxTimeMasks);
+        a.masks = g->d_masks; a.n_fmask = g->n_freq_masks; a.n_tmask = g->n_time_masks; a.fills = g->d_fills; a.fill_zero = g->fill_zero; a.done = g->d_utt_done;
+    }
     dim3 grid((unsigned)((g->max_frames + kWarpRows - 1) / kWarpRows), (unsigned)g->batch);
     // dynamic shared memory (static tables + this stay below 48 kB, no opt-in): the CTA's source rows when staging is compiled in
     // and enough of them fit, else just the statistics partials; with neither, taps come from global memory and the statistics

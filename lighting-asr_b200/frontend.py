@@ -7,6 +7,7 @@ constructor and produces the batch layout of ``AudioDataSet.MergeBatch``
 used for device memory and streams only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -236,6 +237,9 @@ class GpuFbankFrontend(torch.nn.Module):
         # are queued `apply_lag` utterances after its frame tiles.  Opt-in: measured on B200 (C2) at 0.380 ms per step against
         # 0.382 ms for the post pass -- an apply tile costs its CTA about 5 us without FFT work.
         self.inlaunch_cmvn = False
+        # time-warp path: masks applied inside the warp launch (False, or B200FE_FUSE_WARP_MASKS=0 for A/B runs: finalize + post pass launches)
+        self.fuse_warp_masks = os.environ.get("B200FE_FUSE_WARP_MASKS", "1") != "0"
+        self._warp_done = {}             # device -> int32 completion counters of the warp launch (left zero by every call)
         self.apply_lag = 64
         self.overlap_calls = True       # extract_host: the H2D copies of the next call may start before this call's D2H tail ends
         self.kernel_d2h = True
@@ -584,6 +588,17 @@ class GpuFbankFrontend(torch.nn.Module):
         w = _lib.WarpArgs()
         w.d_in, w.d_out, w.d_nsamp, w.batch, w.max_frames = _ptr(pre), _ptr(feats), _ptr(len_dev), B, Tmax
         w.d_warp, w.d_stats, w.stats_stride, w.d_row_bounds, w.n_row_classes = _ptr(warp_dev), _ptr(stats), (n_cls + 1) * D, _ptr(bounds_dev), n_cls
+        if self.fuse_warp_masks:
+            # finalize + mask fill inside the warp launch (the CTA that completes an utterance applies its masks)
+            done = self._warp_done.get(dev)
+            if done is None or done.numel() < B:
+                done = self._warp_done[dev] = torch.zeros((max(B, 1024),), dtype=torch.int32, device=dev)
+            w.d_masks, w.n_freq_masks, w.n_time_masks, w.d_fills = _ptr(masks_dev), n_f, n_t, _ptr(fills)
+            w.fill_zero, w.d_utt_done = int(self.replace_with_zero), _ptr(done)
+            _lib.check(plan.lib.b200fe_time_warp(plan.handle, C.byref(w), stream), "b200fe_time_warp")
+            self.launch_count += 1
+            self.last = dict(stats=stats, fills=fills, masks=masks_dev, warp=warp_dev, pre=pre)
+            return feats, flen
         _lib.check(plan.lib.b200fe_time_warp(plan.handle, C.byref(w), stream), "b200fe_time_warp")
         q = _lib.PostArgs()
         q.d_feats, q.d_nsamp, q.batch, q.max_frames = _ptr(feats), _ptr(len_dev), B, Tmax

@@ -198,3 +198,30 @@ def test_full_specaug_with_time_warp(lasr_b200):
         for i in range(len(lens)):
             lasr_frontend.spec_augment_full(pre[i, : T[i]].copy())
         assert after == (random.random(), np.random.rand())
+
+
+@pytest.mark.gpu
+def test_time_warp_masks_in_the_warp_launch_match_the_separate_launches(lasr_b200):
+    """b200fe_time_warp with d_masks (finalize + fill by the CTA that completes an utterance) against the three-launch
+    chain warp -> finalize -> post pass: same cells, same fills; twice in a row (the completion counters must end at zero)."""
+    rng = np.random.default_rng(5)
+    lens = [int(x) for x in rng.integers(400 + 160 * 3, 16000 * 12, size=37)] + [16000 * 30, 2000]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    for kw in ({}, {"replace_with_zero": True}):
+        outs = []
+        for fused in (True, False, True):
+            fe = lasr_b200.GpuFbankFrontend(specaug=True, time_warp=True, **kw)
+            fe.fuse_warp_masks = fused
+            for rep in range(2):
+                random.seed(3)
+                np.random.seed(3)
+                g = fe(wav, n)[0]
+            outs.append((g.cpu().numpy(), fe.last["fills"].cpu().numpy(), fe.launch_count))
+        assert np.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-7)
+        same_fill = np.all(outs[0][1] == outs[1][1], axis=1)
+        assert same_fill.mean() > 0.9                       # fp64 atomics in another order may move a fill by one float32 ulp
+        assert np.array_equal(outs[0][0][same_fill], outs[1][0][same_fill])
+        assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-6)
+        assert np.allclose(outs[0][0], outs[2][0], rtol=1e-6, atol=1e-6)
+        assert outs[0][2] < outs[1][2]                      # two launches fewer per call
