@@ -379,7 +379,8 @@ typedef struct b200fe_warp_args {
     int n_row_classes;
     /* Optional: the SpecAugment masks that follow the warp (specaugment.py:47-106), applied in the same launch by the CTA that
      * completes an utterance -- fills derived as b200fe_postpass derives them (running mean of the current array, or zero),
-     * later masks win.  Needs d_stats (+ d_row_bounds for mean fills).  NULL = warp only (call b200fe_postpass for the masks). */
+     * later masks win.  Needs d_stats (+ d_row_bounds for mean fills); in this mode d_stats is a WORKSPACE: zero on entry, zero
+     * again on exit, so one buffer serves every call.  NULL = warp only (call b200fe_postpass for the masks). */
     const int* d_masks;          /* [batch][n_freq_masks + n_time_masks][2] int32 (lo, hi) */
     int n_freq_masks, n_time_masks;
     float* d_fills;              /* [batch][n_freq_masks + n_time_masks] outputs */

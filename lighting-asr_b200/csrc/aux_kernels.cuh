@@ -472,6 +472,10 @@ __device__ __forceinline__ void warp_mask_tail(const WarpArgs& a, const int utt,
     q.rows_per_cta = 0; q.feat_offsets = nullptr; q.inline_finalize = 0;
     finalize_body<256>(q, utt, tid);
     __syncthreads();                                               // the fills (written by thread 0) are visible to the CTA
+    {   // the statistics are a workspace in this mode: zero on entry, zero again on exit (no fill launch per call)
+        double* sbz = a.stats + (long long)utt * a.stats_stride;
+        for (int i = tid; i < (a.n_cls + 1) * a.nmel; i += 256) sbz[i] = 0.0;
+    }
     const int nm = a.n_fmask + a.n_tmask;
     const int* mk = a.masks + (long long)utt * nm * 2;
     const float* fl = a.fills + (long long)utt * nm;
@@ -528,6 +532,9 @@ __device__ __forceinline__ void warp_mask_tail(const WarpArgs& a, const int utt,
 constexpr int kWarpRows = B200FE_WARP_ROWS;    // output rows per CTA
 constexpr int kWarpTaps = 16;    // taps per output row: xmax - xmin <= min(in_size, 2 * support + 1); with |in - out| <= W (max_time_warp, 5 in the
                                  // reference) a scale above 2 needs out < W, i.e. in < 2 W, so 16 taps cover W <= 8 (larger windows are clipped as before)
+#ifndef B200FE_WARP_LAUNCH_DEPENDENTS
+#define B200FE_WARP_LAUNCH_DEPENDENTS 0
+#endif
 #ifndef B200FE_WARP_STAGE
 #define B200FE_WARP_STAGE 1
 #endif
@@ -550,6 +557,10 @@ constexpr int kWarpWinExtra = 20;   // source rows staged per CTA beyond kWarpRo
 // partial sums per (row slot, column), added in float64 in a fixed order, one atomic per (moment, column).
 __global__ void __launch_bounds__(256, B200FE_WARP_OCC) time_warp_kernel(const WarpArgs a)
 {
+#if B200FE_WARP_LAUNCH_DEPENDENTS
+    pdl_launch_dependents();
+#endif
+    pdl_wait();                                                    // launched with programmatic serialisation behind the launch that writes `in`
     const int utt = blockIdx.y;
     const long long n = a.nsamp[utt];
     const int T = n >= a.win ? (int)(1 + (n - a.win) / a.shift) : 0;

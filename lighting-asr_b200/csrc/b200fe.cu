@@ -1122,8 +1122,11 @@ extern "C" int b200fe_time_warp(const b200fe_plan* p, const b200fe_warp_args* g,
         if (kWarpStage && fit >= kWarpRows + 12 && (size_t)fit * rowb >= part) { a.win_rows = fit; a.part_ok = 1; smem = (size_t)fit * rowb; }
         else if (part <= budget) { a.part_ok = 1; smem = part; }
     }
-    time_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
-    const cudaError_t e = cudaGetLastError();
+    void* kargs[] = {(void*)&a};
+    static const bool use_pdl = []() { const char* v = getenv("B200FE_WARP_PDL"); return v ? atoi(v) != 0 : true; }();
+    cudaError_t e;
+    if (use_pdl) e = launch_pdl((const void*)time_warp_kernel, grid, dim3(256), kargs, smem, (cudaStream_t)stream);
+    else { time_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a); e = cudaGetLastError(); }
     if (e != cudaSuccess)
         return fail(B200FE_ECUDA, "time_warp: launch failed: %s (grid %u x %u, %zu B dynamic shared memory, %d staged rows)", cudaGetErrorString(e), grid.x, grid.y, smem, a.win_rows);
     return B200FE_OK;
