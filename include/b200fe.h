@@ -102,7 +102,9 @@ int b200fe_build_tile_table_device(const b200fe_plan* plan, const long long* d_n
  * persistent grid holds about 900 claimed tiles, so the frame tiles an apply tile depends on have normally been signalled when it
  * is claimed.  Capacity with apply tiles: b200fe_tile_table_capacity(...) + batch * ceil(max_frames / R).  Pass d_utt_done and
  * apply_cmvn_mode to b200fe_fbank_fused.  Needs b200fe_plan_info(plan, 7) != 0.  Measured on B200 (BASELINE config 2): 0.380 ms
- * per step against 0.382 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3. */
+ * per step against 0.382 ms with b200fe_postpass -- opt-in, see DESIGN.md 5.3.
+ * (3) apply_lag < 0: ONE completion tile per utterance (entry (utterance | 0x40000000, 0)), |apply_lag| utterances behind its frame
+ * tiles, for apply_cmvn_mode 3 of b200fe_fbank_fused (SpecAugment mean fills inside the launch); capacity + batch. */
 int b200fe_build_work_list_device(const b200fe_plan* plan, const long long* d_nsamp, int batch, int max_frames, int with_pads, int apply_lag,
                                   int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, int* d_utt_done,
                                   void* d_zero, long long zero_bytes, void* stream);
@@ -204,6 +206,13 @@ typedef struct b200fe_fbank_args {
     int* d_utt_done;
     float* d_utt_mean;
     float* d_utt_istd;
+    /* apply_cmvn_mode 3: SpecAugment MEAN FILLS inside the launch (the reference's default masks, replace_with_zero=False, on top
+     * of global or no CMVN) by the completion tiles of b200fe_build_work_list_device(apply_lag < 0): the CTA that takes an
+     * utterance's completion tile derives the fills from the row-class statistics as b200fe_postpass does and overwrites the
+     * masked cells, so no b200fe_postpass call follows.  Needs d_masks with mask_zero = 0, per-utterance d_stats with the row
+     * classes of the time masks (d_row_bounds), d_utt_done and the default option set; d_fills (optional,
+     * [batch][n_freq_masks + n_time_masks]) receives the fills. */
+    float* d_fills;
 } b200fe_fbank_args;
 
 int b200fe_fbank_fused(const b200fe_plan* plan, const b200fe_fbank_args* args, void* stream);

@@ -37,7 +37,7 @@ class FbankArgs(_Sized):
         ("d_wav_offsets", C.c_void_p), ("offsets_aligned", C.c_int),
         ("dither_seed", C.c_ulonglong), ("d_dither_noise", C.c_void_p), ("wav_dtype", C.c_int), ("uniform_frames", C.c_int),
         ("d_out_offsets", C.c_void_p), ("tile_table_pads", C.c_int), ("d_n_tiles", C.c_void_p),
-        ("apply_cmvn_mode", C.c_int), ("d_utt_done", C.c_void_p), ("d_utt_mean", C.c_void_p), ("d_utt_istd", C.c_void_p),
+        ("apply_cmvn_mode", C.c_int), ("d_utt_done", C.c_void_p), ("d_utt_mean", C.c_void_p), ("d_utt_istd", C.c_void_p), ("d_fills", C.c_void_p),
     ]
 
 

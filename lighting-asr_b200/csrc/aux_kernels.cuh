@@ -863,7 +863,20 @@ __global__ void __launch_bounds__(256) postpass_vec_kernel(const PostArgs a)
         float4* ptr = base + (long long)r * nq + q;
         const bool anyf = (fhit[0] | fhit[1] | fhit[2] | fhit[3]) >= 0 || fhit[0] >= 0 || fhit[1] >= 0 || fhit[2] >= 0 || fhit[3] >= 0;
         if (!need_read && thit < 0 && !anyf) continue;                    // nothing changes in this float4
-        float4 v = need_read || thit < 0 ? *ptr : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!need_read) {
+            // masks only (global / no CMVN): nothing is read -- a float4 that is masked entirely is one 16-byte store, a partly
+            // masked one gets scalar stores (the read-modify-write of the earlier version made this a latency-bound pass)
+            const bool allf = fhit[0] >= 0 && fhit[1] >= 0 && fhit[2] >= 0 && fhit[3] >= 0;
+            if (thit >= 0) *ptr = make_float4(tf, tf, tf, tf);
+            else if (allf) *ptr = make_float4(ffill[0], ffill[1], ffill[2], ffill[3]);
+            else {
+                float* sp = reinterpret_cast<float*>(ptr);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (fhit[c] >= 0) sp[c] = ffill[c];
+            }
+            continue;
+        }
+        float4 v = *ptr;
         float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

@@ -119,6 +119,7 @@ static bool plan_has_lean(const b200fe_plan* p) { return p->nload == 13 && p->st
 static const void* plan_kernel(const b200fe_plan* p, bool peak, bool i16 = false, bool multi = false, bool lean = false, bool apply = false)
 {
     if (lean && apply) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, true, true>;
+    if (apply) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, false, true>;       // completion tiles: SpecAugment mean fills
     if (lean) return (const void*)fbank_fused_kernel<13, true, false, false, false, false, true>;
     if (multi) {   // multi-utterance tiles (lock-step streaming): the two default option sets, float32, no peak normalisation
         if (p->nfft == 256) return (const void*)fbank_fused_kernel<13, false, false, true, false, true>;
@@ -333,6 +334,7 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     if (e == cudaSuccess && plan_has_lean(p)) {
         e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel(p, false, false, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     }
     if (e == cudaSuccess && plan_has_multi(p))
         e = cudaFuncSetAttribute(plan_kernel(p, false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
@@ -427,6 +429,7 @@ static cudaError_t launch_builder(const b200fe_plan* p, const long long* d_nsamp
                                   int* d_n_tiles, int* d_work_counter, int apply_lag, int* d_utt_done, void* d_zero, long long zero_bytes, void* stream)
 {
     int win = p->win, shift = p->shift, ft = plan_tile_frames(p), pads = with_pads ? 1 : 0, pad_rows = kPadTileRows, apply_bit = kApplyBit, apply_rows = kApplyRows;
+    if (apply_lag < 0) { apply_lag = -apply_lag; apply_rows = 0x20000000; }      // ONE completion tile per utterance that has frames
     int2* table = reinterpret_cast<int2*>(d_table);
     uint4* zero16 = reinterpret_cast<uint4*>(d_zero);
     long long n_zero16 = zero_bytes / 16;
@@ -450,15 +453,15 @@ extern "C" int b200fe_build_work_list_device(const b200fe_plan* p, const long lo
                                              int* d_table, int capacity, int* d_n_tiles, int* d_work_counter, int* d_utt_done,
                                              void* d_zero, long long zero_bytes, void* stream)
 {
-    if (!p || !d_nsamp || !d_table || !d_n_tiles || !d_work_counter || batch <= 0 || max_frames <= 0 || capacity <= 0 || apply_lag < 0)
+    if (!p || !d_nsamp || !d_table || !d_n_tiles || !d_work_counter || batch <= 0 || max_frames <= 0 || capacity <= 0 || apply_lag < -(1 << 20))
         return fail(B200FE_EINVAL, "build_work_list_device: bad argument");
     if (p->use_ws) return fail(B200FE_EINVAL, "build_work_list_device: not available with the experimental kernel");
-    if (apply_lag > 0 && !d_utt_done) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need d_utt_done");
-    if (apply_lag > 0 && !plan_has_lean(p)) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need the default option set (plan_info 7)");
+    if (apply_lag != 0 && !d_utt_done) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need d_utt_done");
+    if (apply_lag != 0 && !plan_has_lean(p)) return fail(B200FE_EINVAL, "build_work_list_device: apply tiles need the default option set (plan_info 7)");
     if (zero_bytes < 0 || (zero_bytes > 0 && (!d_zero || (zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(d_zero) & 15) != 0)))
         return fail(B200FE_EINVAL, "build_work_list_device: d_zero must be 16-byte aligned and zero_bytes a multiple of 16");
     CUDA_TRY(launch_builder(p, d_nsamp, batch, max_frames, with_pads, d_table, capacity, d_n_tiles, d_work_counter, apply_lag,
-                            apply_lag > 0 ? d_utt_done : nullptr, d_zero, zero_bytes, stream));
+                            apply_lag != 0 ? d_utt_done : nullptr, d_zero, zero_bytes, stream));
     return B200FE_OK;
 }
 
@@ -898,7 +901,16 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
     a.ntiles_ptr = g->d_n_tiles;          // table built on the device: n_tiles is only the capacity bound for the grid size
     if (g->apply_cmvn_mode != 0) {
         // utterance CMVN inside the launch: apply tiles of b200fe_build_work_list_device, lean instantiation only
-        if (g->apply_cmvn_mode != 1 && g->apply_cmvn_mode != 2) return fail(B200FE_EINVAL, "fbank_fused: apply_cmvn_mode must be 0, 1 or 2");
+        if (g->apply_cmvn_mode == 3) {
+            // SpecAugment mean fills inside the launch: completion tiles (apply_lag < 0), full-epilogue instantiation
+            if (!(plan_has_lean(p) && !p->use_ws) || g->d_peak || i16 || g->uniform_frames || g->d_out_offsets || !g->d_out || (g->d_cmvn_mean && g->cmvn_stride != 0))
+                return fail(B200FE_EINVAL, "fbank_fused: in-launch mean fills need the default option set, float32 input, the padded output layout and global or no CMVN");
+            if (!a.masks || g->mask_zero || !g->d_utt_done || !g->d_n_tiles || !g->d_stats || g->stats_stride < (long long)(n_cls + 1) * p->nmel)
+                return fail(B200FE_EINVAL, "fbank_fused: in-launch mean fills need d_masks (mask_zero = 0), d_utt_done, a device-built work list and per-utterance statistics");
+            if ((reinterpret_cast<uintptr_t>(g->d_out) & 15) != 0) return fail(B200FE_EINVAL, "fbank_fused: in-launch mean fills need a 16-byte aligned output");
+            a.apply_mode = 3; a.utt_done = g->d_utt_done; a.fills = g->d_fills;
+        } else {
+        if (g->apply_cmvn_mode != 1 && g->apply_cmvn_mode != 2) return fail(B200FE_EINVAL, "fbank_fused: apply_cmvn_mode must be 0, 1, 2 or 3");
         if (!(plan_has_lean(p) && !p->use_ws) || g->d_peak || i16 || g->uniform_frames || g->d_cmvn_mean || a.masks || g->d_out_offsets || !g->d_out)
             return fail(B200FE_EINVAL, "fbank_fused: in-launch utterance CMVN needs the default option set, float32 input and the padded output layout");
         if (!g->d_utt_done || !g->d_n_tiles || !g->d_stats || g->stats_stride < 2LL * p->nmel || n_cls != 1)
@@ -906,6 +918,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
         if ((g->d_utt_mean == nullptr) != (g->d_utt_istd == nullptr)) return fail(B200FE_EINVAL, "fbank_fused: d_utt_mean and d_utt_istd go together");
         if ((reinterpret_cast<uintptr_t>(g->d_out) & 15) != 0) return fail(B200FE_EINVAL, "fbank_fused: in-launch utterance CMVN needs a 16-byte aligned output");
         a.apply_mode = g->apply_cmvn_mode; a.utt_done = g->d_utt_done; a.utt_mean = g->d_utt_mean; a.utt_istd = g->d_utt_istd;
+        }
     }
     // Lock-step streaming (every utterance yields exactly max_frames frames): tiles take several utterances, so a 4-frame
     // push fills a 32-frame tile with 8 streams instead of occupying one tile per stream.
@@ -944,7 +957,7 @@ extern "C" int b200fe_fbank_fused(const b200fe_plan* p, const b200fe_fbank_args*
 #endif
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, (long long)p->num_sms * p->ctas_per_sm));
     // the lean instantiation serves the default option set whenever the launch applies no CMVN, no masks and writes the padded layout
-    const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets;
+    const bool lean = plan_has_lean(p) && !g->d_peak && !i16 && a.multi_fpu == 0 && !a.cm_mean && !a.masks && !a.out_offsets && a.apply_mode != 3;
     CUDA_TRY(launch_pdl(plan_kernel(p, g->d_peak != nullptr, i16, a.multi_fpu > 0, lean, a.apply_mode != 0), dim3(grid), dim3(kThreads), kargs,
                         (size_t)(a.multi_fpu > 0 ? p->multi_smem_bytes : p->smem_bytes), st));
     return B200FE_OK;

@@ -17,6 +17,8 @@
     /* generic mel tables, 512-point family */                      \
     X(3, 13, false, false, false, false, false, false, false)       \
     X(4, 13, false, true, false, false, false, false, false)        \
+    /* default option set, full epilogue + completion tiles (SpecAugment mean fills inside the launch) */ \
+    X(4, 13, true, false, false, false, false, false, true)         \
     X(4, 16, false, false, false, false, false, false, false)       \
     X(5, 16, false, true, false, false, false, false, false)        \
     X(5, 13, false, false, false, true, false, false, false)        \

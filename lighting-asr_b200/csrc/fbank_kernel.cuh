@@ -148,7 +148,8 @@ struct FbankArgs {
     int multi_fpu, multi_upt, multi_span;
     int multi_ragged;               // 1: an utterance may yield FEWER than multi_fpu frames (independent streams): per-slot validity mask
     // utterance CMVN inside the launch (apply tiles of the work list; lean instantiation only)
-    int apply_mode;                 // 0 off, 1 mean, 2 mean + variance
+    int apply_mode;                 // 0 off, 1 mean, 2 mean + variance, 3 SpecAugment mean fills (one completion tile per utterance)
+    float* fills;                   // apply_mode 3: [B][n_fmask + n_tmask] fills (output, optional)
     int* utt_done;                  // [B] frame tiles of the utterance whose features and statistics are globally visible; [B] = error flag
     float* utt_mean;                // optional [B][nmel]: the vectors the apply tiles used
     float* utt_istd;
@@ -556,6 +557,122 @@ __device__ __forceinline__ bool apply_cmvn_tile(const FbankArgs& a, int utt, int
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the buffers belong to the next tile's phase A afterwards
     }
     return true;
+}
+
+// SpecAugment mean fills inside the fused launch (apply_mode 3; the reference's default masks, specaugment.py:47-106, on top of
+// global or no CMVN): the work list carries ONE completion tile per utterance; when every frame tile of the utterance has been
+// signalled, the CTA that took the tile derives the fills from the row-class column sums exactly as finalize_kernel does
+// (x.mean() of the current array before every mask, later masks see the earlier fills) and overwrites the masked cells -- whole
+// float4 stores where four columns are masked, scalar stores otherwise, nothing is read.  Replaces the finalize launch and the
+// mask pass over the batch (8 + 70 us on BASELINE config 3).  `scratch`: >= 256 bytes of idle shared memory.
+__device__ __forceinline__ void apply_mask_tile(const FbankArgs& a, int utt, int Tu, bool ready, unsigned char* scratch, int tid, int nmel)
+{
+    const int T = min(Tu, a.Tmax);
+    if (tid == 0) {
+        if (!ready) {
+            const int need = (T + kFT - 1) / kFT;
+            int spins = 0;
+            while (ld_relaxed_gpu(a.utt_done + utt) < need) {
+                __nanosleep(128);
+                if (++spins > (1 << 22)) { atomicExch(a.utt_done + a.B, 1 + utt); break; }
+            }
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    double* red = reinterpret_cast<double*>(scratch);                        // [kWarps]
+    int* cls_lo = reinterpret_cast<int*>(red + kWarps);                      // [kMaxRowClasses + 1]
+    float* s_fill = reinterpret_cast<float*>(cls_lo + kMaxRowClasses + 3);   // [kMaxFreqMasks + kMaxTimeMasks]
+    const int nb = a.n_cls - 1;
+    const int* bounds = (a.row_bounds != nullptr && nb > 0) ? a.row_bounds + (long long)utt * nb : nullptr;
+    if (tid == 0) {
+        cls_lo[0] = 0;
+        for (int c = 0; c < nb; ++c) cls_lo[c + 1] = min(max(bounds ? __ldg(bounds + c) : T, 0), T);
+        cls_lo[a.n_cls] = T;
+    }
+    __syncthreads();          // orders thread 0's acquire before everybody's reads of the column sums
+    const double* sb = a.stats + (long long)utt * a.stats_stride;
+    const bool col = tid < nmel;
+    double S[kMaxRowClasses];
+    double part = 0.0;
+#pragma unroll
+    for (int c = 0; c < kMaxRowClasses; ++c) {
+        S[c] = (col && c < a.n_cls) ? __ldcg(sb + (long long)c * nmel + tid) : 0.0;
+        part += S[c];
+    }
+    auto block_sum = [&](double v) -> double {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w];
+        return t;
+    };
+    double total = block_sum(part);
+    const int nm = a.n_fmask + a.n_tmask;
+    const int* mk = a.masks + (long long)utt * nm * 2;
+    const double cells = (double)T * (double)nmel;
+    for (int i = 0; i < nm; ++i) {
+        const double fill = cells > 0 ? (double)(float)(total / cells) : 0.0;     // numpy: x[...] = x.mean() of the current array
+        int lo = __ldg(mk + 2 * i), hi = __ldg(mk + 2 * i + 1);
+        double delta = 0.0;
+        if (i < a.n_fmask) {
+            lo = max(lo, 0); hi = min(hi, nmel);
+            if (col && tid >= lo && tid < hi) {
+#pragma unroll
+                for (int c = 0; c < kMaxRowClasses; ++c)
+                    if (c < a.n_cls) { const double nv = fill * (double)(cls_lo[c + 1] - cls_lo[c]); delta += nv - S[c]; S[c] = nv; }
+            }
+        } else {
+            lo = max(lo, 0); hi = min(hi, T);
+            if (col) {
+#pragma unroll
+                for (int c = 0; c < kMaxRowClasses; ++c)
+                    if (c < a.n_cls && cls_lo[c] >= lo && cls_lo[c + 1] <= hi && cls_lo[c + 1] > cls_lo[c]) {
+                        const double nv = fill * (double)(cls_lo[c + 1] - cls_lo[c]); delta += nv - S[c]; S[c] = nv;
+                    }
+            }
+        }
+        total += block_sum(delta);
+        if (tid == 0) { s_fill[i] = (float)fill; if (a.fills != nullptr) a.fills[(long long)utt * nm + i] = (float)fill; }
+    }
+    __syncthreads();
+    int tlo[kMaxTimeMasks], thi[kMaxTimeMasks];
+    float tfill[kMaxTimeMasks];
+#pragma unroll
+    for (int i = 0; i < kMaxTimeMasks; ++i) {
+        tlo[i] = 0; thi[i] = 0; tfill[i] = 0.f;
+        if (i < a.n_tmask) { tlo[i] = __ldg(mk + 2 * (a.n_fmask + i)); thi[i] = __ldg(mk + 2 * (a.n_fmask + i) + 1); tfill[i] = s_fill[a.n_fmask + i]; }
+    }
+    const int nq = nmel >> 2;                     // nmel % 4 == 0 (the static option set)
+    const int slots = kThreads / nq, slot = tid / nq, qd = tid - slot * nq;
+    if (slot < slots) {
+        int fhit[4] = {-1, -1, -1, -1};
+        float ffill[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < a.n_fmask; ++i) {
+            const int lo = __ldg(mk + 2 * i), hi = __ldg(mk + 2 * i + 1);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * qd + c >= lo && 4 * qd + c < hi) { fhit[c] = i; ffill[c] = s_fill[i]; }
+        }
+        const bool anyf = fhit[0] >= 0 || fhit[1] >= 0 || fhit[2] >= 0 || fhit[3] >= 0;
+        const bool allf = fhit[0] >= 0 && fhit[1] >= 0 && fhit[2] >= 0 && fhit[3] >= 0;
+        float* base = a.out + (long long)utt * a.Tmax * nmel + 4 * qd;
+        for (int r = slot; r < T; r += slots) {
+            int thit = -1; float tf = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMaxTimeMasks; ++i) if (r >= tlo[i] && r < thi[i]) { thit = i; tf = tfill[i]; }    // later masks win
+            float* ptr = base + (long long)r * nmel;
+            if (thit >= 0) *reinterpret_cast<float4*>(ptr) = make_float4(tf, tf, tf, tf);             // time masks come after frequency masks
+            else if (allf) *reinterpret_cast<float4*>(ptr) = make_float4(ffill[0], ffill[1], ffill[2], ffill[3]);
+            else if (anyf) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (fhit[c] >= 0) ptr[c] = ffill[c];
+            }
+        }
+    }
 }
 
 // kDual: padded window of 256 samples (8 kHz family).  Two consecutive real frames a, b are packed as
@@ -1222,7 +1339,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                 if (g.apply) {
                     static_assert(kWarps * kRegionWarp * 4 + ((kFT * (B200FE_STATIC_NMEL + 1) * 4 + 15) & ~15) >= kApplyRows * B200FE_STATIC_NMEL * 4,
                                   "an apply tile must fit the transposition / PT regions + the staging tile");
-                    if (apply_cmvn_tile(a, g.utt, g.f0, g.T, g.ready, s_mean, s_istd, smem + L.xbuf_off, &bars[2], (phase_bits >> 1) & 1u, tid, nmel))
+                    if (!kLean) apply_mask_tile(a, g.utt, g.T, g.ready, smem + L.xbuf_off, tid, nmel);      // apply_mode 3 (the lean kernel has no masks)
+                    else if (apply_cmvn_tile(a, g.utt, g.f0, g.T, g.ready, s_mean, s_istd, smem + L.xbuf_off, &bars[2], (phase_bits >> 1) & 1u, tid, nmel))
                         phase_bits ^= 2u;
                 }
             }

@@ -225,3 +225,33 @@ def test_time_warp_masks_in_the_warp_launch_match_the_separate_launches(lasr_b20
         assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-6)
         assert np.allclose(outs[0][0], outs[2][0], rtol=1e-6, atol=1e-6)
         assert outs[0][2] < outs[1][2]                      # two launches fewer per call
+
+
+def test_mean_fills_inside_the_fused_launch_match_the_post_pass(lasr_b200):
+    """apply_cmvn_mode 3 (completion tiles: fills + masked cells written by the fused launch itself) against finalize + post pass:
+    the same cells, the same fills, with and without global CMVN; no completion tile ever gave up waiting."""
+    rng = np.random.default_rng(8)
+    lens = [int(x) for x in rng.integers(400, 16000 * 14, size=70)] + [16000 * 33, 400, 560, 2000]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    st = lasr_b200.GpuFbankFrontend().accumulate_stats(wav, n).cpu().numpy()
+    for kw in ({}, {"cmvn": "global", "cmvn_stats": st}):
+        outs = []
+        for inlaunch in (True, False):
+            fe = lasr_b200.GpuFbankFrontend(specaug=True, **kw)
+            fe.inlaunch_fills = inlaunch
+            fe.fill_lag = 3 if inlaunch else 64               # a short lag makes some completion tiles wait for their frame tiles
+            for rep in range(2):
+                random.seed(17)
+                np.random.seed(17)
+                g = fe(wav, n)[0]
+            flags = fe.last["apply_flags"]
+            if inlaunch:
+                assert flags is not None and int(flags[0][flags[1]].item()) == 0
+            outs.append((g.cpu().numpy(), fe.last["fills"].cpu().numpy(), fe.launch_count))
+        assert np.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-7)
+        same = np.all(outs[0][1] == outs[1][1], axis=1)
+        assert same.mean() > 0.9
+        assert np.array_equal(outs[0][0][same], outs[1][0][same])
+        assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-6)
+        assert outs[0][2] < outs[1][2]
