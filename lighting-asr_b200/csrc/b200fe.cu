@@ -1084,7 +1084,7 @@ extern "C" int b200fe_postpass(const b200fe_plan* p, const b200fe_post_args* g, 
     // utterance CMVN without SpecAugment fills: the post pass derives the vectors itself, one launch instead of two
     a.inline_finalize = (vec && !masks && a.cmvn_mode != 0 && a.n_cls == 1) ? 1 : 0;
     if (!a.inline_finalize) {
-        finalize_kernel<<<g->batch, 128, 0, st>>>(a);
+        finalize_kernel<<<g->batch, 128, 0, st>>>(a);          // (launching it with programmatic serialisation measured no gain)
         CUDA_TRY(cudaGetLastError());
     }
     a.rows_per_cta = vec ? 96 : 64;

@@ -1119,11 +1119,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         // ================= phase C: epilogue + copy-out, zero padding, statistics =================
         // element e = row * nmel + col of the tile (contiguous in global memory) <-> staging row*(nmel+1)+col
         bool stats_fused = stats_cap;          // this tile's statistics are reduced inside the copy-out
-        int tcls = 0;                          // ... into this row class
+        int tcls = 0, tcls_hi = 0;             // ... into these row classes (first and last row of the tile)
         if (has_cls && stats_cap && nvalid > 0) {
             const int* bounds = a.row_bounds + (long long)utt * (a.n_cls - 1);
             tcls = row_class(bounds, a.n_cls - 1, f0);
-            stats_fused = tcls == row_class(bounds, a.n_cls - 1, f0 + nvalid - 1);
+            tcls_hi = row_class(bounds, a.n_cls - 1, f0 + nvalid - 1);
+            // a FULL tile that straddles class boundaries (one in eight on BASELINE config 3) stays on the register path too: the
+            // thread adds its rows class by class; the write-back + barrier + column-reducer path below cost such a tile several
+            // microseconds (fused launch 417 vs 354 us with and without row classes)
+            stats_fused = tcls == tcls_hi || (kStaticMel && nvalid == kFT);
         }
         const bool rowpart_c = stats_fused || rowpart_nostats;
         {
@@ -1170,6 +1174,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
                                     const float dd = x[k] - pivot;
                                     s1 += dd; s2 = fmaf(dd, dd, s2); ++cnt;
                                 }
+                            }
+                            if (!kLean && tcls != tcls_hi) {
+                                // several row classes in this tile: the sums of squares go to the one total as usual, the sums
+                                // are split by class -- the thread's rows are rg + k * parts, a class is a row interval
+                                double* sb = a.stats + (long long)utt * a.stats_stride;
+                                const int* bounds = a.row_bounds + (long long)utt * (a.n_cls - 1);
+                                const double dp = (double)pivot;
+                                for (int c = tcls; c <= tcls_hi; ++c) {
+                                    const int lo = (c == 0 ? 0 : __ldg(bounds + c - 1)) - f0, hi = (c == a.n_cls - 1 ? 0x3fffffff : __ldg(bounds + c)) - f0;
+                                    float sc = 0.f; int nc = 0;
+#pragma unroll
+                                    for (int k = 0; k < kIt; ++k) {
+                                        const int row = rg + k * parts;
+                                        if (tid + k * P < nv && row >= lo && row < hi) { sc += x[k] - pivot; ++nc; }
+                                    }
+                                    if (nc > 0) atomicAdd(sb + (long long)c * nmel + col, (double)sc + nc * dp);
+                                }
+                                const double d1 = (double)s1;
+                                atomicAdd(sb + (long long)a.n_cls * nmel + col, (double)s2 + 2.0 * dp * d1 + cnt * dp * dp);
+                                cnt = 0;                         // flushed
                             }
                         } else {
 #pragma unroll
