@@ -255,3 +255,37 @@ def test_mean_fills_inside_the_fused_launch_match_the_post_pass(lasr_b200):
         assert np.array_equal(outs[0][0][same], outs[1][0][same])
         assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-6)
         assert outs[0][2] < outs[1][2]
+
+
+@pytest.mark.parametrize("nmel", [40, 30])
+def test_time_warp_other_bin_counts(lasr_b200, nmel):
+    """The warp launch with 40 bins (ten float4 per row, 25 row slots) and with 30 bins (not a multiple of four: the scalar
+    path, no staged window, generic statistics and fill loops), masks inside the launch and as separate launches."""
+    rng = np.random.default_rng(nmel)
+    lens = [16000 * 9 + 123, 16000 * 2, 5000, 16000 * 5 + 7, 400 + 160 * 11, 400 + 160 * 64]
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+    wav, n = _pad(wavs)
+    T = [kaldi_fbank.num_frames(x) for x in lens]
+    pre = lasr_b200.GpuFbankFrontend(num_mel_bins=nmel)(wav, n)[0].cpu().numpy()
+    for fused in (True, False):
+        fe = lasr_b200.GpuFbankFrontend(num_mel_bins=nmel, specaug=True, time_warp=True)
+        fe.fuse_warp_masks = fused
+        random.seed(31)
+        np.random.seed(31)
+        g = fe(wav, n)[0].cpu().numpy()
+        random.seed(31)
+        np.random.seed(31)
+        for i in range(len(lens)):
+            xw, _ = lasr_frontend.time_warp(pre[i, : T[i]].copy())
+            warped_only = xw.copy()
+            y, rects = lasr_frontend.spec_augment_masks(xw)
+            masked = np.zeros_like(y, dtype=bool)
+            for kind, lo, hi, _ in rects:
+                if kind == "f":
+                    masked[:, max(lo, 0):max(hi, 0)] = True
+                else:
+                    masked[max(lo, 0):max(hi, 0)] = True
+            gi = g[i, : T[i]]
+            assert np.array_equal(gi[~masked], warped_only[~masked])
+            assert _close(gi[masked], y[masked].astype(np.float64), rtol=1e-4, atol=2e-5) == 0
+            assert np.all(g[i, T[i]:] == 0)
