@@ -75,10 +75,32 @@ inline void zero_stream(void* dst, long long n)
     if (n > 0) memset(d, 0, (size_t)n);
 }
 
+// Copy into the (pinned) staging buffer with non-temporal stores.  glibc's memcpy switches to them only far above a task's
+// 256 kB, so a plain memcpy leaves the staged waveforms dirty in the cores' caches (and reads the destination lines first): the
+// DMA engine then has to snoop them out -- measured on the int16 plug-in call: H2D chunks at 27-39 GB/s instead of 52.
+inline void copy_stream(const void* src, void* dst, long long n)
+{
+    const char* s = static_cast<const char*>(src);
+    char* d = static_cast<char*>(dst);
+    long long i = 0;
+#if defined(__SSE2__)
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+        }
+        _mm_sfence();
+    }
+#endif
+    if (i < n) memcpy(d + i, s + i, (size_t)(n - i));
+}
+
 inline void run_task(const Task& t)
 {
     switch (t.kind) {
-        case 0: memcpy(t.dst, t.src, (size_t)t.n); if (t.tail_zero > 0) memset(static_cast<char*>(t.dst) + t.n, 0, (size_t)t.tail_zero); break;
+        case 0: copy_stream(t.src, t.dst, t.n); if (t.tail_zero > 0) memset(static_cast<char*>(t.dst) + t.n, 0, (size_t)t.tail_zero); break;
         case 1:
             cvt_f64_f32(static_cast<const double*>(t.src), static_cast<float*>(t.dst), t.n);
             if (t.tail_zero > 0) memset(static_cast<float*>(t.dst) + t.n, 0, (size_t)t.tail_zero);
