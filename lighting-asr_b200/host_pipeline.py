@@ -112,7 +112,9 @@ class HostPipeline:
         self.h2d_bytes = self.d2h_bytes = 0
         self.resampler = None               # resample.Resampler: applied on the device to every group before the fused launch (F3)
         self.speed = None                   # resample.SpeedPerturb: one numpy.random.choice per utterance, then resampling by 1 / ratio
-        self.d2h_mode = "kernel"            # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance
+        # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance; "kernel_end" (A/B
+        # only, tools/pipe_ablate3.py): one copy kernel for the whole batch after the last group's kernels, i.e. no D2H overlap
+        self.d2h_mode = "kernel"
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
     def _stamp(self, label):
@@ -291,6 +293,11 @@ class HostPipeline:
                     self._stamp("issued")
                     continue
                 copy = lib.b200fe_copy_ragged_bf16 if bf16 else lib.b200fe_copy_ragged
+                if self.d2h_mode == "kernel_end" and b1 < B:
+                    self._stamp("issued")
+                    continue                                   # A/B: ONE copy kernel for the whole batch after the last group's kernels
+                if self.d2h_mode == "kernel_end":
+                    b0 = 0
                 _lib.check(copy(C.c_void_p(dfeats.data_ptr()), C.c_void_p(tab_dev.data_ptr() + 8 * b0), C.c_void_p(hfeats.data_ptr()),
                                 C.c_void_p(tab_dev.data_ptr() + 8 * (2 * B + b0)), C.c_void_p(tab_dev.data_ptr() + 8 * (B + b0)), b1 - b0,
                                 int(T_host[b0:b1].max()) * D * 4, C.c_void_p(s_out.cuda_stream)), "b200fe_copy_ragged")
