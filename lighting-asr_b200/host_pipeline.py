@@ -115,6 +115,7 @@ class HostPipeline:
         # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance; "kernel_end" (A/B
         # only, tools/pipe_ablate3.py): one copy kernel for the whole batch after the last group's kernels, i.e. no D2H overlap
         self.d2h_mode = "kernel"
+        self.taper = os.environ.get("B200FE_TAPER", "1") != "0"
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
     def _stamp(self, label):
@@ -198,10 +199,22 @@ class HostPipeline:
         hin = self._in[ddt][si][0].get(total + 64)
         dwav = self._in[ddt][si][1].get(total + 64)
         # ---- utterance groups of ~group_bytes of audio; one pack job per group, queued in order ----
+        # the last groups taper (1/2, 1/4 of a group): what follows the last group's packing -- its upload, kernels and D2H -- is
+        # the tail of the call that nothing overlaps
         bounds, acc = [0], 0
+        csum = np.cumsum(lens * esz)
+        total_b = int(csum[-1])
+        taper = self.taper
         for b in range(B):
             acc += int(lens[b]) * esz
-            if acc >= self.group_bytes:
+            left = total_b - int(csum[b])
+            target = self.group_bytes
+            if taper:
+                if left < self.group_bytes // 4:
+                    target = self.group_bytes // 4
+                elif left < self.group_bytes:
+                    target = self.group_bytes // 2
+            if acc >= target:
                 bounds.append(b + 1)
                 acc = 0
         if bounds[-1] != B:
