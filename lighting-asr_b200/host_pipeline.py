@@ -204,7 +204,7 @@ class HostPipeline:
         bounds, acc = [0], 0
         csum = np.cumsum(lens * esz)
         total_b = int(csum[-1])
-        taper = self.taper
+        taper = self.taper and total_b >= 2 * self.group_bytes      # a batch of one or two groups gains nothing from more launches
         for b in range(B):
             acc += int(lens[b]) * esz
             left = total_b - int(csum[b])
