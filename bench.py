@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the short C1/C3/C4/C5 runs of the default line")
     ap.add_argument("--profile-only", action="store_true", help="device-resident loop only (for ncu launch lists)")
+    ap.add_argument("--no-graph", action="store_true", help="time the device-resident loop as eager launches instead of a CUDA graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -283,6 +284,37 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    # The step is three launches on fixed pointers (the work list is built on the device), so it replays as a CUDA graph: the host
+    # cost per step drops from ~0.12 ms of Python to one cudaGraphLaunch, which matters for the FIRST timed step only (the device
+    # waits for its launches; every later step is enqueued while the device is busy).  Falls back to eager launches if the capture
+    # fails; the eager loop is timed as well and reported next to it.
+    graph, graph_note, per_step_launches = None, "eager launches", None
+    if not args.no_graph and not args.profile_only:      # (the ncu launch lists profile the eager launches)
+        try:
+            eager_ref = None
+            step()
+            torch.cuda.synchronize(dev)
+            eager_ref = out.clone()
+            gs = torch.cuda.Stream(dev)
+            gs.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            fe.launch_count = 0
+            with torch.cuda.graph(graph, stream=gs):
+                step()
+            per_step_launches = fe.launch_count
+            out.zero_()
+            graph.replay()
+            torch.cuda.synchronize(dev)
+            if not torch.equal(out, eager_ref):
+                raise RuntimeError("graph replay differs from the eager step")
+            graph_note = "CUDA graph replay of the step's %d launches (bit-equal to the eager step)" % per_step_launches
+            del eager_ref
+        except Exception as e:  # noqa: BLE001
+            graph, graph_note = None, "eager launches (graph capture failed: %s)" % str(e)[:120]
+    run_step = graph.replay if graph is not None else step
+    for _ in range(3):
+        run_step()
+    barrier()
     fe.launch_count = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -291,11 +323,19 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step()
+        run_step()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = fe.launch_count
+    launches = fe.launch_count if graph is None else per_step_launches * args.steps
+    # the same K steps as eager launches (what a training loop with changing shapes does)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_eager = e0.elapsed_time(e1)
     # The same K steps again with a CUDA event pair around every fused launch (roofline.achieved).  Kept out of the loop above:
     # an event record between the work-list builder and the fused launch costs ~5 us per step and keeps the fused kernel's
     # prologue from overlapping the builder (programmatic dependent launch); the instrumented step time is reported next to it.
@@ -477,6 +517,7 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         step_ms = ms_total / args.steps
+        eager_ms = ms_eager / args.steps
         per = e2e_ms / args.steps
 
         def v(h, ms):
@@ -507,6 +548,8 @@ def main():
                                     "vs_floor": per / ((3 * h2d + h2d + d2h) / (3 * h2d / pack_ms)) if pack_ms > 0 else None},
                     "matches_device_path": {"max_abs_diff": e2e_max_diff, "lengths_equal": e2e_len_ok}},
             "gpu_launches": launches,
+            "step_launch": {"timed_loop": graph_note, "eager_ms_per_step": eager_ms,
+                            "note": "value / ms_per_step come from the timed loop above; the eager figure is the same K steps launched call by call"},
             "clocks": clocks,
             "parity": parity,
             "extra": {"pcie_floor": {"what": "this step's H2D (%d B) and D2H (%d B) as two plain pinned cudaMemcpyAsync, all %d ranks at once" % (h2d, d2h, world),
