@@ -136,7 +136,7 @@ def main():
     print("wrote", os.listdir(OUT))
 
 
-if __name__ == "__main__" and "--batching" not in sys.argv:
+if __name__ == "__main__" and "--batching" not in sys.argv and "--cmvn" not in sys.argv:
     main()
 
 
@@ -184,3 +184,41 @@ def gen_batching():
 
 if __name__ == "__main__" and "--batching" in sys.argv:
     gen_batching()
+
+
+def gen_cmvn():
+    """CMVN goldens.  The reference has no CMVN code of its own, but the library it delegates all feature
+    arithmetic to does: torchaudio.functional.sliding_window_cmn is torchaudio's port of Kaldi's apply-cmvn-sliding
+    (TA functional/functional.py, `sliding_window_cmn`).  With center=True and a window longer than twice the matrix it
+    normalises every frame with the statistics of ALL frames, i.e. utterance CMVN (norm_vars=False: mean only,
+    norm_vars=True: mean and population variance); applied to the CONCATENATION of a corpus' feature matrices it is
+    global CMVN from the corpus' accumulated statistics.  Inputs are the reference's own `fbank:80` outputs of
+    fbank_reference.npz; evaluated in float64."""
+    import torch
+    import torchaudio
+    import torchaudio.functional as F
+    fb = np.load(os.path.join(OUT, "fbank_reference.npz"))
+    feats = [fb["fbank_%d" % i] for i in range(6)]
+    out = {}
+
+    def cmn(x, norm_vars):
+        t = torch.from_numpy(np.asarray(x, dtype=np.float64))[None]
+        return F.sliding_window_cmn(t, cmn_window=2 * t.shape[1] + 1000, min_cmn_window=1, center=True, norm_vars=norm_vars)[0].numpy()
+
+    for i, x in enumerate(feats):
+        out["utt_mean_%d" % i] = cmn(x, False)
+        if x.shape[0] > 1:          # one frame: zero variance, sliding_window_cmn yields 0 * inf
+            out["utt_meanvar_%d" % i] = cmn(x, True)
+    cat = np.concatenate(feats, axis=0)
+    bounds = np.cumsum([0] + [x.shape[0] for x in feats])
+    for nv, key in ((False, "global_mean"), (True, "global_meanvar")):
+        y = cmn(cat, nv)
+        for i in range(6):
+            out["%s_%d" % (key, i)] = y[bounds[i]:bounds[i + 1]]
+    out["versions"] = np.array([torch.__version__, torchaudio.__version__, np.__version__])
+    np.savez_compressed(os.path.join(OUT, "cmvn_reference.npz"), **out)
+    print("wrote cmvn_reference.npz")
+
+
+if __name__ == "__main__" and "--cmvn" in sys.argv:
+    gen_cmvn()

@@ -77,6 +77,78 @@ def test_utterance_cmvn(lasr_b200):
                 assert int(((np.abs(g[i, :T] - e2e) > tol) & ok).sum()) == 0
 
 
+def test_cmvn_against_torchaudio_sliding_window_cmn(lasr_b200):
+    """Row A11 pinned: the product's utterance CMVN (mean / mean + variance), its statistics accumulation and global CMVN against
+    torchaudio.functional.sliding_window_cmn (torchaudio's port of Kaldi's apply-cmvn-sliding) with a window that covers the whole
+    matrix: per utterance that is utterance CMVN, on the concatenated corpus it is global CMVN from the corpus' statistics.
+    (1) the committed goldens (tests/golden/cmvn_reference.npz: the reference's own fbank:80 outputs through torchaudio),
+    (2) live torchaudio on a ragged batch.  Tolerance: the fbank tolerance carried through the affine map (times istd)."""
+    import os
+    import torchaudio.functional as F
+    from torchaudio.compliance import kaldi
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fb, cm = np.load(os.path.join(gold, "fbank_reference.npz")), np.load(os.path.join(gold, "cmvn_reference.npz"))
+
+    def run(wavs, refs_of):
+        wav, n = _pad(wavs)
+        st = lasr_b200.GpuFbankFrontend().accumulate_stats(wav, n).cpu().numpy()
+        fbs = [refs_of("fbank", i) for i in range(len(wavs))]
+        assert st[0, 80] == sum(x.shape[0] for x in fbs)
+        gmean, gistd = {}, {}
+        for nv in (False, True):
+            gmean[nv], gistd[nv] = lasr_frontend.cmvn_from_stats(lasr_frontend.cmvn_stats(fbs), norm_vars=nv)
+        checked = 0
+        for mode, nv, key in (("utt_mean", False, "utt_mean"), ("utt_meanvar", True, "utt_meanvar"), ("global", False, "global_mean"),
+                              ("global", True, "global_meanvar")):
+            fe = lasr_b200.GpuFbankFrontend(cmvn=mode, cmvn_stats=st if mode == "global" else None)
+            if mode == "global":
+                fe.set_global_cmvn(st, norm_vars=nv)            # the product's own accumulated statistics
+            g = fe(wav, n)[0].cpu().numpy()
+            for i, x in enumerate(fbs):
+                ref = refs_of(key, i)
+                if ref is None:
+                    continue
+                T = x.shape[0]
+                if mode == "global":
+                    istd = gistd[nv]
+                else:
+                    istd = lasr_frontend.cmvn_from_stats(lasr_frontend.cmvn_stats([x]), norm_vars=nv)[1]
+                # cells in the fp32 noise floor of the FFT (conftest.fbank_parity; ~1e-6 of the cells of a white signal) are exempt
+                lin = lasr_frontend.wav_to_kaldi_fbank(wavs[i], dtype=np.float64, use_log_fbank=False)
+                ok = (lin / lin.sum(1, keepdims=True)) >= 1e-8
+                tol = (1e-5 + 1e-4 * np.abs(x)) * istd[None, :] * 2.0 + 2e-5
+                assert int(((np.abs(g[i, :T] - ref) > tol) & ok).sum()) == 0, (mode, nv, i)
+                assert int((~ok).sum()) <= max(1, ok.size // 10000)
+                assert np.all(g[i, T:] == 0)
+                checked += 1
+        return checked
+
+    # (1) committed goldens
+    wavs = [fb["wav_%d" % i] for i in range(6)]
+    n1 = run(wavs, lambda key, i: (fb["fbank_%d" % i] if key == "fbank" else (cm["%s_%d" % (key, i)] if "%s_%d" % (key, i) in cm.files else None)))
+    assert n1 >= 17
+    # (2) live torchaudio on a ragged batch of broadband signals
+    rng = np.random.default_rng(5)
+    wavs = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in (16000, 16000 * 4 + 7, 8000, 16000 * 11, 1200)]
+    fbs = [kaldi.fbank(torch.from_numpy(w).float()[None] * 32768.0, num_mel_bins=80, dither=0.0, energy_floor=1.0).numpy() for w in wavs]
+    bounds = np.cumsum([0] + [x.shape[0] for x in fbs])
+
+    def cmn(x, nv):
+        t = torch.from_numpy(np.asarray(x, dtype=np.float64))[None]
+        return F.sliding_window_cmn(t, cmn_window=2 * t.shape[1] + 1000, min_cmn_window=1, center=True, norm_vars=nv)[0].numpy()
+
+    cat = {nv: cmn(np.concatenate(fbs), nv) for nv in (False, True)}
+
+    def live(key, i):
+        if key == "fbank":
+            return fbs[i]
+        if key.startswith("utt"):
+            return cmn(fbs[i], key == "utt_meanvar")
+        return cat[key == "global_meanvar"][bounds[i]:bounds[i + 1]]
+
+    assert run(wavs, live) >= 15
+
+
 def _run_specaug(lasr_b200, wavs, seed, replace_with_zero, cmvn_stats):
     wav, n = _pad(wavs)
     fe = lasr_b200.GpuFbankFrontend(cmvn="global", cmvn_stats=cmvn_stats, specaug=True, replace_with_zero=replace_with_zero)

@@ -134,6 +134,37 @@ def test_cmvn_definition():
     assert np.allclose(y.mean(0), 0, atol=1e-5) and np.allclose(y.std(0), 1, atol=1e-4)
 
 
+def test_cmvn_pinned_to_torchaudio_sliding_window_cmn(fb):
+    """Row A11: utterance CMVN (mean / mean + variance), the Kaldi statistics layout and global CMVN from accumulated statistics
+    against torchaudio.functional.sliding_window_cmn (torchaudio's port of Kaldi's apply-cmvn-sliding) with a window that covers
+    the whole matrix -- on one utterance that is utterance CMVN, on the concatenated corpus it is global CMVN
+    (oracle/gen_golden.py --cmvn; inputs are the reference's own fbank:80 outputs)."""
+    cm = np.load(os.path.join(GOLD, "cmvn_reference.npz"))
+    feats = [fb["fbank_%d" % i] for i in range(6)]
+    stats = lasr_frontend.cmvn_stats(feats)
+    assert stats[0, 80] == sum(x.shape[0] for x in feats)
+    for nv, ukey, gkey in ((False, "utt_mean", "global_mean"), (True, "utt_meanvar", "global_meanvar")):
+        mean, istd = lasr_frontend.cmvn_from_stats(stats, norm_vars=nv)
+        for i, x in enumerate(feats):
+            for key, (m, s) in ((gkey, (mean, istd)), (ukey, lasr_frontend.cmvn_from_stats(lasr_frontend.cmvn_stats([x]), norm_vars=nv))):
+                if "%s_%d" % (key, i) not in cm.files:
+                    continue
+                ref = cm["%s_%d" % (key, i)]
+                # (a) the DEFINITION (statistics layout, mean, population variance, no epsilon) in float64: equal to torchaudio's
+                #     result up to the cancellation in sumsq / n - mean^2 (relative 1e-16 * mean^2 / var)
+                x64 = x.astype(np.float64)
+                d64 = np.abs((x64 - m) * s - ref)
+                assert np.all(d64 <= 1e-9 + 1e-9 * (np.abs(x64) + np.abs(m)) ** 2 * s * s), (key, i, d64.max())
+                # (b) the float32 evaluation the device epilogue mirrors: the tolerance plus the rounding of (x - mean) in float32
+                #     (half an ulp of |x| and of |mean|), amplified by istd where a column hardly varies
+                y = lasr_frontend.apply_cmvn(x, m, s)
+                band = 1e-5 + 1e-4 * np.abs(ref) + 2.4e-7 * (np.abs(x64) + np.abs(m)) * s
+                assert np.all(np.abs(y - ref) <= band), (key, i)
+    # one frame: sliding_window_cmn divides by a zero variance; the definition floors it (Kaldi's apply-cmvn floor 1e-20)
+    assert feats[0].shape[0] == 1 and "utt_meanvar_0" not in cm.files
+    assert np.all(lasr_frontend.utterance_cmvn(feats[0]) == 0)
+
+
 def test_masks_match_reference_fixture():
     """make_pad_mask / the encoder source mask / Conv2dSubsampling's mask slicing / hs_len against the reference's own
     functions (oracle/gen_golden.py: lasr.utils.mask.make_pad_mask + the slicing of subsampling.py:60)."""
