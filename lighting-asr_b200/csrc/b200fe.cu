@@ -321,8 +321,10 @@ extern "C" int b200fe_plan_create(const b200fe_opts* opts, b200fe_plan** out)
     }
     p->static_mel = 0;
     if (p->nfft == 512 && p->nload == 13 && p->nmel == B200FE_STATIC_NMEL && o.use_power && o.dither == 0.f) {
-        bool same = memcmp(p->seg_start, kStaticSegStart, sizeof(short) * (p->nmel + 3)) == 0 &&
-                    memcmp(p->grp_begin, kStaticGrpBegin, sizeof kStaticGrpBegin) == 0;
+        // (the straight-line code carries its own bin groups, kStaticGrpBegin: min-max balanced by the generator; p->grp_begin
+        // only serves the generic phase B)
+        bool same = memcmp(p->seg_start, kStaticSegStart, sizeof(short) * (p->nmel + 3)) == 0;
+        (void)kStaticGrpBegin;
         for (int k = 0; same && k < 256; ++k) same = (p->w_updn[k].x == kStaticUp[k] && p->w_updn[k].y == kStaticDn[k]);
         p->static_mel = same ? 1 : 0;
     }

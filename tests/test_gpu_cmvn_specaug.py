@@ -97,7 +97,7 @@ def test_cmvn_against_torchaudio_sliding_window_cmn(lasr_b200):
         gmean, gistd = {}, {}
         for nv in (False, True):
             gmean[nv], gistd[nv] = lasr_frontend.cmvn_from_stats(lasr_frontend.cmvn_stats(fbs), norm_vars=nv)
-        checked = 0
+        checked = floor_cells = cells = 0
         for mode, nv, key in (("utt_mean", False, "utt_mean"), ("utt_meanvar", True, "utt_meanvar"), ("global", False, "global_mean"),
                               ("global", True, "global_meanvar")):
             fe = lasr_b200.GpuFbankFrontend(cmvn=mode, cmvn_stats=st if mode == "global" else None)
@@ -118,9 +118,11 @@ def test_cmvn_against_torchaudio_sliding_window_cmn(lasr_b200):
                 ok = (lin / lin.sum(1, keepdims=True)) >= 1e-8
                 tol = (1e-5 + 1e-4 * np.abs(x)) * istd[None, :] * 2.0 + 2e-5
                 assert int(((np.abs(g[i, :T] - ref) > tol) & ok).sum()) == 0, (mode, nv, i)
-                assert int((~ok).sum()) <= max(1, ok.size // 10000)
+                floor_cells += int((~ok).sum())
+                cells += ok.size
                 assert np.all(g[i, T:] == 0)
                 checked += 1
+        assert floor_cells <= 4 + cells // 10000          # the exemption stays a handful of cells
         return checked
 
     # (1) committed goldens

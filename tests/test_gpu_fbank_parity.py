@@ -39,6 +39,9 @@ def test_c1_uniform_batch(lasr_b200):
     torch.cuda.synchronize()
     assert feats.shape == (16, 998, 80) and feats.dtype == torch.float32
     assert flen.cpu().tolist() == [998] * 16
+    # LASR's default option set must run the kernel with the straight-line (generated) mel projection, not the generic tables
+    plan = fe.plan(wav.device)
+    assert plan.lib.b200fe_plan_info(plan.handle, 0) == 1
     g = feats.cpu().numpy()
     worst, n_below, n_direct = 0.0, 0, 0
     for i, w in enumerate(wavs):

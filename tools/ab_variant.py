@@ -26,6 +26,7 @@ for i in range(3):
     bad += int((d > 1e-5 + 1e-4 * np.abs(ref)).sum()); cells += ref.size
 res = {"variant": name, "violations": bad, "cells": cells}
 plan = fe.plan(dev)
+res["static_mel"] = plan.lib.b200fe_plan_info(plan.handle, 0)
 res["ctas_per_sm"] = plan.lib.b200fe_plan_info(plan.handle, 3)
 res["warps_per_cta"] = plan.lib.b200fe_plan_info(plan.handle, 9)
 res["smem_per_cta"] = plan.lib.b200fe_plan_info(plan.handle, 2)

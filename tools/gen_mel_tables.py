@@ -56,21 +56,77 @@ def tables(num_mel=80, padded=512, sample_freq=16000.0, low=20.0, high=0.0):
     return W, seg, up, dn, seg_start
 
 
-def groups(seg_start, num_mel, n_groups=8):
-    # (a model closer to the instruction counts, 1.0 per non-zero weight + 5 per bin, evens the groups out to 115..135 instructions
-    # instead of 92..155, but measured no faster: the phase-B barrier is not where the time goes)
-    cost = np.array([(seg_start[j + 2] - seg_start[j]) * 0.5 + 6.0 for j in range(num_mel)])
-    tot = cost.sum()
-    g = [0]
-    j, acc = 0, 0.0
-    for w in range(1, n_groups):
-        target = tot * w / n_groups
-        while j < num_mel and acc + cost[j] * 0.5 < target:
-            acc += cost[j]
-            j += 1
-        g.append(j)
-    g.append(num_mel)
-    return g
+def group_cost(jb, je, seg_start, up, dn):
+    """Instructions of group_code(jb, je): one multiply(-add) per non-zero weight, one store per bin, one add where a bin uses two
+    chains, one float4 load per four FFT bins of the group's range."""
+    n = 0
+    for j in range(jb, je):
+        t = sum(1 for k in range(int(seg_start[j]), int(seg_start[j + 1])) if up[k] != 0.0)
+        t += sum(1 for k in range(int(seg_start[j + 1]), int(seg_start[j + 2])) if dn[k] != 0.0)
+        n += t + 1 + (1 if t >= 4 else 0)
+    return n + ((int(seg_start[je + 1]) - 1) >> 2) - (int(seg_start[jb]) >> 2) + 1
+
+
+def groups(seg_start, num_mel, n_groups=8, up=None, dn=None):
+    """Contiguous bin groups (one per warp of phase B) that minimise the LARGEST group: the phase ends at a CTA barrier, so the
+    slowest warp sets its length.  Exact dynamic programme over the cut points."""
+    if up is None:                     # the warp-specialised kernel keeps the older segment-length model
+        cost = np.array([(seg_start[j + 2] - seg_start[j]) * 0.5 + 6.0 for j in range(num_mel)])
+        tot = cost.sum()
+        g = [0]
+        j, acc = 0, 0.0
+        for w in range(1, n_groups):
+            target = tot * w / n_groups
+            while j < num_mel and acc + cost[j] * 0.5 < target:
+                acc += cost[j]
+                j += 1
+            g.append(j)
+        g.append(num_mel)
+        return g
+    INF = 10 ** 9
+    c = [[group_cost(a, b, seg_start, up, dn) if b > a else INF for b in range(num_mel + 1)] for a in range(num_mel + 1)]
+    best = [[INF] * (num_mel + 1) for _ in range(n_groups + 1)]
+    arg = [[0] * (num_mel + 1) for _ in range(n_groups + 1)]
+    best[0][0] = 0
+    for w in range(1, n_groups + 1):
+        for b in range(w, num_mel + 1):
+            for a in range(w - 1, b):
+                v = max(best[w - 1][a], c[a][b])
+                if v < best[w][b]:
+                    best[w][b], arg[w][b] = v, a
+    g, b = [num_mel], num_mel
+    for w in range(n_groups, 0, -1):
+        b = arg[w][b]
+        g.append(b)
+    return g[::-1]
+
+
+def group_code(w, jb, je, seg_start, up, dn):
+    """Straight-line code of one bin group: every float4 of the power row the group touches is loaded first (the loads are
+    independent of everything else, so they overlap instead of each sitting in front of its first use), then every bin is one or
+    two multiply-add chains over its non-zero weights -- no zero-initialised accumulators (an `0.f + x` survives optimisation: it
+    is not an identity for x = -0) and no adds of empty partial sums."""
+    comp = "xyzw"
+    k_lo, k_hi = int(seg_start[jb]), int(seg_start[je + 1])
+    lines = ["MGROUP_BEGIN(%d)" % w]
+    if k_hi > k_lo:
+        lines.append("const float4 " + ", ".join("q%d = pcol[%d]" % (c, c) for c in range(k_lo >> 2, ((k_hi - 1) >> 2) + 1)) + ";")
+    for j in range(jb, je):
+        terms = [(up[k] * 0.25, k) for k in range(int(seg_start[j]), int(seg_start[j + 1])) if up[k] != 0.0]
+        terms += [(dn[k] * 0.25, k) for k in range(int(seg_start[j + 1]), int(seg_start[j + 2])) if dn[k] != 0.0]
+        p = lambda k: "q%d.%s" % (k >> 2, comp[k & 3])
+        if not terms:
+            lines.append("emit_bin(orow, %d, 0.f);" % j)
+            continue
+        chains = [terms] if len(terms) < 4 else [terms[0::2], terms[1::2]]
+        body = []
+        for ci, ch in enumerate(chains):
+            body.append("float r%d = %.9ef * %s;" % (ci, ch[0][0], p(ch[0][1])))
+            for wt, k in ch[1:]:
+                body.append("r%d = fmaf(%.9ef, %s, r%d);" % (ci, wt, p(k), ci))
+        lines.append("{ " + " ".join(body) + " emit_bin(orow, %d, %s); }" % (j, "r0" if len(chains) == 1 else "r0 + r1"))
+    lines.append("MGROUP_END(%d)" % w)
+    return lines
 
 
 def main():
@@ -79,9 +135,10 @@ def main():
     out = []
     out.append("// GENERATED by tools/gen_mel_tables.py -- do not edit.")
     out.append("// Mel projection for sample_frequency=16000, padded window 512, num_mel_bins=80, low_freq=20, high_freq=0.")
-    out.append("// MK(k, up, down): accumulate FFT bin k;  MEND0(): close the leading segment of a group;")
-    out.append("// MEND(j): bin j is complete (its down-slope segment just ended).  One section per CTA shape")
-    out.append("// (B200FE_WARPS warps per CTA = number of bin groups).")
+    out.append("// Device sections: one straight-line function per bin group (float4 loads of the power row first, then one or two")
+    out.append("// multiply-add chains per bin); one section per CTA shape (B200FE_WARPS warps per CTA = number of bin groups).")
+    out.append("// Warp-specialised kernel: MK(k, up, down) accumulates FFT bin k, MEND0() closes the leading segment of a group,")
+    out.append("// MEND(j): bin j is complete (its down-slope segment just ended).")
     out.append("#define B200FE_STATIC_NMEL %d" % num_mel)
     out.append("#ifdef B200FE_MEL_HOST_TABLES")
     out.append("static const short kStaticSegStart[%d] = {%s};" % (len(seg_start), ", ".join(str(int(v)) for v in seg_start)))
@@ -89,22 +146,14 @@ def main():
     out.append("static const float kStaticDn[256] = {%s};" % ", ".join("%.9ef" % (v * 0.25) for v in dn))
     out.append("#endif")
     for ng in (8, 6):
-        grp = groups(seg_start, num_mel, ng)
+        grp = groups(seg_start, num_mel, ng, up, dn)
         out.append("#if B200FE_WARPS == 8 || B200FE_WARPS == 4" if ng == 8 else "#if B200FE_WARPS == %d" % ng)   # 16-frame tiles: one group per half-warp
         out.append("#ifdef B200FE_MEL_HOST_TABLES")
         out.append("static const short kStaticGrpBegin[9] = {%s};" % ", ".join(str(v) for v in (grp + [num_mel] * 9)[:9]))
         out.append("#endif")
         out.append("#ifdef B200FE_MEL_DEVICE_CODE")
         for w in range(ng):
-            jb, je = grp[w], grp[w + 1]
-            out.append("MGROUP_BEGIN(%d)" % w)
-            for s_ in range(jb, je + 1):
-                for k in range(int(seg_start[s_]), int(seg_start[s_ + 1])):
-                    u = up[k] * 0.25 if s_ < je else 0.0      # the trailing segment only feeds bin je-1 (down)
-                    d = dn[k] * 0.25 if s_ > jb else 0.0      # the leading segment only feeds bin jb (up)
-                    out.append("MK(%d, %.9ef, %.9ef)" % (k, u, d))
-                out.append("MEND0()" if s_ == jb else "MEND(%d)" % (s_ - 1))
-            out.append("MGROUP_END(%d)" % w)
+            out.extend(group_code(w, grp[w], grp[w + 1], seg_start, up, dn))
         out.append("#endif")
         out.append("#endif")
     # warp-specialised kernel (fbank_ws_kernel.cuh): one group per epilogue warp
@@ -125,7 +174,7 @@ def main():
             out.append("MGROUP_END(%d)" % w)
         out.append("#endif")
     out.append("#endif")
-    grp = groups(seg_start, num_mel, 8)
+    grp = groups(seg_start, num_mel, 8, up, dn)
     path = os.path.join(ROOT, "lighting-asr_b200", "csrc", "mel_static_default.inc")
     open(path, "w").write("\n".join(out) + "\n")
     nk = sum(int(seg_start[grp[w + 1] + 1] - seg_start[grp[w]]) for w in range(8))
