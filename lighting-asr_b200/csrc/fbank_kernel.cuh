@@ -853,6 +853,45 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         tma_load_1d(smem + L.tile_off[stage], src, bytes, &bars[stage]);
     };
 
+    // ---- descriptor pipeline (frame / padding tiles of the batch kernels) ------------------------------------------------------
+    // resolve() is a chain of three dependent global accesses (work counter -> tile table -> sample count, ~2 us): run in one go at
+    // the top of a tile it stalls warp 0 for a sixth of the tile period, and every CTA barrier then waits for warp 0 (ncu source
+    // page, second session of round 2: 11 % of warp 0's samples on that chain, 7.5 % of ALL warp time at the phase-A barrier).
+    // The chain is therefore spread over three tiles: each tile issues one access per stage and consumes what the previous tile
+    // requested, so thread 0 never waits for global memory.  In flight (registers of thread 0): the claimed id, the table entry
+    // of the id claimed one tile earlier, the sample count of the entry loaded one tile earlier; the rest of the state and the
+    // finished descriptor rest in shared memory (s_pipe, private to thread 0) so that nothing else stays live across phase A.
+    constexpr bool kPipe = !kMulti && !kApply;
+    int* s_pipe = s_sig;        // [0] id, [1] utterance, [2] first frame of the entry whose sample count is in flight; [3] id whose entry is in flight;
+                                // [4] next id of the static schedule; [5..8] descriptor finished at the top of this tile (published after the phase-A barrier)
+    int p_id = 0;
+    int2 p_ent = make_int2(0, 0);
+    unsigned p_n = 0u;
+    auto claim = [&]() -> int {                            // thread 0
+        if (dyn) return atomicAdd(a.work_counter, 1);
+        const int id = s_pipe[4];
+        s_pipe[4] = id + (int)gridDim.x;
+        return id;
+    };
+    auto entry_of = [&](int id) -> int2 {                  // (utterance, first frame); issues the load, does not wait for it
+        if (id >= ntiles) return make_int2(0, 0);
+        if (dyn) return __ldg(a.tile_table + id);
+        const int u = (int)((unsigned)id / (unsigned)a.tiles_per_utt);
+        return make_int2(u, (id - u * a.tiles_per_utt) * kFT);
+    };
+    auto nsamp_of = [&](int id, int2 e) -> unsigned {      // padding tiles (first frame < 0) need no sample count
+        if (id >= ntiles || e.y < 0) return 0u;
+        return (unsigned)__ldg(a.nsamp + e.x);
+    };
+    auto finish = [&](int id, int2 e, unsigned n) -> Desc {
+        Desc d; d.id = id; d.utt = 0; d.f0 = 0; d.T = 0;
+        if (id < ntiles) {
+            d.utt = e.x; d.f0 = e.y;
+            if (e.y >= 0) d.T = n >= (unsigned)a.win ? (int)(1u + (n - (unsigned)a.win) / (unsigned)a.shift) : 0;
+        }
+        return d;
+    };
+
     int it = 0;
     uint32_t phase_bits = 0, consumed_phase = 0;
     // in-launch utterance CMVN: thread 0 collects the utterances of completed frame tiles (a tile is complete at the next CTA-wide
@@ -872,7 +911,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         if (force || s_sig[0] >= kSigBatch) flush_signals();
     };
 
-    if (tid == 0) {
+    if (tid == 0 && kPipe) {
+        // five tiles claimed up front: two finished descriptors, three stages of the pipeline primed (independent loads: they overlap)
+        if (!dyn) s_pipe[4] = (int)blockIdx.x;
+        const int i0 = claim(), i1 = claim(), i2 = claim(), i3 = claim();
+        p_id = claim();
+        const int2 e0 = entry_of(i0), e1 = entry_of(i1), e2 = entry_of(i2);
+        p_ent = entry_of(i3);
+        const unsigned n0 = nsamp_of(i0, e0), n1 = nsamp_of(i1, e1);
+        p_n = nsamp_of(i2, e2);
+        const Desc d0 = finish(i0, e0, n0), d1 = finish(i1, e1, n1);
+        s_desc[0] = make_int4(d0.id, d0.utt, d0.f0, d0.T);
+        s_desc[1] = make_int4(d1.id, d1.utt, d1.f0, d1.T);
+        s_pipe[0] = i2; s_pipe[1] = e2.x; s_pipe[2] = e2.y; s_pipe[3] = i3;
+    } else if (tid == 0) {
         const int id0 = dyn ? atomicAdd(a.work_counter, 1) : (int)blockIdx.x;
         const int id1 = dyn ? atomicAdd(a.work_counter, 1) : (int)(blockIdx.x + gridDim.x);
         const Desc d0 = resolve(id0), d1 = resolve(id1);
@@ -891,7 +943,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         const TileGeom gn = geom(nxt);
         Desc fut; fut.id = ntiles; fut.utt = 0; fut.f0 = 0; fut.T = 0;
         int4 nxt_desc = make_int4(ntiles, 0, 0, 0);
-        if (tid == 0) {
+        if (tid == 0 && kPipe) {
+            // descriptor of the tile after next from the sample count requested one tile ago; then every stage moves on by one
+            const int pe_id = s_pipe[3];
+            const Desc d = finish(s_pipe[0], make_int2(s_pipe[1], s_pipe[2]), p_n);
+            s_pipe[5] = d.id; s_pipe[6] = d.utt; s_pipe[7] = d.f0; s_pipe[8] = d.T;
+            s_pipe[0] = pe_id; s_pipe[1] = p_ent.x; s_pipe[2] = p_ent.y;
+            p_n = nsamp_of(pe_id, p_ent);
+            s_pipe[3] = p_id;
+            p_ent = entry_of(p_id);
+            p_id = claim();
+        } else if (tid == 0) {
             // descriptor of the tile after next: its loads complete while this tile is being computed
             const int id2 = dyn ? atomicAdd(a.work_counter, 1) : nxt.id + (int)gridDim.x;
             fut = resolve(nxt.id < ntiles ? id2 : ntiles);
@@ -1037,7 +1099,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
             TL_STAMP(3);
             if (tid == 0) {
                 if (!kEarlyTma && a.use_tma && nxt.id < ntiles) issue_load(gn, 0);
-                s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);     // read by everyone after B2
+                if (kPipe) s_desc[it & 1] = make_int4(s_pipe[5], s_pipe[6], s_pipe[7], s_pipe[8]);     // read by everyone after B2
+                else s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
                 if (kApply) signal_pending(false);        // after the TMA issue: the fence must not delay the next tile's load
             }
             if (kApply) pending = utt;
@@ -1353,7 +1416,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
         // No closing barrier: a warp that finishes phase C goes straight to the next tile's phase A.  (A tile
         // without frames has no B1 / B2, so the descriptor exchange gets its own barrier.)
         if (nvalid <= 0) {
-            if (tid == 0) s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
+            if (tid == 0) {
+                if (kPipe) s_desc[it & 1] = make_int4(s_pipe[5], s_pipe[6], s_pipe[7], s_pipe[8]);
+                else s_desc[it & 1] = make_int4(fut.id, fut.utt, fut.f0, fut.T);
+            }
             __syncthreads();
             nxt_desc = s_desc[it & 1];
             if (kApply) {
