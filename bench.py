@@ -538,7 +538,7 @@ def main():
             "e2e": {"value": v(e2e_h, e2e_ms), "unit": "audio-h/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": per,
                     "api": "lasr_b200.lasr_plugin.B200Collate(to_host=True, cmvn='utt_meanvar')(list of 256 float64 ndarrays) -> {'wav_array': pinned host (B, Tmax, 80) "
                            "float32, 'wav_len': (B,) int64}; synchronous call, rotating distinct batches",
-                    "host_threads": pipe.threads, "host_pack_convert_ms": pack_ms,
+                    "host_threads": pipe.threads, "host_isa": ["sse2", "avx512f"][pipe.lib.b200fe_host_isa()], "host_pack_convert_ms": pack_ms,
                     "pcie_floor_ms": fl_both, "vs_pcie_floor": per / fl_both if fl_both > 0 else None,
                     # float64 lists are bound by the HOST memory system, not by PCIe: per step the cores read 8 B/sample and write 4 B/sample
                     # (pack), the DMA engines read those 4 B/sample again and write the features; the pack alone measures what this box's

@@ -266,6 +266,9 @@ typedef struct b200fe_host_pool b200fe_host_pool;
 int b200fe_host_pool_create(int n_threads /* <= 0: one per hardware thread */, b200fe_host_pool** pool);
 void b200fe_host_pool_destroy(b200fe_host_pool* pool);
 int b200fe_host_pool_threads(const b200fe_host_pool* pool);
+/* Instruction set of the packing / zero-fill loops, chosen once at load time: 0 = SSE2, 1 = AVX-512F (64-byte loads, whole-line
+ * non-temporal stores, L2 prefetch ahead of the loads; B200FE_HOST_ISA=sse2 in the environment forces the baseline). */
+int b200fe_host_isa(void);
 /* Utterance u: nsamp[u] elements from h_src[u] go to h_dst + dst_offsets[u] (elements of the DESTINATION type; starts must be
  * 16-byte aligned); the gap up to the next 16-byte boundary is cleared.  src_dtype: 0 float32 -> float32, 1 int16 -> int16
  * (PCM as the file holds it), 2 float64 -> float32.  dst_capacity = elements h_dst can hold. */

@@ -31,6 +31,8 @@ def _units():
     inc = os.path.join(os.path.dirname(HERE), "include", "b200fe.h")
     units = [(os.path.join(OBJ, "b200fe.o"), os.path.join(CSRC, "b200fe.cu"), [],
               [os.path.join(CSRC, "b200fe.cu"), inc] + [os.path.join(CSRC, h) for h in MAIN_HDRS])]
+    # host-only SIMD loops of the staging pool: a .cpp, i.e. nvcc hands it to the host compiler untouched (function-level target attributes)
+    units.append((os.path.join(OBJ, "host_simd.o"), os.path.join(CSRC, "host_simd.cpp"), [], [os.path.join(CSRC, "host_simd.cpp")]))
     for g in range(_groups()):
         units.append((os.path.join(OBJ, "fbank_inst_%d.o" % g), os.path.join(CSRC, "fbank_inst.cu"), ["-DB200FE_INST_GROUP=%d" % g],
                       [os.path.join(CSRC, "fbank_inst.cu")] + [os.path.join(CSRC, h) for h in KERNEL_HDRS]))

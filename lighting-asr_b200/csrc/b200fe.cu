@@ -532,6 +532,7 @@ extern "C" int b200fe_host_pool_create(int n_threads, b200fe_host_pool** pool)
 }
 extern "C" void b200fe_host_pool_destroy(b200fe_host_pool* pool) { delete pool; }
 extern "C" int b200fe_host_pool_threads(const b200fe_host_pool* pool) { return pool ? (int)pool->threads.size() : 0; }
+extern "C" int b200fe_host_isa(void) { return b200fe_host::host_isa(); }
 
 static long long host_pack_submit(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
                                   void* h_dst, const long long* dst_offsets, long long dst_capacity, std::function<void()> on_done)

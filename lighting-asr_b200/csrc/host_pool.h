@@ -3,7 +3,7 @@
 //     float64 from soundfile.read, R/lasr/data/reader.py:24) into one pinned staging buffer, converting float64 -> float32
 //     on the way (the `.float()` of WavToKaldiFbank, R/lasr/data/datatrans.py:73) with non-temporal stores, and
 //   * zero-fills the padding rows of the host feature batch (pad_audio = 0, R/lasr/data/dataset.py:18)
-// while the GPU works.  Plain C++11 threads; no CUDA calls in here.
+// while the GPU works.  Plain C++11 threads; no CUDA calls in here (the SIMD loops live in host_simd.cpp).
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -16,9 +16,6 @@
 #include <mutex>
 #include <thread>
 #include <vector>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 
 namespace b200fe_host {
 
@@ -39,63 +36,17 @@ struct Task {
     std::shared_ptr<Job> job;
 };
 
-inline void cvt_f64_f32(const double* __restrict__ s, float* __restrict__ d, long long n)
-{
-    long long i = 0;
-#if defined(__SSE2__)
-    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-        for (; i + 8 <= n; i += 8) {
-            const __m128 a = _mm_cvtpd_ps(_mm_loadu_pd(s + i)), b = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 2));
-            const __m128 c = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 4)), e = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 6));
-            _mm_stream_ps(d + i, _mm_movelh_ps(a, b));          // the staging buffer is read next by the DMA engine, not by a core
-            _mm_stream_ps(d + i + 4, _mm_movelh_ps(c, e));
-        }
-        _mm_sfence();
-    }
-#endif
-    for (; i < n; ++i) d[i] = (float)s[i];
-}
-
-// Zero fill of (pinned) memory nobody will read from a core before the GPU / trainer does: non-temporal stores, no
-// read-for-ownership traffic (a 1 MB memset stays below glibc's non-temporal threshold and costs twice the DRAM traffic).
-inline void zero_stream(void* dst, long long n)
-{
-    char* d = static_cast<char*>(dst);
-#if defined(__SSE2__)
-    while (n > 0 && (reinterpret_cast<uintptr_t>(d) & 15) != 0) { *d++ = 0; --n; }
-    const __m128i z = _mm_setzero_si128();
-    long long i = 0;
-    for (; i + 64 <= n; i += 64) {
-        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), z); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), z);
-        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), z); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), z);
-    }
-    _mm_sfence();
-    d += i; n -= i;
-#endif
-    if (n > 0) memset(d, 0, (size_t)n);
-}
-
-// Copy into the (pinned) staging buffer with non-temporal stores.  glibc's memcpy switches to them only far above a task's
-// 256 kB, so a plain memcpy leaves the staged waveforms dirty in the cores' caches (and reads the destination lines first): the
-// DMA engine then has to snoop them out -- measured on the int16 plug-in call: H2D chunks at 27-39 GB/s instead of 52.
-inline void copy_stream(const void* src, void* dst, long long n)
-{
-    const char* s = static_cast<const char*>(src);
-    char* d = static_cast<char*>(dst);
-    long long i = 0;
-#if defined(__SSE2__)
-    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-        for (; i + 64 <= n; i += 64) {
-            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
-            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
-        }
-        _mm_sfence();
-    }
-#endif
-    if (i < n) memcpy(d + i, s + i, (size_t)(n - i));
-}
+// Streaming primitives (host_simd.cpp: SSE2 baseline and an AVX-512 variant with software prefetch, picked at load time).
+//   cvt_f64_f32: float64 -> float32 with non-temporal stores (the staging buffer is read next by the DMA engine, not by a core)
+//   zero_stream: zero fill of (pinned) memory nobody reads from a core before the GPU / trainer does: no read-for-ownership
+//                traffic (a 1 MB memset stays below glibc's non-temporal threshold and costs twice the DRAM traffic)
+//   copy_stream: copy with non-temporal stores.  glibc's memcpy switches to them only far above a task's 256 kB, so a plain
+//                memcpy leaves the staged waveforms dirty in the cores' caches (and reads the destination lines first): the DMA
+//                engine then has to snoop them out -- measured on the int16 plug-in call: H2D chunks at 27-39 GB/s instead of 52.
+void cvt_f64_f32(const double* s, float* d, long long n);
+void zero_stream(void* dst, long long n);
+void copy_stream(const void* src, void* dst, long long n);
+int host_isa();          // 0 SSE2, 1 AVX-512F
 
 inline void run_task(const Task& t)
 {

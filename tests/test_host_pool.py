@@ -47,6 +47,58 @@ def test_pack_list_of_utterances(pool, src_dtype, code, dst_dtype):
     assert lib.b200fe_host_wait(h, tk) != 0                                            # a ticket can be waited for once
 
 
+def test_pack_unaligned_sources_and_special_values(pool):
+    """The streaming loops (host_simd.cpp, SSE2 or AVX-512F picked at load time): sources at odd element offsets, lengths around the
+    vector widths, values that round, overflow or are not numbers -- element for element what numpy's astype(float32) gives."""
+    lib, h = pool
+    assert lib.b200fe_host_isa() in (0, 1)
+    rng = np.random.default_rng(11)
+    base = rng.normal(0, 1, 300000)
+    base[::97] *= 1e-42                       # float32 denormals
+    base[5::101] *= 1e39                      # beyond float32: +-inf
+    base[7::211] = np.nan
+    base[11::223] = np.inf
+    base[13::227] = 1.0 + 2.0 ** -24          # ties round to even
+    lens = np.array([0, 1, 15, 16, 17, 31, 33, 63, 64, 65, 127, 129, 1000, 65536, 65537, 70001], dtype=np.int64)
+    starts = np.arange(len(lens)) * 3 + 1     # odd element offsets: 8-byte aligned, not 16 / 64
+    wavs = [base[st:st + n] for st, n in zip(starts, lens)]
+    offs = np.zeros(len(lens), dtype=np.int64)
+    np.cumsum((lens[:-1] + 3) // 4 * 4, out=offs[1:])
+    total = int(offs[-1] + (lens[-1] + 3) // 4 * 4)
+    dst = _aligned(total, np.float32)
+    dst[:] = 99
+    ptrs = (C.c_void_p * len(wavs))(*[max(w.ctypes.data, 1) for w in wavs])
+    tk = lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, len(wavs), 2, dst.ctypes.data, offs.ctypes.data, total)
+    assert tk > 0 and lib.b200fe_host_wait(h, tk) == 0
+    with np.errstate(over="ignore"):
+        for w, o, n in zip(wavs, offs, lens):
+            assert np.array_equal(dst[o:o + n], w.astype(np.float32), equal_nan=True)
+    # byte copies (int16 / float32 lists) from odd byte offsets
+    raw = rng.integers(-32768, 32767, 200000).astype(np.int16)
+    lens16 = np.array([1, 7, 8, 9, 31, 32, 33, 255, 70003], dtype=np.int64)
+    w16 = [raw[1 + 5 * i:1 + 5 * i + n] for i, n in enumerate(lens16)]
+    offs16 = np.zeros(len(lens16), dtype=np.int64)
+    np.cumsum((lens16[:-1] + 7) // 8 * 8, out=offs16[1:])
+    tot16 = int(offs16[-1] + (lens16[-1] + 7) // 8 * 8)
+    d16 = _aligned(tot16, np.int16)
+    d16[:] = 99
+    p16 = (C.c_void_p * len(w16))(*[w.ctypes.data for w in w16])
+    tk = lib.b200fe_host_pack_begin(h, p16, lens16.ctypes.data, len(w16), 1, d16.ctypes.data, offs16.ctypes.data, tot16)
+    assert tk > 0 and lib.b200fe_host_wait(h, tk) == 0
+    for w, o, n in zip(w16, offs16, lens16):
+        assert np.array_equal(d16[o:o + n], w)
+    # zero fill of ranges that start and end anywhere
+    buf = np.full(5000, 7, dtype=np.uint8)
+    zo = np.array([1, 100, 1000, 4093], dtype=np.int64)
+    zn = np.array([63, 129, 2049, 7], dtype=np.int64)
+    tk = lib.b200fe_host_zero_ranges_begin(h, buf.ctypes.data, zo.ctypes.data, zn.ctypes.data, len(zo))
+    assert tk > 0 and lib.b200fe_host_wait(h, tk) == 0
+    want = np.full(5000, 7, dtype=np.uint8)
+    for o, n in zip(zo, zn):
+        want[o:o + n] = 0
+    assert np.array_equal(buf, want)
+
+
 def test_pack_argument_errors(pool):
     lib, h = pool
     w = np.zeros(10)
