@@ -40,6 +40,9 @@ namespace b200fe {
 // 0.3285 ms baseline): issuing the next tile's TMA as soon as every warp holds its last frames in registers instead of
 // after the phase-A barrier (0.3422 ms: the transfer then competes with phase A for the shared-memory pipe), and routing
 // the plain copy-out through the (row part, column) mapping of the statistics path (0.3400 ms: 240 of 256 threads, 11 rounds).
+#ifndef B200FE_DESC_PIPE
+#define B200FE_DESC_PIPE 1          // 0 (A/B runs): thread 0 resolves a tile descriptor in one blocking chain at the top of every tile, as in round 1
+#endif
 #ifndef B200FE_EARLY_TMA
 #define B200FE_EARLY_TMA 0
 #endif
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fbank_fused_kernel(const
     // requested, so thread 0 never waits for global memory.  In flight (registers of thread 0): the claimed id, the table entry
     // of the id claimed one tile earlier, the sample count of the entry loaded one tile earlier; the rest of the state and the
     // finished descriptor rest in shared memory (s_pipe, private to thread 0) so that nothing else stays live across phase A.
-    constexpr bool kPipe = !kMulti && !kApply;
+    constexpr bool kPipe = !kMulti && !kApply && B200FE_DESC_PIPE != 0;
     int* s_pipe = s_sig;        // [0] id, [1] utterance, [2] first frame of the entry whose sample count is in flight; [3] id whose entry is in flight;
                                 // [4] next id of the static schedule; [5..8] descriptor finished at the top of this tile (published after the phase-A barrier)
     int p_id = 0;
