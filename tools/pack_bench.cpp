@@ -1,3 +1,7 @@
+// Microbenchmark behind csrc/host_simd.cpp: float64 -> float32 packing of ~584 MB by N threads in 256 kB tasks (the host staging
+// pool's task size), SSE2 / AVX-512F non-temporal stores with and without software prefetch; best of 12 interleaved rounds.
+//   g++ -O3 -std=c++17 -pthread -o tools/pack_bench tools/pack_bench.cpp && tools/pack_bench 8
+// Results of the build container (Xeon model 207, 8 vCPUs): profiles/r03_host_simd.txt.
 #include <immintrin.h>
 #include <thread>
 #include <vector>
