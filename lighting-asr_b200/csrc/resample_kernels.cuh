@@ -2,9 +2,10 @@
 //
 // The reference resamples per utterance on the CPU with librosa's `kaiser_fast` (R/lasr/data/datatrans.py:16-20 -- resampy's
 // precomputed Kaiser-windowed sinc table) and perturbs speed with sox (datatrans.py:29-39: `speed` = resample by 1 / ratio and
-// keep the nominal rate).  Neither library is in this image, so their exact filters cannot be pinned; the filter used here is
-// the one of scipy.signal.resample_poly (firwin, Kaiser beta = 5, half length 10 * max(up, down)), built on the host by
-// lighting-asr_b200/resample.py and checked against scipy itself (tests/test_gpu_resample.py).  Index arithmetic of
+// keep the nominal rate).  Neither library is in this image, so their outputs cannot be pinned; the filter comes from the host
+// (lighting-asr_b200/resample.py): either librosa's path restated -- resampy's interpolation with its `kaiser_fast` window, which
+// for a rational ratio is one fixed FIR per output phase -- or the one of scipy.signal.resample_poly (firwin, Kaiser beta = 5,
+// half length 10 * max(up, down)), checked against scipy itself (tests/test_gpu_resample.py).  Index arithmetic of
 // scipy.signal.upfirdn / resample_poly:
 //     out[m] = sum_j h[(m + pre_remove) * down - j * up] * x[j]        (h zero outside [0, len))
 // One thread per output sample; the filter phase (t mod up) is warp-divergent only in its start index, every lane walks

@@ -94,7 +94,7 @@ class B200Collate:
     copied (what a DataLoader's prefetching does for the reference's CPU workers)."""
 
     def __init__(self, device="cuda:0", to_host=False, ring=3, threads=None, out_dtype=torch.float32, input_rate=None, speed_perturb=None,
-                 **frontend_kwargs):
+                 res_type="kaiser_fast", **frontend_kwargs):
         from .host_pipeline import HostPipeline
         from . import resample as _rs
         self.device = torch.device(device)
@@ -106,7 +106,8 @@ class B200Collate:
         # `soxspeed` (datatrans.py:29-39) with the reference's ratio list, e.g. speed_perturb=(1, 1.1, 0.9)
         rate = self.frontend.opts["sample_frequency"]
         if input_rate is not None and float(input_rate) != float(rate):
-            self.pipeline.resampler = _rs.Resampler(int(input_rate), int(rate))
+            # res_type="kaiser_fast": librosa's filter and index arithmetic, what `resample:16k` calls (datatrans.py:19); "poly": scipy's
+            self.pipeline.resampler = _rs.Resampler(int(input_rate), int(rate), res_type=res_type)
         if speed_perturb:
             self.pipeline.speed = _rs.SpeedPerturb(speed_perturb)
 

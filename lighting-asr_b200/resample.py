@@ -3,7 +3,9 @@
 Reference: ``ReSample`` = ``librosa.resample(wav, ssr, 16000, res_type="kaiser_fast")`` (lasr/data/datatrans.py:16-20) and
 ``SoxSpeedPt`` = sox ``speed`` with a ratio drawn by ``numpy.random.choice([1, 1.1, 0.9])`` (datatrans.py:29-39; ``speed``
 resamples by 1 / ratio and keeps the nominal rate, so pitch and tempo change together).  librosa / resampy / sox are not in
-this image and not vendored by the reference, so their exact filters cannot be pinned; the filter used here is
+this image and not vendored by the reference, so their exact filters cannot be pinned.  Two filters are offered:
+``res_type="kaiser_fast"`` restates librosa's path (resampy's sinc interpolation with its documented ``kaiser_fast`` window,
+re-expressed as a polyphase FIR; checked against the oracle's direct restatement of resampy's loop) and ``res_type="poly"`` is
 ``scipy.signal.resample_poly``'s default -- a Kaiser (beta = 5) windowed sinc of half length ``10 * max(up, down)`` -- restated
 below with numpy and checked against scipy itself in tests/test_gpu_resample.py.  The draws of ``SoxSpeedPt`` are replayed with
 the same ``numpy.random.choice`` call, one per utterance, so the global generator ends where the reference leaves it.
@@ -34,6 +36,52 @@ def poly_filter(up, down):
     return np.concatenate([np.zeros(n_pre_pad), h]), pre_remove
 
 
+def kaiser_fast_filter(up, down, num_zeros=16, precision=9, rolloff=0.85, beta=8.555504641634386):
+    """(h, pre_remove, n_valid_fn) for the device polyphase kernel such that it reproduces
+    ``librosa.resample(x, sr, sr * up / down, res_type="kaiser_fast")`` = resampy's band-limited sinc interpolation with its
+    ``kaiser_fast`` window (16 zero crossings, Kaiser beta 8.5555, roll-off 0.85, 512 table entries per zero crossing, linear
+    interpolation between entries; resampy/filters.py, resampy/interpn.py).
+
+    For a rational ratio the interpolation positions repeat with period ``up``: output m sits at input time m * down / up =
+    n + r / up, so resampy's two tap loops (left wing x[n - i], right wing x[n + 1 + k], weights read from the table at
+    ``offset + i * index_step`` with ``offset = int(frac * num_table)``, ``index_step = int(scale * num_table)`` -- truncations
+    included) are a fixed FIR per phase r.  They are laid out as one filter in the kernel's convention
+    ``out[m] = sum_j h[(m + pre_remove) * down - j * up] * x[j]``: q = (m * down - j * up) = r + i * up on the left wing,
+    r - (k + 1) * up on the right wing, shifted by pre_remove * down.  Phases are exact rationals here; resampy evaluates
+    ``t * (1 / ratio)`` in float64, which moves a weight by ~1e-13."""
+    num_table = 2 ** precision
+    n = num_table * num_zeros
+    win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True)) * np.kaiser(2 * n + 1, beta)[n:]
+    ratio = up / down
+    if ratio < 1:
+        win = win * ratio
+    delta = np.zeros_like(win)
+    delta[:-1] = np.diff(win)
+    scale = min(1.0, ratio)
+    index_step = int(scale * num_table)
+    nwin = win.shape[0]
+    max_taps = nwin // index_step + 1
+    pre_remove = -(-(max_taps * up) // down)                  # shift S = pre_remove * down >= max right-wing reach
+    S = pre_remove * down
+    h = np.zeros(S + (max_taps + 1) * up, dtype=np.float64)
+    for r in range(up):
+        frac = scale * (r / up)
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        i = np.arange((nwin - offset) // index_step)
+        idx = offset + i * index_step
+        h[S + r + i * up] = win[idx] + eta * delta[idx]       # left wing: x[n - i]
+        frac = scale - frac
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        k = np.arange((nwin - offset) // index_step)
+        idx = offset + k * index_step
+        h[S + r - (k + 1) * up] = win[idx] + eta * delta[idx]   # right wing: x[n + 1 + k]
+    return h, pre_remove
+
+
 def out_length(n, up, down):
     n = np.asarray(n, dtype=np.int64)
     return (n * up + down - 1) // down
@@ -42,7 +90,14 @@ def out_length(n, up, down):
 class Resampler:
     """Polyphase resampling ``src_rate -> dst_rate`` (or an explicit ``up`` / ``down``) of a packed ragged batch on the GPU."""
 
-    def __init__(self, src_rate=None, dst_rate=None, up=None, down=None):
+    def __init__(self, src_rate=None, dst_rate=None, up=None, down=None, res_type="poly"):
+        """``res_type``: ``"poly"`` = scipy.signal.resample_poly's filter (pinned against scipy); ``"kaiser_fast"`` = the filter
+        and the index arithmetic of ``librosa.resample(..., res_type="kaiser_fast")``, what the reference's ``resample:16k``
+        calls (datatrans.py:16-20; restated from resampy's documentation, the library is not in the image)."""
+        if res_type not in ("poly", "kaiser_fast"):
+            raise ValueError("res_type must be 'poly' or 'kaiser_fast'")
+        self.res_type = res_type
+        self.rates = (src_rate, dst_rate)
         if up is None:
             fr = Fraction(int(dst_rate), int(src_rate))
             up, down = fr.numerator, fr.denominator
@@ -53,8 +108,18 @@ class Resampler:
         self.identity = up == 1 and down == 1
         self._tables = {}
         if not self.identity:
-            h, self.pre_remove = poly_filter(up, down)
+            h, self.pre_remove = kaiser_fast_filter(up, down) if res_type == "kaiser_fast" else poly_filter(up, down)
             self.h = h.astype(np.float32)
+
+    def valid_lengths(self, n):
+        """Samples the resampler itself produces.  ``kaiser_fast``: resampy yields int(n * ratio) samples (the ratio as the
+        float64 quotient of the rates, as resampy computes it) and librosa pads with zeros to ceil(n * ratio) = out_lengths."""
+        n = np.asarray(n, dtype=np.int64)
+        if self.identity or self.res_type != "kaiser_fast":
+            return self.out_lengths(n)
+        src, dst = self.rates if self.rates[0] is not None else (self.down, self.up)
+        ratio = float(dst) / src
+        return np.minimum(np.array([int(int(v) * ratio) for v in n.reshape(-1)], dtype=np.int64).reshape(n.shape), self.out_lengths(n))
 
     def out_lengths(self, n):
         return np.asarray(n, dtype=np.int64).copy() if self.identity else out_length(n, self.up, self.down)
@@ -103,6 +168,11 @@ class Resampler:
             _lib.check(lib.b200fe_resample_poly(C.c_void_p(wav.data_ptr()), C.c_void_p(p), C.c_void_p(p + 8 * B), B, C.c_void_p(out.data_ptr()),
                                                 C.c_void_p(p + 16 * B), C.c_void_p(p + 24 * B), int(n_out.max()), C.c_void_p(h.data_ptr()), int(h.numel()),
                                                 self.up, self.down, int(self.pre_remove), 1.0, stream), "b200fe_resample_poly")
+            if self.res_type == "kaiser_fast":
+                # librosa's fix_length: where resampy stops one sample short of ceil(n * ratio), that sample is a zero
+                short = np.nonzero(self.valid_lengths(lens) < n_out)[0]
+                if len(short):
+                    out[torch.from_numpy(out_offsets[short] + n_out[short] - 1).to(dev)] = 0.0
         return out, n_out, out_offsets
 
 

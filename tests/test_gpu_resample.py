@@ -45,17 +45,55 @@ def test_resampler_matches_scipy_resample_poly(lasr_b200, src, dst):
     assert torch.equal(out2[: int(o2[-1] + n2[-1])], out[: int(o_out[-1] + n_out[-1])])
 
 
+@pytest.mark.parametrize("src,dst", [(16000, 8000), (8000, 16000), (44100, 16000), (48000, 16000), (22050, 16000)])
+def test_resampler_kaiser_fast_matches_the_librosa_restatement(lasr_b200, src, dst):
+    """`resample:16k` as the reference calls it: librosa.resample(wav, ssr, tsr, res_type="kaiser_fast") (datatrans.py:19).  The
+    device path (resampy's interpolation re-expressed as a polyphase FIR) against the oracle's direct restatement of resampy's
+    tap loops + librosa's length fix (oracle/resampy_port.py; the libraries themselves are absent: parity unpinned)."""
+    from oracle import resampy_port
+    rng = np.random.default_rng(src + 3 * dst)
+    wavs = [rng.uniform(-0.5, 0.5, n).astype(np.float32) for n in (4001, 6173, 441, 37, 2500)]
+    rs = lasr_b200.resample.Resampler(src, dst, res_type="kaiser_fast")
+    dw, lens, offs = _pack(wavs)
+    out, n_out, o_out = rs(dw, lens, offs)
+    got = out.cpu().numpy()
+    for w, n, o in zip(wavs, n_out, o_out):
+        want = resampy_port.librosa_resample(w.astype(np.float64), src, dst)
+        assert n == len(want) and o % 4 == 0                         # ceil(n * ratio) samples, librosa's fix_length
+        assert np.abs(got[o:o + n] - want).max() < 3e-6              # float32 taps and accumulation against the float64 oracle
+    # a tone well inside the pass band keeps its amplitude, one above the new Nyquist frequency is removed (decimation only)
+    t = np.arange(20000) / float(src)
+    tones = [np.sin(2 * np.pi * 0.2 * min(src, dst) * t).astype(np.float32), np.sin(2 * np.pi * 0.62 * min(src, dst) * t).astype(np.float32)]
+    dw, lens, offs = _pack(tones)
+    out, n_out, o_out = rs(dw, lens, offs)
+    g = out.cpu().numpy()
+    mid = lambda i: g[o_out[i] + 300:o_out[i] + n_out[i] - 300]
+    # (resampy truncates its table step, int(ratio * 512): at 44.1 -> 16 kHz the pass-band gain is 185.76 / 185 = 1.004, reproduced here)
+    assert abs(np.sqrt(2.0 * np.mean(mid(0).astype(np.float64) ** 2)) - 1.0) < 6e-3
+    if dst < src:
+        assert np.abs(mid(1)).max() < 1e-3
+
+
 def test_switchboard_path_16k_to_8k_features(lasr_b200):
     """16 kHz audio -> 8 kHz on the device -> the 8 kHz front end (BASELINE config 5's SwitchBoard shape) against live
     torchaudio on the scipy-resampled waveform."""
     from torchaudio.compliance import kaldi
     rng = np.random.default_rng(8)
     wavs = [rng.uniform(-0.5, 0.5, n) for n in (32000, 48001)]
-    col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, input_rate=16000, sample_frequency=8000.0)
-    batch = col(wavs)
-    f, fl = batch["wav_array"].numpy(), batch["wav_len"].tolist()
+    from oracle import resampy_port
+    for res_type in ("poly", "kaiser_fast"):
+        col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, input_rate=16000, sample_frequency=8000.0, res_type=res_type)
+        batch = col(wavs)
+        f, fl = batch["wav_array"].numpy(), batch["wav_len"].tolist()
+        _check_switchboard(wavs, f, fl, (lambda w: ss.resample_poly(w, 1, 2)) if res_type == "poly" else (lambda w: resampy_port.librosa_resample(w, 16000, 8000)))
+    # the drop-in default is the reference's own resampler
+    assert lasr_b200.lasr_plugin.B200Collate(DEV, input_rate=16000, sample_frequency=8000.0).pipeline.resampler.res_type == "kaiser_fast"
+
+
+def _check_switchboard(wavs, f, fl, resample):
+    from torchaudio.compliance import kaldi
     for i, w in enumerate(wavs):
-        w8 = ss.resample_poly(w, 1, 2)
+        w8 = resample(w)
         ref = kaldi.fbank(torch.from_numpy(w8.astype(np.float32) * 32768.0).unsqueeze(0), num_mel_bins=80, dither=0.0, energy_floor=1.0,
                           sample_frequency=8000.0).numpy()
         assert fl[i] == ref.shape[0]
