@@ -114,7 +114,7 @@ class HostPipeline:
         self.speed = None                   # resample.SpeedPerturb: one numpy.random.choice per utterance, then resampling by 1 / ratio
         # "kernel": one copy kernel per group writes the pinned batch; "dma": one cudaMemcpyAsync per utterance; "kernel_end" (A/B
         # only, tools/pipe_ablate3.py): one copy kernel for the whole batch after the last group's kernels, i.e. no D2H overlap
-        self.d2h_mode = "kernel"
+        self.d2h_mode = os.environ.get("B200FE_D2H_MODE", "kernel")       # + "dma_block": one DMA per group over the padded block (padding rows included)
         self.taper = os.environ.get("B200FE_TAPER", "1") != "0"
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
@@ -253,6 +253,8 @@ class HostPipeline:
             row0 = np.arange(B, dtype=np.int64) * (Tmax * D * osz)
             valid = [(int(a), int(a + t * D * osz)) for a, t in zip(row0, T_host) if t > 0]
             zr, self._hout[so].dirty = stale_ranges(self._hout[so].dirty, valid, hbytes)
+            if self.d2h_mode == "dma_block" and not bf16:
+                zr = []                                        # the block copies bring the device's zero rows along
             if zr:
                 zo = np.array([r[0] for r in zr], dtype=np.int64)
                 zn = np.array([r[1] - r[0] for r in zr], dtype=np.int64)
@@ -298,6 +300,15 @@ class HostPipeline:
                 ev_c = torch.cuda.Event()
                 ev_c.record(main)
                 s_out.wait_event(ev_c)
+                if self.d2h_mode == "dma_block" and not bf16:
+                    # ONE DMA per group: the group's utterances are one contiguous block of the padded layout on both sides; the
+                    # padding rows travel too (zeros written by the fused launch), so the pool has nothing to clear on the host
+                    with torch.cuda.stream(s_out):
+                        hfeats[b0:b1].copy_(dfeats[b0:b1], non_blocking=True)
+                    self.d2h_bytes += (b1 - b0) * Tmax * D * 4
+                    self._dev_stamp("d2h %d done" % g, s_out)
+                    self._stamp("issued")
+                    continue
                 if self.d2h_mode == "dma" and not bf16:
                     rows = np.ascontiguousarray(T_host[b0:b1].astype(np.int64))
                     _lib.check(lib.b200fe_d2h_ragged(C.c_void_p(dfeats.data_ptr() + b0 * Tmax * D * 4), D, Tmax, C.c_void_p(rows.ctypes.data), b1 - b0,
