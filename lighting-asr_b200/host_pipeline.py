@@ -116,6 +116,7 @@ class HostPipeline:
         # only, tools/pipe_ablate3.py): one copy kernel for the whole batch after the last group's kernels, i.e. no D2H overlap
         self.d2h_mode = os.environ.get("B200FE_D2H_MODE", "kernel")       # + "dma_block": one DMA per group over the padded block (padding rows included)
         self.taper = os.environ.get("B200FE_TAPER", "1") != "0"
+        self.head_taper = os.environ.get("B200FE_HEAD_TAPER", "1") != "0"       # measured: float64 call -0.8 %, int16 call -4..7 % (profiles/r03_host_simd.txt)
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
     def _stamp(self, label):
@@ -205,10 +206,15 @@ class HostPipeline:
         csum = np.cumsum(lens * esz)
         total_b = int(csum[-1])
         taper = self.taper and total_b >= 2 * self.group_bytes      # a batch of one or two groups gains nothing from more launches
+        head = self.head_taper and taper
         for b in range(B):
             acc += int(lens[b]) * esz
             left = total_b - int(csum[b])
             target = self.group_bytes
+            if head and len(bounds) <= 2:
+                # ... and so do the first groups (1/4, 1/2): nothing is on the link until the first group is packed and nothing comes
+                # back until it has gone up and through the kernels
+                target = self.group_bytes // (4 if len(bounds) == 1 else 2)
             if taper:
                 if left < self.group_bytes // 4:
                     target = self.group_bytes // 4
