@@ -269,6 +269,11 @@ int b200fe_host_pool_threads(const b200fe_host_pool* pool);
 /* Instruction set of the packing / zero-fill loops, chosen once at load time: 0 = SSE2, 1 = AVX-512F (64-byte loads, whole-line
  * non-temporal stores, L2 prefetch ahead of the loads; B200FE_HOST_ISA=sse2 in the environment forces the baseline). */
 int b200fe_host_isa(void);
+/* Data pointers of n NumPy arrays from the addresses of their Python objects (id(array)): the collate loop hands over a LIST of
+ * ndarrays (R/lasr/data/dataset.py:190-206) and asking each one for its address through the interpreter costs ~2 us per utterance
+ * -- half a millisecond of a C2 call before the first packing job can start.  data_offset = offset of PyArrayObject's `data` field
+ * (the first field after the object header: 16 on 64-bit CPython); the caller verifies it on a probe array before relying on it. */
+int b200fe_host_ndarray_data(const long long* py_objects, int n, void** data_out, int data_offset);
 /* Utterance u: nsamp[u] elements from h_src[u] go to h_dst + dst_offsets[u] (elements of the DESTINATION type; starts must be
  * 16-byte aligned); the gap up to the next 16-byte boundary is cleared.  src_dtype: 0 float32 -> float32, 1 int16 -> int16
  * (PCM as the file holds it), 2 float64 -> float32.  dst_capacity = elements h_dst can hold. */

@@ -533,6 +533,15 @@ extern "C" int b200fe_host_pool_create(int n_threads, b200fe_host_pool** pool)
 extern "C" void b200fe_host_pool_destroy(b200fe_host_pool* pool) { delete pool; }
 extern "C" int b200fe_host_pool_threads(const b200fe_host_pool* pool) { return pool ? (int)pool->threads.size() : 0; }
 extern "C" int b200fe_host_isa(void) { return b200fe_host::host_isa(); }
+extern "C" int b200fe_host_ndarray_data(const long long* py_objects, int n, void** data_out, int data_offset)
+{
+    if (!py_objects || !data_out || n < 0 || data_offset < 0 || (data_offset & 7) != 0) return fail(B200FE_EINVAL, "host_ndarray_data: bad argument");
+    for (int i = 0; i < n; ++i) {
+        if (py_objects[i] == 0) return fail(B200FE_EINVAL, "host_ndarray_data: null object %d", i);
+        data_out[i] = *reinterpret_cast<void* const*>(static_cast<uintptr_t>(py_objects[i]) + (uintptr_t)data_offset);
+    }
+    return B200FE_OK;
+}
 
 static long long host_pack_submit(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
                                   void* h_dst, const long long* dst_offsets, long long dst_capacity, std::function<void()> on_done)

@@ -99,6 +99,22 @@ def test_pack_unaligned_sources_and_special_values(pool):
     assert np.array_equal(buf, want)
 
 
+def test_ndarray_data_pointers(pool):
+    """b200fe_host_ndarray_data: the data pointers of ndarrays from the addresses of their Python objects (what HostPipeline
+    uses instead of 256 __array_interface__ look-ups), on whole arrays, offset views and rows of a 2-D array."""
+    lib, h = pool
+    base = np.arange(1000, dtype=np.float64)
+    m = np.zeros((7, 33), dtype=np.int16)
+    arrs = [base, base[3:], base[10:500:1], m[4], np.zeros(0), np.zeros(5, dtype=np.float32)]
+    ids = np.fromiter(map(id, arrs), dtype=np.int64, count=len(arrs))
+    out = np.zeros(len(arrs), dtype=np.uint64)
+    assert lib.b200fe_host_ndarray_data(ids.ctypes.data, len(arrs), out.ctypes.data, 16) == 0
+    assert [int(v) for v in out] == [a.__array_interface__["data"][0] for a in arrs]
+    ids[2] = 0
+    assert lib.b200fe_host_ndarray_data(ids.ctypes.data, len(arrs), out.ctypes.data, 16) != 0
+    assert lib.b200fe_host_ndarray_data(ids.ctypes.data, len(arrs), out.ctypes.data, 12) != 0
+
+
 def test_pack_argument_errors(pool):
     lib, h = pool
     w = np.zeros(10)
