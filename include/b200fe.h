@@ -276,7 +276,10 @@ int b200fe_host_isa(void);
 int b200fe_host_ndarray_data(const long long* py_objects, int n, void** data_out, int data_offset);
 /* Utterance u: nsamp[u] elements from h_src[u] go to h_dst + dst_offsets[u] (elements of the DESTINATION type; starts must be
  * 16-byte aligned); the gap up to the next 16-byte boundary is cleared.  src_dtype: 0 float32 -> float32, 1 int16 -> int16
- * (PCM as the file holds it), 2 float64 -> float32.  dst_capacity = elements h_dst can hold. */
+ * (PCM as the file holds it), 2 float64 -> float32, 3 float64 that HOLDS 16-bit PCM values (k / 32768, what
+ * soundfile.read returns for PCM_16 files) -> int16 k: half the staging and PCIe bytes, bit-identical features; a sample that is
+ * not such a value raises the job's flag (b200fe_host_wait_flag) and the caller repeats the batch with src_dtype 2.
+ * dst_capacity = elements h_dst can hold. */
 long long b200fe_host_pack_begin(b200fe_host_pool* pool, const void* const* h_src, const long long* nsamp, int batch, int src_dtype,
                                  void* h_dst, const long long* dst_offsets, long long dst_capacity);
 /* b200fe_host_pack_begin plus the upload: the pool thread that finishes the job's last task issues ONE
@@ -293,6 +296,12 @@ long long b200fe_host_zero_rows_begin(b200fe_host_pool* pool, float* h_feats, in
  * batch buffer that still hold an earlier batch's rows and fall into this batch's padding. */
 long long b200fe_host_zero_ranges_begin(b200fe_host_pool* pool, void* h_base, const long long* offsets, const long long* nbytes, int n);
 int b200fe_host_wait(b200fe_host_pool* pool, long long ticket);
+/* b200fe_host_wait that also returns the job's flag: 1 when a task of a src_dtype 3 packing job met a sample that is not a PCM16
+ * value (the staged data of that job is then unusable), else 0. */
+int b200fe_host_wait_flag(b200fe_host_pool* pool, long long ticket, int* flag);
+/* 1 when `windows` windows of `window_len` float64 samples, spread evenly over every utterance, hold PCM16 values only (the cheap
+ * test before a batch is packed with src_dtype 3), 0 otherwise, negative on error. */
+int b200fe_host_pcm16_probe(const void* const* h_src, const long long* nsamp, int batch, int windows, int window_len);
 
 /* Host-only SpecAugment planner (no device work): the rectangles of the reference's `freq_mask` / `time_mask` and the
  * (center, warped) pair of `time_warp` for a whole batch, utterances in order, drawn exactly as the reference draws them

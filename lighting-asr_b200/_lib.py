@@ -66,7 +66,7 @@ EXPORTS = [
     "b200fe_peak_absmax", "b200fe_peak_absmax_i16", "b200fe_fbank_fused", "b200fe_h2d_ragged", "b200fe_d2h_ragged", "b200fe_copy_ragged", "b200fe_src_mask", "b200fe_specaug_plan", "b200fe_postpass", "b200fe_time_warp", "b200fe_cmvn_from_stats",
     "b200fe_cast_bf16", "b200fe_copy_ragged_bf16", "b200fe_resample_poly", "b200fe_avg_channels",
     "b200fe_stream_create", "b200fe_stream_destroy", "b200fe_stream_max_frames", "b200fe_stream_reset", "b200fe_stream_push", "b200fe_stream_flags",
-    "b200fe_host_pool_create", "b200fe_host_pool_destroy", "b200fe_host_pool_threads", "b200fe_host_isa", "b200fe_host_ndarray_data", "b200fe_host_pack_begin", "b200fe_host_pack_copy_begin", "b200fe_host_zero_rows_begin", "b200fe_host_zero_ranges_begin", "b200fe_host_wait",
+    "b200fe_host_pool_create", "b200fe_host_pool_destroy", "b200fe_host_pool_threads", "b200fe_host_isa", "b200fe_host_ndarray_data", "b200fe_host_pack_begin", "b200fe_host_pack_copy_begin", "b200fe_host_zero_rows_begin", "b200fe_host_zero_ranges_begin", "b200fe_host_wait", "b200fe_host_wait_flag", "b200fe_host_pcm16_probe",
 ]
 
 _lib = None
@@ -182,6 +182,10 @@ def load(build_if_missing=True):
     lib.b200fe_host_zero_ranges_begin.restype = c_ll
     lib.b200fe_host_wait.argtypes = [C.c_void_p, c_ll]
     lib.b200fe_host_wait.restype = C.c_int
+    lib.b200fe_host_wait_flag.argtypes = [C.c_void_p, c_ll, C.c_void_p]
+    lib.b200fe_host_wait_flag.restype = C.c_int
+    lib.b200fe_host_pcm16_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.b200fe_host_pcm16_probe.restype = C.c_int
     _lib = lib
     return lib
 

@@ -547,9 +547,9 @@ static long long host_pack_submit(b200fe_host_pool* pool, const void* const* h_s
                                   void* h_dst, const long long* dst_offsets, long long dst_capacity, std::function<void()> on_done)
 {
     if (!pool || !h_src || !nsamp || !h_dst || !dst_offsets || batch < 0) return fail(B200FE_EINVAL, "host_pack: bad argument");
-    if (src_dtype < 0 || src_dtype > 2) return fail(B200FE_EINVAL, "host_pack: src_dtype must be 0 (float32), 1 (int16) or 2 (float64)");
+    if (src_dtype < 0 || src_dtype > 3) return fail(B200FE_EINVAL, "host_pack: src_dtype must be 0 (float32), 1 (int16), 2 (float64) or 3 (float64 holding PCM16 values -> int16)");
     if ((reinterpret_cast<uintptr_t>(h_dst) & 15) != 0) return fail(B200FE_EINVAL, "host_pack: the staging buffer must be 16-byte aligned");
-    const long long dsz = src_dtype == 1 ? 2 : 4, ssz = src_dtype == 1 ? 2 : src_dtype == 2 ? 8 : 4, al = 16 / dsz;
+    const long long dsz = (src_dtype == 1 || src_dtype == 3) ? 2 : 4, ssz = src_dtype == 1 ? 2 : src_dtype >= 2 ? 8 : 4, al = 16 / dsz;
     const long long chunk = (256LL << 10) / dsz;                  // elements per task: 256 kB of destination
     std::vector<b200fe_host::Task> tasks;
     for (int u = 0; u < batch; ++u) {
@@ -560,10 +560,10 @@ static long long host_pack_submit(b200fe_host_pool* pool, const void* const* h_s
         for (long long c = 0; c < n || c == 0; c += chunk) {
             const long long m = std::min(chunk, n - c);
             b200fe_host::Task t;
-            t.kind = src_dtype == 2 ? 1 : 0;
+            t.kind = src_dtype == 2 ? 1 : src_dtype == 3 ? 3 : 0;
             t.src = static_cast<const char*>(h_src[u]) + c * ssz;
             t.dst = static_cast<char*>(h_dst) + (o + c) * dsz;
-            t.n = src_dtype == 2 ? m : m * dsz;
+            t.n = src_dtype >= 2 ? m : m * dsz;
             t.tail_zero = (c + m >= n) ? (padded - n) * dsz : 0;
             tasks.push_back(t);
             if (n == 0) break;
@@ -589,7 +589,7 @@ extern "C" long long b200fe_host_pack_copy_begin(b200fe_host_pool* pool, const v
         pool->bind_device = [](int dev) { cudaSetDevice(dev); cudaFree(nullptr); };
         pool->device.store(device);
     }
-    const long long dsz = src_dtype == 1 ? 2 : 4;
+    const long long dsz = (src_dtype == 1 || src_dtype == 3) ? 2 : 4;
     const char* hs = static_cast<const char*>(h_dst) + dst_offsets[0] * dsz;
     char* dd = static_cast<char*>(d_dst) + dst_offsets[0] * dsz;
     const size_t bytes = (size_t)(copy_elems * dsz);
@@ -636,6 +636,30 @@ extern "C" long long b200fe_host_zero_ranges_begin(b200fe_host_pool* pool, void*
     }
     if (tasks.empty()) { b200fe_host::Task t; t.kind = 2; t.src = nullptr; t.dst = h_base; t.n = 0; t.tail_zero = 0; tasks.push_back(t); }
     return pool->submit(tasks);
+}
+
+extern "C" int b200fe_host_wait_flag(b200fe_host_pool* pool, long long ticket, int* flag)
+{
+    if (!pool || ticket <= 0 || !flag) return fail(B200FE_EINVAL, "host_wait_flag: bad argument");
+    if (pool->wait(ticket, flag) != 0) return fail(B200FE_EINVAL, "host_wait_flag: unknown ticket %lld", ticket);
+    return B200FE_OK;
+}
+
+extern "C" int b200fe_host_pcm16_probe(const void* const* h_src, const long long* nsamp, int batch, int windows, int window_len)
+{
+    if (!h_src || !nsamp || batch < 0 || windows <= 0 || window_len <= 0) return fail(B200FE_EINVAL, "host_pcm16_probe: bad argument");
+    for (int u = 0; u < batch; ++u) {
+        const long long n = nsamp[u];
+        if (n < 0 || (n > 0 && !h_src[u])) return fail(B200FE_EINVAL, "host_pcm16_probe: utterance %d: bad length or pointer", u);
+        const double* s = static_cast<const double*>(h_src[u]);
+        for (int w = 0; w < windows; ++w) {
+            // windows spread over the utterance: leading digital silence holds PCM16 values whatever follows
+            const long long len = std::min<long long>(window_len, n);
+            const long long start = windows > 1 ? (n - len) * w / (windows - 1) : 0;
+            if (len > 0 && !b200fe_host::cvt_f64_pcm16(s + start, nullptr, len)) return 0;
+        }
+    }
+    return 1;
 }
 
 extern "C" int b200fe_host_wait(b200fe_host_pool* pool, long long ticket)

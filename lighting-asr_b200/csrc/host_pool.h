@@ -22,13 +22,14 @@ namespace b200fe_host {
 struct Job {
     std::atomic<long long> remaining{0};
     std::atomic<bool> done{false};
+    std::atomic<int> flag{0};           // set by a task that could not do what was asked (kind 3: a sample that is not a PCM16 value)
     std::function<void()> on_done;      // runs on the thread that finishes the job's last task, before waiters are released
     std::mutex m;
     std::condition_variable cv;
 };
 
 struct Task {
-    int kind;                 // 0 memcpy, 1 float64 -> float32, 2 zero fill
+    int kind;                 // 0 memcpy, 1 float64 -> float32, 2 zero fill, 3 float64 holding PCM16 values -> int16 (checked)
     const void* src;
     void* dst;
     long long n;              // bytes (kinds 0, 2) or elements (kind 1)
@@ -44,6 +45,7 @@ struct Task {
 //                memcpy leaves the staged waveforms dirty in the cores' caches (and reads the destination lines first): the DMA
 //                engine then has to snoop them out -- measured on the int16 plug-in call: H2D chunks at 27-39 GB/s instead of 52.
 void cvt_f64_f32(const double* s, float* d, long long n);
+bool cvt_f64_pcm16(const double* s, short* d, long long n);     // false: a sample is not k / 32768 with an int16 k; d may be null (probe)
 void zero_stream(void* dst, long long n);
 void copy_stream(const void* src, void* dst, long long n);
 int host_isa();          // 0 SSE2, 1 AVX-512F
@@ -55,6 +57,10 @@ inline void run_task(const Task& t)
         case 1:
             cvt_f64_f32(static_cast<const double*>(t.src), static_cast<float*>(t.dst), t.n);
             if (t.tail_zero > 0) memset(static_cast<float*>(t.dst) + t.n, 0, (size_t)t.tail_zero);
+            break;
+        case 3:
+            if (!cvt_f64_pcm16(static_cast<const double*>(t.src), static_cast<short*>(t.dst), t.n)) t.job->flag.store(1);
+            if (t.tail_zero > 0) memset(static_cast<short*>(t.dst) + t.n, 0, (size_t)t.tail_zero);
             break;
         default: zero_stream(t.dst, t.n); break;
     }
@@ -128,7 +134,7 @@ struct b200fe_host_pool {
         return ticket;
     }
     // The waiting thread helps: it drains queued tasks (of any job, FIFO) until its own job is complete.
-    int wait(long long ticket)
+    int wait(long long ticket, int* flag = nullptr)
     {
         std::shared_ptr<b200fe_host::Job> job;
         {
@@ -149,6 +155,7 @@ struct b200fe_host_pool {
             std::unique_lock<std::mutex> g(job->m);
             job->cv.wait(g, [&] { return job->done.load(); });
         }
+        if (flag) *flag = job->flag.load();
         return 0;
     }
 };

@@ -108,6 +108,55 @@ __attribute__((target("avx512f"))) static void copy_avx512(const void* src, void
     if (i < n) memcpy(d + i, s + i, (size_t)(n - i));
 }
 
+// ---- float64 samples that hold 16-bit PCM values (k / 32768: what soundfile.read returns for PCM_16 files, R/lasr/data/reader.py:24)
+// -> the int16 k itself: half the staging and PCIe bytes of float32, bit-identical features ((float)k == float(x) * 2^15).  Returns
+// false as soon as the range holds a sample that is not such a value (the caller then repeats the batch as float32); d may be null
+// (probe only).
+static bool pcm16_sse2(const double* __restrict__ s, short* __restrict__ d, long long n)
+{
+    bool ok = true;
+    for (long long i = 0; i < n; ++i) {
+        const double v = s[i] * 32768.0;
+        const bool in = v >= -32768.0 && v <= 32767.0;                 // NaN fails both
+        const int k = in ? (int)__builtin_rint(v) : 0;
+        ok = ok && in && (double)k == v;
+        if (d) d[i] = (short)k;
+    }
+    return ok;
+}
+
+__attribute__((target("avx512f"))) static bool pcm16_avx512(const double* __restrict__ s, short* __restrict__ d, long long n)
+{
+    const __m512d sc = _mm512_set1_pd(32768.0), lo = _mm512_set1_pd(-32768.0), hi = _mm512_set1_pd(32767.0);
+    long long i = 0;
+    bool ok = true;
+    if (d) while (i < n && (reinterpret_cast<uintptr_t>(d + i) & 63) != 0) { ok = pcm16_sse2(s + i, d + i, 1) && ok; ++i; }
+    unsigned bad = 0;
+    for (; i + 32 <= n; i += 32) {
+        _mm_prefetch(reinterpret_cast<const char*>(s + i) + kPrefetch, _MM_HINT_T1);
+        _mm_prefetch(reinterpret_cast<const char*>(s + i) + kPrefetch + 64, _MM_HINT_T1);
+        _mm_prefetch(reinterpret_cast<const char*>(s + i) + kPrefetch + 128, _MM_HINT_T1);
+        _mm_prefetch(reinterpret_cast<const char*>(s + i) + kPrefetch + 192, _MM_HINT_T1);
+        __m256i k[4];
+        for (int j = 0; j < 4; ++j) {
+            const __m512d v = _mm512_mul_pd(_mm512_loadu_pd(s + i + 8 * j), sc);
+            k[j] = _mm512_cvtpd_epi32(v);                                                  // round to nearest even (MXCSR default)
+            const __mmask8 good = _mm512_cmp_pd_mask(_mm512_cvtepi32_pd(k[j]), v, _CMP_EQ_OQ) & _mm512_cmp_pd_mask(v, lo, _CMP_GE_OQ) &
+                                  _mm512_cmp_pd_mask(v, hi, _CMP_LE_OQ);
+            bad |= (unsigned)(unsigned char)~good;
+        }
+        if (d) {
+            const __m256i a = _mm512_cvtepi32_epi16(_mm512_inserti64x4(_mm512_castsi256_si512(k[0]), k[1], 1));
+            const __m256i b = _mm512_cvtepi32_epi16(_mm512_inserti64x4(_mm512_castsi256_si512(k[2]), k[3], 1));
+            _mm512_stream_si512(reinterpret_cast<__m512i*>(d + i), _mm512_inserti64x4(_mm512_castsi256_si512(a), b, 1));
+        }
+    }
+    if (d) _mm_sfence();
+    ok = ok && bad == 0;
+    if (i < n) ok = pcm16_sse2(s + i, d ? d + i : nullptr, n - i) && ok;
+    return ok;
+}
+
 // ---- dispatch -----------------------------------------------------------------------------------------------------------------
 typedef void (*cvt_fn)(const double*, float*, long long);
 typedef void (*zero_fn)(void*, long long);
@@ -127,6 +176,9 @@ static const cvt_fn g_cvt = g_isa ? cvt_f64_f32_avx512 : cvt_f64_f32_sse2;
 static const zero_fn g_zero = g_isa ? zero_avx512 : zero_sse2;
 static const copy_fn g_copy = g_isa ? copy_avx512 : copy_sse2;
 
+typedef bool (*pcm_fn)(const double*, short*, long long);
+static const pcm_fn g_pcm = g_isa ? pcm16_avx512 : pcm16_sse2;
+bool cvt_f64_pcm16(const double* s, short* d, long long n) { return g_pcm(s, d, n); }
 int host_isa() { return g_isa; }
 void cvt_f64_f32(const double* s, float* d, long long n) { g_cvt(s, d, n); }
 void zero_stream(void* dst, long long n) { g_zero(dst, n); }

@@ -117,6 +117,13 @@ class HostPipeline:
         self.d2h_mode = os.environ.get("B200FE_D2H_MODE", "kernel")       # + "dma_block": one DMA per group over the padded block (padding rows included)
         self.taper = os.environ.get("B200FE_TAPER", "1") != "0"
         self.head_taper = os.environ.get("B200FE_HEAD_TAPER", "1") != "0"       # measured: float64 call -0.8 %, int16 call -4..7 % (profiles/r03_host_simd.txt)
+        # float64 lists that HOLD 16-bit PCM values (soundfile.read of PCM_16 files, the reference's reader) go up as int16: half the
+        # staging and PCIe bytes, bit-identical features.  A cheap probe decides per batch; a batch that fails the full check inside
+        # the packing is repeated as float32 and the next `_pcm16_backoff` calls skip the attempt.
+        self.pcm16_auto = os.environ.get("B200FE_PCM16_AUTO", "1") != "0"
+        self._pcm16_skip = 0
+        self._pcm16_backoff = 16
+        self.pcm16_batches = 0              # batches that went up as int16 through the automatic path
         self._fast_ptrs = None              # data pointers read by the library from the ndarray objects (verified on first use)
         self.trace = None                   # set to [] to collect (label, perf_counter) stamps of every call (tools/pipe_trace.py)
 
@@ -162,7 +169,7 @@ class HostPipeline:
         return np.array([a.__array_interface__["data"][0] for a in arrs], dtype=np.uint64)
 
     # ------------------------------------------------------------------------------------------------------------
-    def submit(self, wavs, to_host=True):
+    def submit(self, wavs, to_host=True, _allow_pcm16=True):
         """Starts one batch; returns a handle for ``result``.  Packing (host threads) is complete when this returns,
         the copies and kernels are queued on the device."""
         fe, lib, dev = self.fe, self.lib, self.dev
@@ -187,10 +194,19 @@ class HostPipeline:
             raise ValueError("expected mono 1-D waveforms (run 'avgchannel' first, datatrans.py:10-14)")
         arrs = [a if a.flags.c_contiguous else np.ascontiguousarray(a) for a in arrs]
         code = _SRC_CODE[dt]
-        ddt = _DST_TORCH[code]
-        esz = 2 if code == 1 else 4
-        al = 16 // esz
         lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=B)
+        ptrs = self._data_pointers(arrs)
+        pcm_try = False
+        if code == 2 and self.pcm16_auto and _allow_pcm16 and self.resampler is None and self.speed is None:
+            if self._pcm16_skip > 0:
+                self._pcm16_skip -= 1
+            else:
+                pcm_try = lib.b200fe_host_pcm16_probe(C.c_void_p(ptrs.ctypes.data), C.c_void_p(lens.ctypes.data), B, 8, 64) == 1
+        if pcm_try:
+            code = 3                        # float64 holding PCM16 values -> int16 staging (checked while it is packed)
+        ddt = torch.int16 if code == 3 else _DST_TORCH[code]
+        esz = 2 if code in (1, 3) else 4
+        al = 16 // esz
         lens_eff, ratios = lens, None
         if self.resampler is not None or self.speed is not None:
             if code == 1:
@@ -248,7 +264,6 @@ class HostPipeline:
                 acc = 0
         if bounds[-1] != B:
             bounds.append(B)
-        ptrs = self._data_pointers(arrs)
         if self._comp_done[si] is not None:
             s_in.wait_event(self._comp_done[si])       # kernels of the call that last read this device staging buffer
         while len(self._events) < len(bounds) - 1:
@@ -313,8 +328,16 @@ class HostPipeline:
             main.wait_event(self._out_done[so])        # D2H of the call that last used this device feature slot
         self.d2h_bytes = 0
         self._stamp("prepared")
+        pcm_failed = False
+        flag = C.c_int(0)
         for g, ((b0, b1), tk) in enumerate(zip(zip(bounds[:-1], bounds[1:]), tickets)):
-            _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")      # packed, DMA issued, event recorded
+            if pcm_try:
+                _lib.check(lib.b200fe_host_wait_flag(self.pool, tk, C.byref(flag)), "b200fe_host_wait_flag")
+                pcm_failed = pcm_failed or flag.value != 0
+                if pcm_failed:
+                    continue                # a sample was not a PCM16 value: nothing more is launched, the batch is repeated as float32 below
+            else:
+                _lib.check(lib.b200fe_host_wait(self.pool, tk), "b200fe_host_wait")      # packed, DMA issued, event recorded
             self._stamp("packed")
             self._dev_stamp("h2d %d done" % g, s_in)
             main.wait_event(self._events[g])
@@ -377,6 +400,14 @@ class HostPipeline:
             done.record(s_out)
             self._out_done[so] = done
             tab_dev.record_stream(s_out)
+        if pcm_failed:
+            # the events above cover whatever the abandoned attempt queued; its ring slots are simply overwritten by later calls
+            if zero_ticket:
+                _lib.check(lib.b200fe_host_wait(self.pool, zero_ticket), "b200fe_host_wait")
+            self._pcm16_skip = self._pcm16_backoff
+            return self.submit(wavs, to_host, _allow_pcm16=False)
+        if pcm_try:
+            self.pcm16_batches += 1
         return dict(to_host=to_host, done=done, zero=zero_ticket, hfeats=hfeats, hlen=hlen, dfeats=dfeats, dlen=dlen, keep=arrs)
 
     def result(self, h):

@@ -80,6 +80,47 @@ def test_collate_input_types_and_prefetch(lasr_b200):
         col([np.zeros((100, 2, 2))])
 
 
+def test_float64_lists_that_hold_pcm16_values_go_up_as_int16(lasr_b200):
+    """The reference's reader hands over float64 = int16 / 32768 (soundfile.read of PCM_16 files, reader.py:24).  Such lists are
+    staged and uploaded as int16 (half the bytes) with BIT-IDENTICAL features; a batch with one sample off the PCM grid -- where the
+    probe does not look -- is caught by the check inside the packing and repeated as float32; float lists never take the path."""
+    rng = np.random.default_rng(21)
+    lens = (16000, 48123, 9000, 70001, 33333)
+    pcm = [np.round(np.clip(rng.normal(0, 0.1, n), -1, 1) * 32767).astype(np.int16) for n in lens]
+    f64 = [k.astype(np.float64) / 32768.0 for k in pcm]
+    for kw in (dict(cmvn="utt_meanvar"), dict(peak_norm=True)):
+        auto = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, **kw)
+        plain = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=True, **kw)
+        plain.pipeline.pcm16_auto = False
+        a, b = auto(f64), plain(f64)
+        assert auto.pipeline.pcm16_batches == 1 and plain.pipeline.pcm16_batches == 0
+        assert auto.pipeline.h2d_bytes * 2 <= plain.pipeline.h2d_bytes + 64
+        assert torch.equal(a["wav_len"], b["wav_len"]) and torch.equal(a["wav_array"], b["wav_array"])
+        # the same as int16 lists
+        c = plain(pcm)
+        assert torch.equal(a["wav_array"], c["wav_array"])
+        # one sample off the grid in the middle of an utterance: caught while packing, repeated as float32, then a pause
+        bad = [w.copy() for w in f64]
+        bad[3][35000] += 1e-7                # (the probe's windows of this utterance start at 0, 9991, ..., 29973, 39964, ...)
+        a2, b2 = auto(bad), plain(bad)
+        assert auto.pipeline.pcm16_batches == 1 and auto.pipeline._pcm16_skip == auto.pipeline._pcm16_backoff
+        assert torch.equal(a2["wav_array"], b2["wav_array"]) and torch.equal(a2["wav_len"], b2["wav_len"])
+        a3 = auto(f64)                       # inside the pause: float32 path, same features
+        assert auto.pipeline.pcm16_batches == 1 and torch.equal(a3["wav_array"], b["wav_array"])
+        auto.pipeline._pcm16_skip = 0
+        # float data: the probe says no, nothing is attempted
+        flt = [np.clip(rng.normal(0, 0.1, n), -1, 1) for n in lens]
+        a4, b4 = auto(flt), plain(flt)
+        assert auto.pipeline.pcm16_batches == 1 and auto.pipeline._pcm16_skip == 0
+        assert torch.equal(a4["wav_array"], b4["wav_array"])
+        # features stay on the device / prefetch
+        dev_col = lasr_b200.lasr_plugin.B200Collate(DEV, to_host=False, **kw)
+        d = dev_col(f64)
+        torch.cuda.synchronize()
+        ref = plain(f64)                     # (b's ring slot has been handed out again by now)
+        assert dev_col.pipeline.pcm16_batches == 1 and torch.equal(d["wav_array"].cpu(), ref["wav_array"])
+
+
 def test_zero_masks_with_utterance_cmvn_are_applied_after_normalisation(lasr_b200):
     """specaug + replace_with_zero + utterance CMVN: statistics over the UNMASKED features, zeros written after the
     normalisation (CMVN first, masks second -- the order of the mean-fill and time-warp paths)."""

@@ -115,6 +115,49 @@ def test_ndarray_data_pointers(pool):
     assert lib.b200fe_host_ndarray_data(ids.ctypes.data, len(arrs), out.ctypes.data, 12) != 0
 
 
+def test_pack_float64_that_holds_pcm16_values(pool):
+    """src_dtype 3: float64 samples k / 32768 (soundfile.read of PCM_16 files) are staged as the int16 k; one sample that is not such
+    a value raises the job's flag; the probe looks at windows spread over every utterance."""
+    lib, h = pool
+    rng = np.random.default_rng(3)
+    lens = np.array([1, 31, 32, 33, 401, 70001, 0, 12345], dtype=np.int64)
+    ks = [rng.integers(-32768, 32768, n).astype(np.int16) for n in lens]
+    ks[4][:4] = [-32768, 32767, 0, -1]
+    wavs = [k.astype(np.float64) / 32768.0 for k in ks]
+    wavs[3][5], ks[3][5] = -0.0, 0                       # minus zero is the PCM value 0
+    offs = np.zeros(len(lens), dtype=np.int64)
+    np.cumsum((lens[:-1] + 7) // 8 * 8, out=offs[1:])
+    total = int(offs[-1] + (lens[-1] + 7) // 8 * 8)
+    dst = _aligned(total, np.int16)
+
+    def run(ws):
+        dst[:] = 99
+        ptrs = (C.c_void_p * len(ws))(*[max(w.ctypes.data, 1) for w in ws])
+        assert lib.b200fe_host_pcm16_probe(ptrs, lens.ctypes.data, len(ws), 8, 64) in (0, 1)
+        tk = lib.b200fe_host_pack_begin(h, ptrs, lens.ctypes.data, len(ws), 3, dst.ctypes.data, offs.ctypes.data, total)
+        assert tk > 0, lib.b200fe_last_error()
+        flag = C.c_int(-1)
+        assert lib.b200fe_host_wait_flag(h, tk, C.byref(flag)) == 0
+        return flag.value, lib.b200fe_host_pcm16_probe(ptrs, lens.ctypes.data, len(ws), 8, 64)
+
+    flag, probe = run(wavs)
+    assert flag == 0 and probe == 1
+    for k, o, n in zip(ks, offs, lens):
+        assert np.array_equal(dst[o:o + n], k)
+        assert np.all(dst[o + n:o + (n + 7) // 8 * 8] == 0)
+    # values that are not PCM16: off the grid, out of range (+1.0 = 32768 / 32768), NaN, infinity -- in the middle of a long utterance,
+    # where the probe's windows do not look, and at its start, where they do
+    for bad in (0.1, 1.0, -1.0000305, np.nan, np.inf, 2.0 ** -16):
+        w2 = [w.copy() for w in wavs]
+        w2[5][33333] = bad
+        flag, probe = run(w2)
+        assert flag == 1 and probe == 1, bad
+        w2[5][3] = bad
+        flag, probe = run(w2)
+        assert flag == 1 and probe == 0, bad
+    assert lib.b200fe_host_pcm16_probe(None, lens.ctypes.data, 2, 8, 64) < 0
+
+
 def test_pack_argument_errors(pool):
     lib, h = pool
     w = np.zeros(10)
