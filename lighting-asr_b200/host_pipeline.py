@@ -405,6 +405,9 @@ class HostPipeline:
             if zero_ticket:
                 _lib.check(lib.b200fe_host_wait(self.pool, zero_ticket), "b200fe_host_wait")
             self._pcm16_skip = self._pcm16_backoff
+            # the repeat takes the SAME ring slots (its work is queued behind the abandoned attempt's on the same streams and its
+            # staging buffers are the float32 ones): a batch handed out earlier stays valid for `ring` further CALLS, as promised
+            self._turn -= 1
             return self.submit(wavs, to_host, _allow_pcm16=False)
         if pcm_try:
             self.pcm16_batches += 1

@@ -102,7 +102,9 @@ def test_float64_lists_that_hold_pcm16_values_go_up_as_int16(lasr_b200):
         # one sample off the grid in the middle of an utterance: caught while packing, repeated as float32, then a pause
         bad = [w.copy() for w in f64]
         bad[3][35000] += 1e-7                # (the probe's windows of this utterance start at 0, 9991, ..., 29973, 39964, ...)
+        turn = auto.pipeline._turn
         a2, b2 = auto(bad), plain(bad)
+        assert auto.pipeline._turn == turn + 1                  # the repeat reuses the abandoned attempt's ring slots
         assert auto.pipeline.pcm16_batches == 1 and auto.pipeline._pcm16_skip == auto.pipeline._pcm16_backoff
         assert torch.equal(a2["wav_array"], b2["wav_array"]) and torch.equal(a2["wav_len"], b2["wav_len"])
         a3 = auto(f64)                       # inside the pause: float32 path, same features
