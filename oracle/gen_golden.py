@@ -136,7 +136,7 @@ def main():
     print("wrote", os.listdir(OUT))
 
 
-if __name__ == "__main__" and "--batching" not in sys.argv and "--cmvn" not in sys.argv:
+if __name__ == "__main__" and not any(f in sys.argv for f in ("--batching", "--cmvn", "--options")):
     main()
 
 
@@ -222,3 +222,39 @@ def gen_cmvn():
 
 if __name__ == "__main__" and "--cmvn" in sys.argv:
     gen_cmvn()
+
+
+OPTION_SETS = {
+    "sf8000": dict(sample_frequency=8000.0),                                   # BASELINE config 5: the SwitchBoard shape (200 / 80 samples, 256-point FFT)
+    "mel40": dict(num_mel_bins=40),
+    "win20": dict(frame_length=20.0),
+    "magnitude": dict(use_power=False),
+    "linear": dict(use_log_fbank=False),
+    "hamming_nodc": dict(window_type="hamming", remove_dc_offset=False),
+    "pre0_hf": dict(preemphasis_coefficient=0.0, high_freq=-200.0, low_freq=60.0),
+    "bit24": dict(audio_bit=24),
+    "sf8000_mel40_shift5": dict(sample_frequency=8000.0, num_mel_bins=40, frame_shift=5.0),
+}
+
+
+def gen_options():
+    """fbank goldens for the other option sets of the reference's WavToKaldiFbank (datatrans.py:43-71), the 8 kHz family of BASELINE
+    config 5 among them: the UNMODIFIED reference function called with keyword arguments, as a config.yaml `kwargs` block would."""
+    import torch
+    import torchaudio
+    dt, _, _ = import_reference()
+    rng = np.random.default_rng(4321)
+    out = {}
+    for i, n in enumerate((4000, 9001)):
+        out["wav_%d" % i] = np.clip(rng.normal(0, 0.1, n), -1, 1) if i == 0 else np.round(rng.uniform(-0.4, 0.4, n) * 32768.0) / 32768.0
+    for name, kw in OPTION_SETS.items():
+        for i in range(2):
+            out["%s_%d" % (name, i)] = dt.WavToKaldiFbank(out["wav_%d" % i], **kw)
+    out["names"] = np.array(sorted(OPTION_SETS))
+    out["versions"] = np.array([torch.__version__, torchaudio.__version__, np.__version__])
+    np.savez_compressed(os.path.join(OUT, "fbank_options_reference.npz"), **out)
+    print("wrote fbank_options_reference.npz")
+
+
+if __name__ == "__main__" and "--options" in sys.argv:
+    gen_options()

@@ -142,6 +142,37 @@ def test_other_option_sets(lasr_b200):
         assert below <= 1e-3 * g.size, kw
 
 
+def test_option_sets_against_reference_goldens(lasr_b200):
+    """The CUDA path against tests/golden/fbank_options_reference.npz: the UNMODIFIED reference's WavToKaldiFbank called with the
+    keyword arguments a config.yaml would carry (8 kHz family, 40 bins, 20 ms window, magnitude / linear spectra, Hamming window
+    without DC removal, no pre-emphasis with moved band edges, 24-bit scaling, 5 ms shift at 8 kHz)."""
+    import os
+    from oracle.gen_golden import OPTION_SETS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fbank_options_reference.npz"))
+    for name, kw in OPTION_SETS.items():
+        fe = lasr_b200.GpuFbankFrontend(**kw)
+        wavs = [g["wav_0"], g["wav_1"]]
+        wav, n = _pad_batch(wavs, "cuda:0")
+        feats, flen = fe(wav, n)
+        f = feats.cpu().numpy()
+        for i, w in enumerate(wavs):
+            ref = g["%s_%d" % (name, i)]
+            assert int(flen[i]) == ref.shape[0] and f.shape[2] == ref.shape[1], name
+            got = f[i, : ref.shape[0]]
+            okw = {k: v for k, v in kw.items() if k != "audio_bit"}
+            x = w.astype(np.float32) * np.float32(2 ** (kw.get("audio_bit", 16) - 1))
+            ref64 = kaldi_fbank.fbank(x, dtype=np.float64, **okw)
+            okw.update(use_log_fbank=False, use_power=True)
+            lin64 = kaldi_fbank.fbank(x, dtype=np.float64, **okw)
+            if kw.get("use_log_fbank", True):
+                hard, soft, below = fbank_parity(got, ref, ref64, lin64)
+                assert hard == 0 and soft == 0 and below <= 1e-3 * got.size, name
+            else:                       # linear energies: the tolerance plus the fp32 FFT floor of the frame
+                band = 1e-5 + 1e-4 * np.abs(ref) + 1e-7 * np.abs(ref).sum(axis=1, keepdims=True)
+                assert np.all(np.abs(got - ref) <= band), name
+            assert np.all(f[i, ref.shape[0]:] == 0), name
+
+
 def test_packed_input_and_host_pipeline_match_padded(lasr_b200):
     """The packed (ragged) device layout and the pipelined host API give bit-identical features."""
     rng = np.random.default_rng(7)

@@ -134,6 +134,23 @@ def test_cmvn_definition():
     assert np.allclose(y.mean(0), 0, atol=1e-5) and np.allclose(y.std(0), 1, atol=1e-4)
 
 
+def test_fbank_option_sets_match_reference_fixture():
+    """The other option sets of WavToKaldiFbank (datatrans.py:43-71; the 8 kHz family of BASELINE config 5 among them) against the
+    UNMODIFIED reference called with keyword arguments (oracle/gen_golden.py --options)."""
+    from oracle.gen_golden import OPTION_SETS
+    g = np.load(os.path.join(GOLD, "fbank_options_reference.npz"))
+    assert sorted(OPTION_SETS) == [str(n) for n in g["names"]]
+    for name, kw in OPTION_SETS.items():
+        for i in range(2):
+            ref = g["%s_%d" % (name, i)]
+            got = lasr_frontend.wav_to_kaldi_fbank(g["wav_%d" % i], **kw)
+            assert got.shape == ref.shape and got.dtype == np.float32
+            band = 1e-5 + 1e-4 * np.abs(ref)
+            if not kw.get("use_log_fbank", True):
+                band = band + 1e-7 * np.abs(ref).sum(axis=1, keepdims=True)      # linear energies: the fp32 FFT floor of the frame
+            assert np.all(np.abs(got - ref) <= band), (name, i)
+
+
 def test_cmvn_pinned_to_torchaudio_sliding_window_cmn(fb):
     """Row A11: utterance CMVN (mean / mean + variance), the Kaldi statistics layout and global CMVN from accumulated statistics
     against torchaudio.functional.sliding_window_cmn (torchaudio's port of Kaldi's apply-cmvn-sliding) with a window that covers
